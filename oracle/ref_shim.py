@@ -1,0 +1,56 @@
+"""Import the UNMODIFIED reference ``layers`` package from /root/reference (build container only).
+
+TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box; nothing that runs
+there imports this module.  The two stubbed modules are text-front-end dependencies the
+acoustic path never calls.
+"""
+import os
+import sys
+import types
+
+REF_DIR = os.environ.get("ES_REFERENCE_DIR", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REF_DIR, "layers", "networks.py"))
+
+
+def import_reference_layers():
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REF_DIR}")
+    for n in ("unidecode", "inflect"):
+        if n not in sys.modules:
+            sys.modules[n] = types.ModuleType(n)
+    sys.modules["unidecode"].unidecode = lambda s: s
+    sys.modules["inflect"].engine = lambda: types.SimpleNamespace(number_to_words=lambda *a, **k: "")
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import layers  # noqa: E402  (the reference package)
+    return layers
+
+
+def build_reference_model(cfg, state):
+    """Reference Phoneme2Mel with our weights loaded strict=True (proves state-dict compatibility)."""
+    import torch
+    layers = import_reference_layers()
+    enc = layers.PhonemeEncoder(pitch_stats=cfg.pitch_stats, energy_stats=cfg.energy_stats,
+                                depth=cfg.depth, reduction=cfg.reduction, head=cfg.head,
+                                embed_dim=cfg.embed_dim, kernel_size=cfg.kernel_size,
+                                expansion=cfg.expansion)
+    dec = layers.MelDecoder(dim=cfg.embed_dim // cfg.reduction, kernel_size=cfg.decoder_kernel_size,
+                            n_blocks=cfg.n_blocks, block_depth=cfg.block_depth)
+    m = layers.Phoneme2Mel(enc, dec).eval()
+    m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in state.items()}, strict=True)
+    return m
+
+
+def run_reference(model, batch, train):
+    """batch: dict of numpy arrays in the reference layout -> dict of numpy outputs."""
+    import torch
+    tb = {k: torch.from_numpy(v.copy()) for k, v in batch.items()}
+    with torch.no_grad():
+        out = model(tb, train=train)
+    if not train:
+        mel, mel_len, dur = out
+        return {"mel": mel.numpy(), "mel_len": mel_len.numpy(), "duration": dur.numpy()}
+    return {k: (v.numpy() if v is not None else None) for k, v in out.items()}
