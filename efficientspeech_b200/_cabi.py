@@ -1,0 +1,103 @@
+"""ctypes binding of libes_b200.so (include/es_b200.h).  The structures mirror the header field
+for field; tests/test_cabi_cpu.py parses the header and checks that they still agree."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+from . import build as _build
+
+ES_ABI_VERSION = 3
+ES_MAX_ENC_BLOCKS = 2
+ES_MAX_DEC_LAYERS = 24
+ES_MAX_DEC_BLOCKS = 8
+
+_fp = C.c_void_p      # device pointers travel as integers
+
+
+class es_config_t(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "embed_dim", "dim", "kernel_size", "head", "expansion", "n_blocks", "block_depth",
+        "decoder_kernel_size", "n_mel", "n_symbols")]
+
+
+class es_enc_block_w_t(C.Structure):
+    _fields_ = [(n, _fp) for n in (
+        "merge_w", "qkv_w", "proj_w", "proj_b", "ln1_g", "ln1_b", "ffn1_w", "ffn1_tapb", "ffn1_b",
+        "ffn2_w", "ffn2_b", "ln2_g", "ln2_b")]
+
+
+class es_predictor_w_t(C.Structure):
+    _fields_ = [(n, _fp) for n in (
+        "conv1_w", "conv1_b", "ln1_g", "ln1_b", "conv2_w", "conv2_b", "ln2_g", "ln2_b", "lin_w", "lin_b",
+        "bins", "table")]
+
+
+class es_dec_layer_w_t(C.Structure):
+    _fields_ = [(n, _fp) for n in ("dw_w", "dw_b", "pw_w", "pw_b", "ln_g", "ln_b", "pw_w_h16")]
+
+
+class es_weights_t(C.Structure):
+    _fields_ = [
+        ("enc", es_enc_block_w_t * ES_MAX_ENC_BLOCKS),
+        ("fuse_a0", _fp), ("fuse_g", _fp), ("fuse_gb", _fp), ("fuse_c", _fp),
+        ("pitch", es_predictor_w_t), ("energy", es_predictor_w_t), ("duration", es_predictor_w_t),
+        ("dproj_w", _fp), ("dproj_b", _fp), ("dproj_ln_g", _fp), ("dproj_ln_b", _fp),
+        ("dec", es_dec_layer_w_t * ES_MAX_DEC_LAYERS),
+        ("blk_ln_g", _fp * ES_MAX_DEC_BLOCKS), ("blk_ln_b", _fp * ES_MAX_DEC_BLOCKS),
+        ("mel_w", _fp), ("mel_b", _fp),
+    ]
+
+
+# name -> (restype, argtypes); exactly the functions include/es_b200.h declares
+_i, _sz, _vp = C.c_int, C.c_size_t, C.c_void_p
+PROTOTYPES = {
+    "es_abi_version": (_i, []),
+    "es_last_error": (C.c_char_p, []),
+    "es_model_create": (_i, [C.POINTER(es_config_t), C.POINTER(es_weights_t), C.POINTER(_vp)]),
+    "es_model_destroy": (None, [_vp]),
+    "es_model_set_tensor_core": (_i, [_vp, _i]),
+    "es_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "es_encoder_forward": (_i, [_vp, _vp, _i, _i] + [_vp] * 12 + [_vp, _sz]),
+    "es_length_regulate": (_i, [_vp, _vp, _i, _i, _i] + [_vp] * 6),
+    "es_decoder_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _sz]),
+    "es_decoder_forward_gathered": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz]),
+    "es_launch_count": (C.c_uint64, []),
+    "es_selftest_umma_gemm": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen the in-tree library.  There is no fallback: a missing/unloadable library raises."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.isfile(path):
+        if not build_if_missing:
+            raise RuntimeError(f"{path} is missing: run `python -m efficientspeech_b200.build` "
+                               "(there is no CPU/PyTorch fallback for the acoustic path)")
+        _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.es_abi_version()
+    if got != ES_ABI_VERSION:
+        raise RuntimeError(f"libes_b200.so ABI {got} != binding ABI {ES_ABI_VERSION}: rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().es_last_error()
+        raise RuntimeError("es_b200: " + (msg.decode() if msg else f"error {rc}"))

@@ -1,0 +1,313 @@
+// C ABI (include/es_b200.h): model handle, workspace planning and the kernel sequence of the
+// acoustic forward path.  Host code only; every kernel lives in the sibling .cu files.
+#include <math.h>
+#include <string.h>
+
+#include <new>
+
+#include "es_common.cuh"
+#include "es_kernels.cuh"
+
+namespace es {
+
+static thread_local std::string g_error;
+std::atomic<uint64_t> g_launches{0};
+void set_error(const std::string& msg) { g_error = msg; }
+
+}  // namespace es
+
+struct es_model {
+    es_config_t cfg;
+    es_weights_t w;
+    int use_tensor_core;
+    // derived geometry
+    int d, C[2], H[2], k[2], hC[2], dx4, dx2, n_layers;
+};
+
+namespace {
+
+using namespace es;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace; with base == nullptr it only measures.
+struct Arena {
+    char* base;
+    size_t off = 0;
+    explicit Arena(void* b) : base(static_cast<char*>(b)) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = align_up(off, 256);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+inline int enc_n1(const es_model* m, int N) {
+    const int k1 = m->k[1];
+    return (N + 2 * (k1 / 2) - k1) / 2 + 1;           // Conv1d(stride 2) output length (networks.py:40)
+}
+
+struct EncBufs {
+    float *x0, *qkv, *att, *x1, *h, *feat0, *xm1, *feat1, *fused, *y1, *dur_feat;
+    uint8_t* mask1;
+};
+
+EncBufs plan_encoder(const es_model* m, Arena& a, int B, int N) {
+    EncBufs e;
+    const size_t n1 = enc_n1(m, N);
+    const size_t r0 = (size_t)B * N, r1 = (size_t)B * n1;
+    auto mx = [](size_t x, size_t y) { return x > y ? x : y; };
+    e.x0 = a.take<float>(r0 * m->C[0]);
+    e.qkv = a.take<float>(mx(r0 * 3 * m->H[0] * m->C[0], r1 * 3 * m->H[1] * m->C[1]));
+    e.att = a.take<float>(mx(r0 * m->H[0] * m->C[0], r1 * m->H[1] * m->C[1]));
+    e.x1 = a.take<float>(mx(r0 * m->C[0], r1 * m->C[1]));
+    e.h = a.take<float>(mx(r0 * m->hC[0], r1 * m->hC[1]));
+    e.feat0 = a.take<float>(r0 * m->C[0]);
+    e.xm1 = a.take<float>(r1 * m->C[1]);
+    e.feat1 = a.take<float>(r1 * m->C[1]);
+    e.fused = a.take<float>(r0 * m->d);
+    e.y1 = a.take<float>(r0 * m->d);
+    e.dur_feat = a.take<float>(r0 * m->d);
+    e.mask1 = a.take<uint8_t>(r1);
+    return e;
+}
+
+struct DecBufs {
+    float* buf[3];
+};
+
+DecBufs plan_decoder(const es_model* m, Arena& a, int B, int T) {
+    DecBufs d;
+    for (int i = 0; i < 3; ++i) d.buf[i] = a.take<float>((size_t)B * T * m->dx2);
+    return d;
+}
+
+RowGemmParams base_params(int B, int n_in, int n_out, int K, int Nout, const float* A, int lda,
+                          const float* W, float* Y, int ldy) {
+    RowGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.n_in = n_in; p.n_out = n_out; p.K = K; p.Nout = Nout;
+    p.ldw = (Nout + 31) / 32 * 32;
+    p.taps = 1; p.stride = 1; p.pad = 0; p.mode = ROW_PLAIN;
+    p.A = A; p.lda = lda; p.W = W; p.Y = Y; p.ldy = ldy;
+    return p;
+}
+
+// One encoder block after its merge conv (networks.py:72-85).
+int encoder_block(const es_model* m, int i, int B, int n, const float* x_in, const uint8_t* mask,
+                  const EncBufs& e, float* feat_out, cudaStream_t s) {
+    const es_enc_block_w_t& w = m->w.enc[i];
+    const int C = m->C[i], H = m->H[i], hC = m->hC[i];
+    // qkv = x Wqkv^T                                                            blocks.py:45
+    RowGemmParams p = base_params(B, n, n, C, 3 * H * C, x_in, C, w.qkv_w, e.qkv, 3 * H * C);
+    if (launch_rowgemm(p, s)) return 1;
+    // softmax(QK^T scale) V, all keys (mask never applied)                         blocks.py:49-65
+    const float scale = 1.0f / sqrtf((float)(C / H));
+    if (launch_attention(e.qkv, e.att, B, n, C, H, scale, s)) return 1;
+    // x1 = mask(LN1(proj(att) + x))                                                blocks.py:66, networks.py:73-75
+    p = base_params(B, n, n, H * C, C, e.att, H * C, w.proj_w, e.x1, C);
+    p.bias = w.proj_b; p.res1 = x_in; p.ldr1 = C; p.ln_g = w.ln1_g; p.ln_b = w.ln1_b; p.row_mask = mask;
+    if (launch_rowgemm(p, s)) return 1;
+    // h = GELU(conv3(mlp1(x1)))  with mlp1 folded into the conv taps               blocks.py:23-27
+    p = base_params(B, n, n, C, hC, e.x1, C, w.ffn1_w, e.h, hC);
+    p.taps = 3; p.pad = 1; p.bias = w.ffn1_b; p.tap_bias = w.ffn1_tapb; p.act1 = ACT_GELU;
+    if (launch_rowgemm(p, s)) return 1;
+    // feat = mask(LN2(mlp2(h) + x1))                                               blocks.py:28, networks.py:80-83
+    p = base_params(B, n, n, hC, C, e.h, hC, w.ffn2_w, feat_out, C);
+    p.bias = w.ffn2_b; p.res1 = e.x1; p.ldr1 = C; p.ln_g = w.ln2_g; p.ln_b = w.ln2_b; p.row_mask = mask;
+    return launch_rowgemm(p, s);
+}
+
+// AcousticDecoder.forward (networks.py:151-165)
+int predictor(const es_model* m, const es_predictor_w_t& w, int B, int N, const float* fused, float* y1,
+              float* pred, bool is_duration, float* feat_out, cudaStream_t s) {
+    const int d = m->d;
+    RowGemmParams p = base_params(B, N, N, d, d, fused, d, w.conv1_w, y1, d);
+    p.taps = 3; p.pad = 1; p.bias = w.conv1_b; p.act1 = ACT_RELU;
+    p.ln_g = w.ln1_g; p.ln_b = w.ln1_b; p.act2 = ACT_RELU;
+    if (launch_rowgemm(p, s)) return 1;
+    p = base_params(B, N, N, d, d, y1, d, w.conv2_w, is_duration ? feat_out : nullptr, d);
+    p.taps = 3; p.pad = 1; p.bias = w.conv2_b; p.act1 = ACT_RELU;
+    p.dot_w = w.lin_w; p.dot_b = w.lin_b; p.dot_out = pred; p.dot_relu = is_duration ? 1 : 0;
+    if (is_duration) { p.ln_g = w.ln2_g; p.ln_b = w.ln2_b; }   // norm2 output is only consumed for duration
+    return launch_rowgemm(p, s);
+}
+
+int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, const int* zero_from,
+                   float* mel, cudaStream_t s);
+
+}  // namespace
+
+extern "C" {
+
+int es_abi_version(void) { return ES_ABI_VERSION; }
+const char* es_last_error(void) { return es::g_error.c_str(); }
+uint64_t es_launch_count(void) { return es::g_launches.load(); }
+
+int es_model_create(const es_config_t* cfg, const es_weights_t* w, es_model_t** out) {
+    ES_CHECK(cfg && w && out, "null argument");
+    ES_CHECK(cfg->dim % 32 == 0 && cfg->dim >= 32 && cfg->dim <= 128, "dim must be 32..128, multiple of 32");
+    ES_CHECK(cfg->kernel_size == 3 || cfg->kernel_size == 5, "kernel_size must be 3 or 5");
+    ES_CHECK(cfg->n_blocks >= 1 && cfg->n_blocks <= ES_MAX_DEC_BLOCKS, "n_blocks out of range");
+    ES_CHECK(cfg->n_blocks * cfg->block_depth <= ES_MAX_DEC_LAYERS && cfg->block_depth >= 1, "too many decoder layers");
+    ES_CHECK(cfg->decoder_kernel_size % 2 == 1 && cfg->decoder_kernel_size <= ES_MAX_TAPS, "bad decoder kernel size");
+    ES_CHECK(cfg->n_mel >= 1 && cfg->n_mel <= 256, "n_mel out of range");
+    ES_CHECK(cfg->head >= 1 && cfg->expansion >= 1, "bad head/expansion");
+    es_model* m = new (std::nothrow) es_model;
+    ES_CHECK(m, "out of memory");
+    m->cfg = *cfg;
+    m->w = *w;
+    m->use_tensor_core = 1;
+    m->d = cfg->dim;
+    m->C[0] = cfg->dim; m->C[1] = 2 * cfg->dim;
+    m->H[0] = cfg->head; m->H[1] = 2 * cfg->head;
+    m->k[0] = cfg->kernel_size; m->k[1] = cfg->kernel_size - 2;
+    m->hC[0] = m->C[0] * cfg->expansion; m->hC[1] = m->C[1] * cfg->expansion;
+    m->dx4 = 4 * cfg->dim;
+    m->dx2 = m->dx4 < 256 ? m->dx4 : 256;
+    m->n_layers = cfg->n_blocks * cfg->block_depth;
+    *out = m;
+    return 0;
+}
+
+void es_model_destroy(es_model_t* m) { delete m; }
+
+int es_model_set_tensor_core(es_model_t* m, int enable) {
+    ES_CHECK(m, "null model");
+    m->use_tensor_core = enable ? 1 : 0;
+    return 0;
+}
+
+size_t es_workspace_bytes(const es_model_t* m, int B, int N, int T) {
+    if (!m || B <= 0) return 0;
+    Arena a(nullptr);
+    if (N > 0) plan_encoder(m, a, B, N);
+    if (T > 0) plan_decoder(m, a, B, T);
+    return align_up(a.off, 256) + 256;
+}
+
+int es_encoder_forward(es_model_t* m, void* stream, int B, int N,
+                       const int32_t* phoneme, const uint8_t* phoneme_mask,
+                       const float* pitch_tgt, const float* energy_tgt, const int32_t* dur_tgt,
+                       float* pitch_pred, float* energy_pred, float* dur_pred,
+                       float* fused4, int32_t* dur_int, int32_t* dur_cum, int32_t* mel_len,
+                       void* workspace, size_t workspace_bytes) {
+    ES_CHECK(m, "null model");
+    ES_CHECK(B >= 1 && B <= 65535 && N >= 2, "need 1 <= B <= 65535 and N >= 2 phonemes");
+    ES_CHECK(phoneme && pitch_pred && energy_pred && dur_pred && fused4 && dur_int && dur_cum && mel_len,
+             "null tensor");
+    ES_CHECK(workspace && workspace_bytes >= es_workspace_bytes(m, B, N, 0), "workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Arena a(reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256)));
+    EncBufs e = plan_encoder(m, a, B, N);
+    const int d = m->d, n1 = enc_n1(m, N);
+
+    // block 0: embedding + merge conv + 1x1 as k table gathers (networks.py:54,64-67)
+    if (launch_embed_merge(phoneme, m->w.enc[0].merge_w, e.x0, B, N, m->C[0], m->k[0], m->cfg.n_symbols, s)) return 1;
+    if (encoder_block(m, 0, B, N, e.x0, phoneme_mask, e, e.feat0, s)) return 1;
+    // block 1 merge: Conv1d(d,d,k-2,stride 2) . Conv1d(d,2d,1) folded (networks.py:64-67)
+    {
+        RowGemmParams p = base_params(B, N, n1, m->C[0], m->C[1], e.feat0, m->C[0], m->w.enc[1].merge_w, e.xm1, m->C[1]);
+        p.taps = m->k[1]; p.stride = 2; p.pad = m->k[1] / 2;
+        if (launch_rowgemm(p, s)) return 1;
+    }
+    const uint8_t* mask1 = nullptr;
+    if (phoneme_mask) {
+        // pool = round(N / n1), torch.round of an fp32 tensor: half-to-even (networks.py:69-70)
+        const int pool = (int)nearbyintf((float)((double)N / (double)n1));
+        if (launch_pool_mask(phoneme_mask, e.mask1, B, N, n1, pool, s)) return 1;
+        mask1 = e.mask1;
+    }
+    if (encoder_block(m, 1, B, n1, e.xm1, mask1, e, e.feat1, s)) return 1;
+    // fuse (networks.py:189-219)
+    if (launch_fuse(e.feat0, e.feat1, m->w.fuse_a0, m->w.fuse_g, m->w.fuse_gb, m->w.fuse_c, phoneme_mask,
+                    e.fused, B, N, n1, d, m->k[0], s)) return 1;
+    // predictors (networks.py:349,357,366)
+    if (predictor(m, m->w.pitch, B, N, e.fused, e.y1, pitch_pred, false, nullptr, s)) return 1;
+    if (predictor(m, m->w.energy, B, N, e.fused, e.y1, energy_pred, false, nullptr, s)) return 1;
+    if (predictor(m, m->w.duration, B, N, e.fused, e.y1, dur_pred, true, e.dur_feat, s)) return 1;
+    // variance embeddings, concat, duration rounding, integer scan (networks.py:349-384, 234, 255)
+    return launch_variance_scan(e.fused, e.dur_feat, pitch_pred, energy_pred, dur_pred, pitch_tgt, energy_tgt,
+                                dur_tgt, phoneme_mask, m->w.pitch, m->w.energy, fused4, dur_int, dur_cum,
+                                mel_len, B, N, d, s);
+}
+
+int es_length_regulate(es_model_t* m, void* stream, int B, int N, int T,
+                       const float* fused4, const int32_t* dur_cum, const uint8_t* phoneme_mask,
+                       float* features, uint8_t* frame_mask, int32_t* src) {
+    ES_CHECK(m, "null model");
+    ES_CHECK(B >= 1 && N >= 1 && T >= 0, "bad shape");
+    ES_CHECK(dur_cum && (fused4 || !features), "null tensor");
+    return launch_length_regulate(fused4, dur_cum, phoneme_mask, features, frame_mask, src, B, N, T, m->dx4,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int es_decoder_forward(es_model_t* m, void* stream, int B, int T, const float* features, float* mel,
+                       void* workspace, size_t workspace_bytes) {
+    ES_CHECK(m, "null model");
+    ES_CHECK(B >= 1 && B <= 65535 && T >= 1, "need 1 <= B <= 65535 and T >= 1 frames");
+    ES_CHECK(features && mel, "null tensor");
+    ES_CHECK(workspace && workspace_bytes >= es_workspace_bytes(m, B, 0, T), "workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Arena a(reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256)));
+    DecBufs db = plan_decoder(m, a, B, T);
+    // skip = LN(tanh(Linear(features)))                                           networks.py:292
+    RowGemmParams p = base_params(B, T, T, m->dx4, m->dx2, features, m->dx4, m->w.dproj_w, db.buf[0], m->dx2);
+    p.bias = m->w.dproj_b; p.act1 = ACT_TANH; p.ln_g = m->w.dproj_ln_g; p.ln_b = m->w.dproj_ln_b;
+    if (launch_rowgemm(p, s)) return 1;
+    return decoder_layers(m, B, T, db, 0, nullptr, mel, s);
+}
+
+int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T,
+                                const float* fused4, const int32_t* dur_cum, const int32_t* mel_len,
+                                int zero_padded_frames, float* mel, void* workspace, size_t workspace_bytes) {
+    ES_CHECK(m, "null model");
+    ES_CHECK(B >= 1 && B <= 65535 && N >= 1 && T >= 1, "need 1 <= B <= 65535, N >= 1 and T >= 1 frames");
+    ES_CHECK(fused4 && dur_cum && mel_len && mel, "null tensor");
+    ES_CHECK(workspace && workspace_bytes >= es_workspace_bytes(m, B, 0, T), "workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Arena a(reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256)));
+    DecBufs db = plan_decoder(m, a, B, T);
+    // length-regulator gather fused into the projection's operand load (networks.py:228-258, :292)
+    RowGemmParams p = base_params(B, N, T, m->dx4, m->dx2, fused4, m->dx4, m->w.dproj_w, db.buf[0], m->dx2);
+    p.mode = ROW_GATHER; p.cum = dur_cum; p.valid_len = mel_len;
+    p.bias = m->w.dproj_b; p.act1 = ACT_TANH; p.ln_g = m->w.dproj_ln_g; p.ln_b = m->w.dproj_ln_b;
+    if (launch_rowgemm(p, s)) return 1;
+    return decoder_layers(m, B, T, db, 0, zero_padded_frames ? mel_len : nullptr, mel, s);
+}
+
+}  // extern "C"
+
+namespace {
+
+// Decoder blocks + mel head (networks.py:293-302, :424-427).  db.buf[s_idx] holds `skip`.
+int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, const int* zero_from,
+                   float* mel, cudaStream_t s) {
+    const int C = m->dx2;
+    int layer = 0;
+    for (int blk = 0; blk < m->cfg.n_blocks; ++blk) {
+        int in_idx = s_idx;
+        for (int l = 0; l < m->cfg.block_depth; ++l, ++layer) {
+            int out_idx = 0;
+            while (out_idx == s_idx || out_idx == in_idx) ++out_idx;
+            const es_dec_layer_w_t& w = m->w.dec[layer];
+            RowGemmParams p = base_params(B, T, T, C, C, db.buf[in_idx], C, w.pw_w, db.buf[out_idx], C);
+            p.mode = ROW_DWCONV; p.dw_w = w.dw_w; p.dw_b = w.dw_b; p.dw_k = m->cfg.decoder_kernel_size;
+            p.bias = w.pw_b; p.act1 = ACT_TANH; p.ln_g = w.ln_g; p.ln_b = w.ln_b;
+            if (l == m->cfg.block_depth - 1) {       // skip = LN_blk(x + skip)   networks.py:299
+                p.res2 = db.buf[s_idx]; p.ldr2 = C; p.ln2_g = m->w.blk_ln_g[blk]; p.ln2_b = m->w.blk_ln_b[blk];
+            }
+            if (launch_rowgemm(p, s)) return 1;
+            in_idx = out_idx;
+        }
+        s_idx = in_idx;
+    }
+    // mel = Linear(skip); padded frames zeroed                                      networks.py:302, :424-427
+    RowGemmParams p = base_params(B, T, T, C, m->cfg.n_mel, db.buf[s_idx], C, m->w.mel_w, mel, m->cfg.n_mel);
+    p.bias = m->w.mel_b; p.zero_from = zero_from;
+    return launch_rowgemm(p, s);
+}
+
+}  // namespace

@@ -1,0 +1,114 @@
+// Shared device/host helpers for the EfficientSpeech sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/es_b200.h"
+
+namespace es {
+
+constexpr float kLnEps = 1e-5f;   // nn.LayerNorm default eps (layers/networks.py:45-46)
+
+// ---- error plumbing (host) -----------------------------------------------------------
+void set_error(const std::string& msg);
+extern std::atomic<uint64_t> g_launches;
+
+#define ES_CHECK(cond, msg)                                                   \
+    do {                                                                      \
+        if (!(cond)) {                                                        \
+            ::es::set_error(std::string(__func__) + ": " + (msg));            \
+            return 1;                                                         \
+        }                                                                     \
+    } while (0)
+
+#define ES_CUDA(expr)                                                         \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) {                                              \
+            ::es::set_error(std::string(__func__) + ": " #expr " -> " +       \
+                            cudaGetErrorString(_e));                          \
+            return 1;                                                         \
+        }                                                                     \
+    } while (0)
+
+#define ES_LAUNCH_OK()                                                        \
+    do {                                                                      \
+        ::es::g_launches.fetch_add(1, std::memory_order_relaxed);             \
+        ES_CUDA(cudaGetLastError());                                          \
+    } while (0)
+
+// ---- activations -----------------------------------------------------------------------
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_TANH = 3 };
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(v, 0.f);
+        case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));  // exact erf GELU (blocks.py:19)
+        case ACT_TANH: return tanhf(v);
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- generic fused row-GEMM (es_rowgemm.cu) ----------------------------------------------
+enum RowMode : int { ROW_PLAIN = 0, ROW_GATHER = 1, ROW_DWCONV = 2 };
+
+struct RowGemmParams {
+    // geometry: output rows are (b, t), t in [0, n_out); input rows (b, t_in), t_in in [0, n_in)
+    int B, n_in, n_out;
+    int K, Nout, ldw;          // ldw: row stride of W (Nout padded to a multiple of 32)
+    int taps, stride, pad;     // PLAIN: t_in = t*stride + tau - pad, zero outside [0, n_in)
+    int mode;
+    const float* A;            // [B*n_in][lda]
+    int lda;
+    // GATHER: A row of frame t is row upper_bound(cum[b,:], t) of utterance b, zero for t >= valid_len[b]
+    const int* cum;            // [B][n_in] inclusive prefix sums
+    const int* valid_len;      // [B]
+    // DWCONV: A'[t][c] = dw_b[c] + sum_tau dw_w[tau][c] * A[t + tau - dw_k/2][c]
+    const float* dw_w;
+    const float* dw_b;
+    int dw_k;
+    // weights
+    const float* W;            // [taps][K][ldw]
+    const float* bias;         // [ldw] or null
+    const float* tap_bias;     // [taps][ldw] or null: added where tap tau reads inside the sequence
+    int act1;
+    // optional scalar head on the post-act1 values: dot_out[row] = (relu?)(sum_c v[c] dot_w[c] + dot_b[0])
+    const float* dot_w;
+    const float* dot_b;
+    float* dot_out;
+    int dot_relu;
+    const float* res1;         // added before LN1, [B*n_out][ldr1]
+    int ldr1;
+    const float* ln_g;         // LayerNorm over Nout (requires one column tile) or null
+    const float* ln_b;
+    int act2;
+    const float* res2;         // out = LN2(out + res2)
+    int ldr2;
+    const float* ln2_g;
+    const float* ln2_b;
+    const uint8_t* row_mask;   // [B][n_out], 1 -> zero the row
+    const int* zero_from;      // [B], rows t >= zero_from[b] are zeroed
+    float* Y;                  // [B*n_out][ldy] or null
+    int ldy;
+};
+
+int launch_rowgemm(const RowGemmParams& p, cudaStream_t stream);
+
+}  // namespace es

@@ -1,0 +1,23 @@
+// Launch wrappers of the non-GEMM kernels (es_encoder.cu) and of the tcgen05 path (es_umma.cu).
+#pragma once
+#include "es_common.cuh"
+
+namespace es {
+
+int launch_embed_merge(const int32_t* ids, const float* tab, float* out, int B, int N, int C, int k,
+                       int n_symbols, cudaStream_t s);
+int launch_pool_mask(const uint8_t* mask, uint8_t* out, int B, int N, int n1, int pool, cudaStream_t s);
+int launch_attention(const float* qkv, float* out, int B, int n, int C, int H, float scale, cudaStream_t s);
+int launch_fuse(const float* f0, const float* f1, const float* a0, const float* g, const float* gb,
+                const float* cst, const uint8_t* mask, float* out, int B, int N, int n1, int d, int k,
+                cudaStream_t s);
+int launch_variance_scan(const float* fused, const float* dur_feat, const float* pitch_pred,
+                         const float* energy_pred, const float* dur_pred, const float* pitch_tgt,
+                         const float* energy_tgt, const int32_t* dur_tgt, const uint8_t* mask,
+                         const es_predictor_w_t& pw, const es_predictor_w_t& ew, float* fused4,
+                         int32_t* dur_int, int32_t* dur_cum, int32_t* mel_len, int B, int N, int d,
+                         cudaStream_t s);
+int launch_length_regulate(const float* fused4, const int32_t* cum, const uint8_t* pmask, float* feats,
+                           uint8_t* fmask, int32_t* src, int B, int N, int T, int C, cudaStream_t s);
+
+}  // namespace es

@@ -1,0 +1,200 @@
+/*
+ * es_b200.h -- C ABI of the B200-native EfficientSpeech acoustic forward path.
+ *
+ * The reference (roatienza/efficientspeech @ 218f62f) has no FFI of its own: the boundary
+ * it exposes for this path is the Python nn.Module API
+ *     layers/__init__.py:1        from .networks import PhonemeEncoder, MelDecoder, Phoneme2Mel
+ *     model.py:132-147            construction of the three modules
+ *     model.py:155-164            the forward that calls them
+ * Each entry point below names the reference method it replaces.  The Python mirror of the
+ * reference modules (efficientspeech_b200/modules.py) binds these with ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - tensors are dense, row-major, channels-last: [B, n, C] fp32, ids/durations int32,
+ *     masks uint8 (1 = padding, the reference's bool True);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call
+ *     synchronises the device;
+ *   - every function returns 0 on success, non-zero on error; es_last_error() returns a
+ *     thread-local message (bad shape, unsupported geometry, CUDA launch failure ...).
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef ES_B200_H
+#define ES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ES_ABI_VERSION 3
+#define ES_MAX_ENC_BLOCKS 2
+#define ES_MAX_DEC_LAYERS 24
+#define ES_MAX_DEC_BLOCKS 8
+#define ES_MAX_TAPS 9
+
+/* Geometry; mirrors the ctor arguments of PhonemeEncoder / MelDecoder
+ * (layers/networks.py:310-333, :264-270). */
+typedef struct es_config {
+    int32_t embed_dim;            /* 128 */
+    int32_t dim;                  /* d = embed_dim / reduction */
+    int32_t kernel_size;          /* encoder merge-conv kernel (3 | 5) */
+    int32_t head;                 /* heads of block 0 (block 1 has 2x) */
+    int32_t expansion;            /* MixFFN hidden multiplier */
+    int32_t n_blocks;             /* decoder blocks */
+    int32_t block_depth;          /* layers per decoder block */
+    int32_t decoder_kernel_size;  /* depthwise kernel (5) */
+    int32_t n_mel;                /* 80 */
+    int32_t n_symbols;            /* 153 */
+} es_config_t;
+
+/* Folded, kernel-ready weights (fp32, device).  Built on the host by
+ * efficientspeech_b200/packing.py from the reference state dict; layouts are
+ * "[taps][K][Nout_padded]" (K-major rows, output channel contiguous, Nout padded to a
+ * multiple of 32 with zeros) unless noted. */
+typedef struct es_enc_block_w {
+    const float* merge_w;    /* block 0: gather tables [k][n_symbols][C] = E . (W1x1 Wk)^T  (networks.py:54,65-66)
+                                block 1: folded conv   [k'][Cin][C]      = W1x1 . Wk'        (networks.py:65-66) */
+    const float* qkv_w;      /* [1][C][3HC]                 blocks.py:45 */
+    const float* proj_w;     /* [1][HC][C]                  blocks.py:66 */
+    const float* proj_b;     /* [C] */
+    const float* ln1_g;      /* networks.py:73 */
+    const float* ln1_b;
+    const float* ffn1_w;     /* [3][C][hC] = conv3 . mlp1   blocks.py:23-25 */
+    const float* ffn1_tapb;  /* [3][hC]    = Wc_tau . b1 (added only where tap tau is inside the sequence) */
+    const float* ffn1_b;     /* [hC] conv bias */
+    const float* ffn2_w;     /* [1][hC][C]                  blocks.py:28 */
+    const float* ffn2_b;
+    const float* ln2_g;      /* networks.py:80 */
+    const float* ln2_b;
+} es_enc_block_w_t;
+
+typedef struct es_predictor_w {     /* AcousticDecoder, networks.py:98-122,151-165 */
+    const float* conv1_w;    /* [3][d][d] */
+    const float* conv1_b;
+    const float* ln1_g;
+    const float* ln1_b;
+    const float* conv2_w;    /* [3][d][d] */
+    const float* conv2_b;
+    const float* ln2_g;      /* used by the duration predictor only (networks.py:159) */
+    const float* ln2_b;
+    const float* lin_w;      /* [d] */
+    const float* lin_b;      /* [1] */
+    const float* bins;       /* [d-1]  (pitch / energy) or NULL */
+    const float* table;      /* [d][d] (pitch / energy) or NULL */
+} es_predictor_w_t;
+
+typedef struct es_dec_layer_w {     /* networks.py:279-283 */
+    const float* dw_w;       /* [k][dx2]   depthwise taps, channel contiguous */
+    const float* dw_b;       /* [dx2] */
+    const float* pw_w;       /* [1][dx2][dx2] */
+    const float* pw_b;
+    const float* ln_g;
+    const float* ln_b;
+    /* split-fp16 image of pw_w for the tcgen05 kernel: [2][dx2(N)][dx2(K)] halves, hi then lo,
+     * K contiguous (NULL -> SIMT kernel is used) */
+    const void*  pw_w_h16;
+} es_dec_layer_w_t;
+
+typedef struct es_weights {
+    es_enc_block_w_t enc[ES_MAX_ENC_BLOCKS];
+    /* Fuse (networks.py:189-219), all linear maps folded: */
+    const float* fuse_a0;    /* [d][d]        = Wf[:, :d] . Wm0            (K-major) */
+    const float* fuse_g;     /* [k][2d][d]    = Wf[:, d:] . Wct_tau^T . Wm1 */
+    const float* fuse_gb;    /* [k][d]        = Wf[:, d:] . Wct_tau^T . bm1 */
+    const float* fuse_c;     /* [d]           = Wf[:, :d] bm0 + Wf[:, d:] bct + bf */
+    es_predictor_w_t pitch;
+    es_predictor_w_t energy;
+    es_predictor_w_t duration;
+    /* MelDecoder (networks.py:272-288) */
+    const float* dproj_w;    /* [1][dx4][dx2] */
+    const float* dproj_b;
+    const float* dproj_ln_g;
+    const float* dproj_ln_b;
+    es_dec_layer_w_t dec[ES_MAX_DEC_LAYERS];
+    const float* blk_ln_g[ES_MAX_DEC_BLOCKS];
+    const float* blk_ln_b[ES_MAX_DEC_BLOCKS];
+    const float* mel_w;      /* [1][dx2][96] */
+    const float* mel_b;      /* [96] */
+} es_weights_t;
+
+typedef struct es_model es_model_t;   /* opaque */
+
+int         es_abi_version(void);
+const char* es_last_error(void);
+
+/* Replaces PhonemeEncoder.__init__/MelDecoder.__init__/Phoneme2Mel.__init__ (networks.py:310-333,
+ * :264-288, :407-413) as far as device state goes.  The weights struct is copied; the
+ * buffers it points to stay owned by the caller and must outlive the model. */
+int  es_model_create(const es_config_t* cfg, const es_weights_t* w, es_model_t** out);
+void es_model_destroy(es_model_t* m);
+/* 0: SIMT fp32 kernels everywhere; 1 (default): tcgen05 split-fp16 decoder layers where supported */
+int  es_model_set_tensor_core(es_model_t* m, int enable);
+
+/* Scratch requirement (bytes) of the calls below for a batch of B utterances, N phonemes,
+ * T frames (T may be 0 for encoder-only use). */
+size_t es_workspace_bytes(const es_model_t* m, int B, int N, int T);
+
+/*
+ * Replaces PhonemeEncoder.forward up to (not including) the feature upsampler
+ * (networks.py:336-384): embedding, 2 encoder blocks, fuse, the three predictors, variance
+ * embeddings, concat, duration rounding/clamp, plus the integer scan of the length regulator.
+ *   phoneme       [B,N] int32
+ *   phoneme_mask  [B,N] uint8 or NULL (the reference's B==1 mask-free path, networks.py:338)
+ *   pitch_tgt / energy_tgt [B,N] f32, dur_tgt [B,N] int32: teacher-forcing targets
+ *                 (train=True) or NULL (free running: predictions are embedded / rounded)
+ * outputs
+ *   pitch_pred, energy_pred, dur_pred  [B,N] f32   (the reference's [B,N,1])
+ *   fused4        [B,N,4d] f32  concat [fused | pitch_emb | energy_emb | duration_feat]
+ *   dur_int       [B,N] int32   durations driving the length regulator (networks.py:379-384,234)
+ *   dur_cum       [B,N] int32   inclusive prefix sum of dur_int
+ *   mel_len       [B]   int32   (networks.py:255)
+ */
+int es_encoder_forward(es_model_t* m, void* stream, int B, int N,
+                       const int32_t* phoneme, const uint8_t* phoneme_mask,
+                       const float* pitch_tgt, const float* energy_tgt, const int32_t* dur_tgt,
+                       float* pitch_pred, float* energy_pred, float* dur_pred,
+                       float* fused4, int32_t* dur_int, int32_t* dur_cum, int32_t* mel_len,
+                       void* workspace, size_t workspace_bytes);
+
+/*
+ * Replaces FeatureUpsampler.forward (networks.py:228-258): materialises the expanded
+ * features.  src[b,t] = min{n : dur_cum[b,n] > t} for t < mel_len[b], else -1.
+ *   features [B,T,4d] f32 (zeros on padding), frame_mask [B,T] uint8 (1 = padding; the
+ *   reference's [B,T,4d] bool mask is this broadcast over channels, ORed with the source
+ *   phoneme's mask), src [B,T] int32 (may be NULL).
+ */
+int es_length_regulate(es_model_t* m, void* stream, int B, int N, int T,
+                       const float* fused4, const int32_t* dur_cum, const uint8_t* phoneme_mask,
+                       float* features, uint8_t* frame_mask, int32_t* src);
+
+/* Replaces MelDecoder.forward (networks.py:291-304): features [B,T,4d] -> mel [B,T,n_mel]. */
+int es_decoder_forward(es_model_t* m, void* stream, int B, int T,
+                       const float* features, float* mel,
+                       void* workspace, size_t workspace_bytes);
+
+/*
+ * Replaces the decoder half of Phoneme2Mel.forward (networks.py:422-427) without ever
+ * materialising [B,T,4d]: the length-regulator gather is the prologue of the first decoder
+ * kernel, and frames t >= mel_len[b] of the mel are zeroed when zero_padded_frames != 0
+ * (the reference does so only when B > 1).
+ */
+int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T,
+                                const float* fused4, const int32_t* dur_cum, const int32_t* mel_len,
+                                int zero_padded_frames, float* mel,
+                                void* workspace, size_t workspace_bytes);
+
+/* Number of kernels the library has launched since process start (bench.py's gpu_launches). */
+uint64_t es_launch_count(void);
+
+/* Self-test of the tcgen05/TMA building block: C[M,N] = A[M,K] B[N,K]^T with split-fp16
+ * operands (3 MMAs), M multiple of 128, N in {128,256}, K multiple of 64.  fp32 in/out. */
+int es_selftest_umma_gemm(void* stream, int M, int N, int K, const float* A, const float* Bm, float* C);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ES_B200_H */

@@ -1,0 +1,190 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) vs the reference fixtures and the oracle.
+
+Bars (BASELINE.json north_star / SURVEY.md section 8c):
+  mel max-abs <= 1e-3 vs the reference fp32 CPU path; scalar predictions <= 1e-4;
+  every integer (mel_len, rounded durations, bucket indices via the embedded rows,
+  length-regulator source indices, masks) bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import efficientspeech_b200 as es
+from efficientspeech_b200 import _cabi
+from efficientspeech_b200.config import VARIANTS
+from efficientspeech_b200.params import init_state_dict
+from efficientspeech_b200.synthetic import make_batch
+from helpers import TOL_MEL, TOL_PRED, golden_files, load_golden
+from oracle import es_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cuda_model(vname, sd):
+    m = es.build_model(vname)
+    es.load_numpy_state(m, sd)
+    return m.to(DEV).eval()
+
+
+def to_dev(batch):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)).to(DEV) for k, v in batch.items()}
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_reference_fixture_parity(path):
+    vname, cfg, sd, batch, g = load_golden(path)
+    model = cuda_model(vname, sd)
+    x = to_dev(batch)
+    with torch.no_grad():
+        tf = model(x, train=True)
+        mel_fr, len_fr, dur_fr = model(x, train=False)
+    assert tf["mel_len"].dtype == torch.int32
+    assert np.array_equal(npy(tf["mel_len"]), g["tf_mel_len"])
+    assert tuple(tf["mel"].shape) == g["tf_mel"].shape
+    assert np.abs(npy(tf["mel"]) - g["tf_mel"]).max() <= TOL_MEL
+    for k in ("pitch", "energy", "duration"):
+        assert tuple(tf[k].shape) == g["tf_" + k].shape
+        assert np.abs(npy(tf[k]) - g["tf_" + k]).max() <= TOL_PRED, k
+    # free running: durations are rounded predictions -> same T, same lengths, same mel
+    assert np.array_equal(npy(len_fr), g["fr_mel_len"])
+    assert tuple(mel_fr.shape) == g["fr_mel"].shape
+    assert np.abs(npy(mel_fr) - g["fr_mel"]).max() <= TOL_MEL
+    assert np.abs(npy(dur_fr) - g["fr_duration"]).max() <= TOL_PRED
+    # length-regulator source map from the reference FeatureUpsampler: bit-exact
+    B, N = batch["phoneme"].shape
+    T = int(g["tf_mel_len"].max())
+    src = torch.empty(B, T, dtype=torch.int32, device=DEV)
+    _cabi.check(_cabi.load().es_length_regulate(
+        model.encoder._backend.handle, torch.cuda.current_stream().cuda_stream, B, N, T, None,
+        tf["_dur_cum"].data_ptr(), None, None, None, src.data_ptr()))
+    assert np.array_equal(npy(src), g["tf_src"])
+
+
+CASES = [("tiny", 5, 40, True), ("tiny", 1, 19, False), ("tiny", 3, 129, True), ("tiny", 2, 2, False),
+         ("small", 4, 33, True), ("small", 1, 64, False), ("base", 3, 31, True), ("base", 2, 70, True),
+         ("tiny", 7, 300, True)]
+
+
+@pytest.mark.parametrize("vname,B,N,ragged", CASES, ids=lambda v: str(v))
+def test_oracle_parity_all_outputs(vname, B, N, ragged):
+    cfg = VARIANTS[vname]
+    sd = init_state_dict(cfg, seed=100 + B + N)
+    batch = make_batch(cfg, B, N, seed=B * 7 + N, ragged=ragged, fixed_duration=None, max_dur=6)
+    model = cuda_model(vname, sd)
+    x = to_dev(batch)
+    for train in (True, False):
+        o = es_oracle.phoneme2mel(batch, sd, train=train)
+        with torch.no_grad():
+            out = model(x, train=True) if train else model.encoder(x, train=False)
+            mel = out["mel"] if train else model(x, train=False)[0]
+        assert np.array_equal(npy(out["mel_len"]), o["mel_len"])
+        assert np.array_equal(npy(out["_dur_int"]), o["_dur_int"])                   # rounded durations: exact
+        assert np.abs(npy(out["_fused4"]) - o["_fused4"]).max() <= TOL_PRED * 5        # a bucket flip would be O(1)
+        assert np.abs(npy(out["features"]) - o["features"]).max() <= TOL_PRED * 5
+        if B > 1:
+            assert np.array_equal(npy(out["masks"]), o["masks"])                     # bool [B,T,4d]: exact
+        else:
+            assert out["masks"] is None and o["masks"] is None
+        for k in ("pitch", "energy", "duration"):
+            assert np.abs(npy(out[k]) - o[k]).max() <= TOL_PRED, k
+        assert tuple(mel.shape) == o["mel"].shape
+        assert np.abs(npy(mel) - o["mel"]).max() <= TOL_MEL
+
+
+@pytest.mark.parametrize("vname", list(VARIANTS))
+def test_mel_decoder_standalone(vname):
+    cfg = VARIANTS[vname]
+    sd = init_state_dict(cfg, seed=5)
+    model = cuda_model(vname, sd)
+    rng = np.random.default_rng(0)
+    feats = rng.standard_normal((3, 77, cfg.dx4)).astype(np.float32)
+    S = es_oracle._cast_state(sd, np.float32)
+    want = es_oracle.mel_decoder(feats, S, es_oracle.infer_config(S))
+    with torch.no_grad():
+        got = model.decoder(torch.from_numpy(feats).to(DEV))
+    assert np.abs(npy(got) - want).max() <= TOL_MEL
+
+
+def test_length_regulator_exact_random():
+    model = cuda_model("tiny", init_state_dict(VARIANTS["tiny"], seed=1))
+    model.encoder._backend.ensure(torch.device(DEV))
+    lib = _cabi.load()
+    rng = np.random.default_rng(123)
+    for trial in range(25):
+        B, N = int(rng.integers(1, 9)), int(rng.integers(1, 200))
+        dur = rng.integers(0, 9, size=(B, N)).astype(np.int32)
+        if trial % 5 == 0:
+            dur[rng.integers(0, B)] = 0                                      # an utterance with no frames
+        if trial % 7 == 0:
+            dur[:, : N // 2] = 0                                             # leading zero-duration phonemes
+        feats = rng.standard_normal((B, N, 128)).astype(np.float32)
+        pmask = rng.random((B, N)) < 0.1
+        f, m, ml, src = es_oracle.feature_upsampler(feats, np.repeat(pmask[..., None], 128, 2), dur)
+        T = int(ml.max())
+        if T == 0:
+            continue
+        cum = torch.from_numpy(np.cumsum(dur, axis=1).astype(np.int32)).to(DEV)
+        tf = torch.from_numpy(feats).to(DEV)
+        tm = torch.from_numpy(pmask).to(DEV).view(torch.uint8)
+        out = torch.empty(B, T, 128, device=DEV)
+        fm = torch.empty(B, T, dtype=torch.uint8, device=DEV)
+        sr = torch.empty(B, T, dtype=torch.int32, device=DEV)
+        _cabi.check(lib.es_length_regulate(model.encoder._backend.handle, torch.cuda.current_stream().cuda_stream,
+                                           B, N, T, tf.data_ptr(), cum.data_ptr(), tm.data_ptr(),
+                                           out.data_ptr(), fm.data_ptr(), sr.data_ptr()))
+        assert np.array_equal(npy(sr), src)
+        assert np.array_equal(npy(out), f)                                   # pure copy: bit-exact
+        assert np.array_equal(npy(fm).astype(bool), m[..., 0])
+
+
+def test_full_size_properties_tiny_b256():
+    """BASELINE configs[1] shape: size-independent properties + spot parity vs the oracle."""
+    cfg = VARIANTS["tiny"]
+    sd = init_state_dict(cfg, seed=0)
+    model = cuda_model("tiny", sd)
+    B, N = 256, 128
+    batch = make_batch(cfg, B, N, seed=0, ragged=False, fixed_duration=6)
+    x = to_dev(batch)
+    x["max_mel_len"] = 6 * N
+    with torch.no_grad():
+        out = model(x, train=True)
+    mel = npy(out["mel"])
+    assert mel.shape == (B, 6 * N, 80) and np.isfinite(mel).all()
+    assert np.array_equal(npy(out["mel_len"]), batch["mel_len"])
+    # utterances are independent: a shard of the batch gives bit-identical results
+    idx = [0, 100, 255]
+    sub = {k: v[idx] for k, v in batch.items()}
+    xs = to_dev(sub)
+    xs["max_mel_len"] = 6 * N
+    with torch.no_grad():
+        outs = model(xs, train=True)
+    assert np.array_equal(npy(outs["mel"]), mel[idx])
+    o = es_oracle.phoneme2mel(sub, sd, train=True)
+    assert np.abs(mel[idx] - o["mel"]).max() <= TOL_MEL
+    # ragged: padded frames are exactly zero, lengths are the duration sums
+    rb = make_batch(cfg, 64, N, seed=3, ragged=True, fixed_duration=None)
+    with torch.no_grad():
+        ro = model(to_dev(rb), train=True)
+    rmel, rlen = npy(ro["mel"]), npy(ro["mel_len"])
+    assert np.array_equal(rlen, rb["duration"].sum(1))
+    for b in range(64):
+        assert (rmel[b, rlen[b]:] == 0).all()
+
+
+def test_errors_are_python_exceptions():
+    model = cuda_model("tiny", init_state_dict(VARIANTS["tiny"], seed=1))
+    with pytest.raises(RuntimeError):
+        model.decoder(torch.zeros(1, 8, 64, device=DEV))                     # wrong channel count
+    cfg = VARIANTS["tiny"]
+    b = make_batch(cfg, 2, 8, seed=0)
+    b["duration"][:] = 0
+    b["mel_len"][:] = 0
+    with pytest.raises(RuntimeError, match="no frames"):
+        model(to_dev(b), train=True)

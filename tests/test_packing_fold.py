@@ -1,0 +1,54 @@
+"""CPU validation of the weight folding (packing.py) against the oracle, via tests/kernel_model.py."""
+import os
+
+import numpy as np
+import pytest
+
+from efficientspeech_b200 import packing
+from helpers import golden_files, load_golden
+from kernel_model import encoder_model, length_regulator_model, predictor_model
+from oracle import es_oracle
+
+
+@pytest.mark.parametrize("path", golden_files()[::3] + golden_files()[2::3], ids=lambda p: os.path.basename(p)[:-4])
+def test_folded_encoder_matches_oracle(path):
+    vname, cfg, sd, batch, g = load_golden(path)
+    F = packing.fold_encoder(sd, cfg)
+    o = es_oracle.phoneme2mel(batch, sd, train=True, dtype=np.float64)
+    mask = batch["phoneme_mask"] if batch["phoneme"].shape[0] > 1 else None
+    feats, fused = encoder_model(F, cfg, batch["phoneme"], mask)
+    for a, b in zip(feats, o["_enc_features"]):
+        assert np.abs(a - b).max() < 1e-9
+    assert np.abs(fused - o["_fused"]).max() < 1e-9
+    for which in ("pitch", "energy", "duration"):
+        pred, feat = predictor_model(F, which, fused)
+        assert np.abs(pred - o[which][..., 0]).max() < 1e-9
+    d = cfg.dim
+    assert np.abs(feat * (1 if mask is None else ~mask[..., None]) - o["_fused4"][..., 3 * d:]).max() < 1e-9
+
+
+def test_length_regulator_model_matches_oracle():
+    rng = np.random.default_rng(5)
+    for _ in range(30):
+        B, N = int(rng.integers(1, 5)), int(rng.integers(1, 50))
+        dur = rng.integers(0, 7, size=(B, N)).astype(np.int32)
+        feats = np.zeros((B, N, 1), np.float32)
+        _, _, ml, src = es_oracle.feature_upsampler(feats, np.zeros((B, N, 1), bool), dur)
+        T = int(ml.max())
+        got = length_regulator_model(np.cumsum(dur, axis=1), T)
+        assert np.array_equal(got, src)
+
+
+def test_pack_layout_and_split_fp16():
+    vname, cfg, sd, batch, g = load_golden(golden_files()[0])
+    F = dict(packing.fold_encoder(sd, cfg))
+    F.update(packing.fold_decoder(sd, cfg))
+    flat, off = packing.pack(F)
+    assert flat.dtype == np.float32
+    for k, v in F.items():
+        assert off[k] % packing.ALIGN == 0
+        assert np.array_equal(flat[off[k]:off[k] + v.size], np.asarray(v, np.float32).reshape(-1))
+    assert F["mel_w"].shape == (1, cfg.dx2, 96) and F["mel_b"].shape == (96,)
+    w = F["dec0.pw_w"][0].astype(np.float32)
+    halves = packing.split_fp16(w).view(np.float16).reshape(2, *w.shape).astype(np.float64)
+    assert np.abs(halves[0] + halves[1] - w).max() < 2e-7
