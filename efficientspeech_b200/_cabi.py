@@ -8,10 +8,12 @@ from typing import Optional
 
 from . import build as _build
 
-ES_ABI_VERSION = 3
+ES_ABI_VERSION = 4
 ES_MAX_ENC_BLOCKS = 2
 ES_MAX_DEC_LAYERS = 24
 ES_MAX_DEC_BLOCKS = 8
+KERNEL_KINDS = ["embed", "enc_gemm", "attention", "fuse", "predictor", "variance", "lenreg",
+                "dec_proj", "dec_layer", "mel", "poolmask"]
 
 _fp = C.c_void_p      # device pointers travel as integers
 
@@ -64,6 +66,9 @@ PROTOTYPES = {
     "es_decoder_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _sz]),
     "es_decoder_forward_gathered": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz]),
     "es_launch_count": (C.c_uint64, []),
+    "es_profile_begin": (_i, [_i]),
+    "es_profile_end": (_i, []),
+    "es_profile_collect": (_i, [_vp, _vp, _i, C.POINTER(_i)]),
     "es_selftest_umma_gemm": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
 }
 

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "es_common.cuh"
 #include "es_kernels.cuh"
@@ -13,6 +14,31 @@ namespace es {
 static thread_local std::string g_error;
 std::atomic<uint64_t> g_launches{0};
 void set_error(const std::string& msg) { g_error = msg; }
+
+// per-launch event timing -------------------------------------------------------------------
+namespace {
+struct Profiler {
+    bool on = false;
+    size_t cap = 0;
+    std::vector<cudaEvent_t> ev0, ev1;
+    std::vector<int> kinds;
+    size_t n = 0;
+    bool open = false;
+} g_prof;
+}  // namespace
+
+void prof_begin_range(int kind, cudaStream_t s) {
+    if (!g_prof.on || g_prof.n >= g_prof.cap) return;
+    g_prof.kinds[g_prof.n] = kind;
+    cudaEventRecord(g_prof.ev0[g_prof.n], s);
+    g_prof.open = true;
+}
+void prof_end_range(cudaStream_t s) {
+    if (!g_prof.on || !g_prof.open) return;
+    cudaEventRecord(g_prof.ev1[g_prof.n], s);
+    g_prof.n++;
+    g_prof.open = false;
+}
 
 }  // namespace es
 
@@ -102,21 +128,22 @@ int encoder_block(const es_model* m, int i, int B, int n, const float* x_in, con
     const int C = m->C[i], H = m->H[i], hC = m->hC[i];
     // qkv = x Wqkv^T                                                            blocks.py:45
     RowGemmParams p = base_params(B, n, n, C, 3 * H * C, x_in, C, w.qkv_w, e.qkv, 3 * H * C);
-    if (launch_rowgemm(p, s)) return 1;
+    { ProfRange r(ES_K_ENC_GEMM, s); if (launch_rowgemm(p, s)) return 1; }
     // softmax(QK^T scale) V, all keys (mask never applied)                         blocks.py:49-65
     const float scale = 1.0f / sqrtf((float)(C / H));
-    if (launch_attention(e.qkv, e.att, B, n, C, H, scale, s)) return 1;
+    { ProfRange r(ES_K_ATTENTION, s); if (launch_attention(e.qkv, e.att, B, n, C, H, scale, s)) return 1; }
     // x1 = mask(LN1(proj(att) + x))                                                blocks.py:66, networks.py:73-75
     p = base_params(B, n, n, H * C, C, e.att, H * C, w.proj_w, e.x1, C);
     p.bias = w.proj_b; p.res1 = x_in; p.ldr1 = C; p.ln_g = w.ln1_g; p.ln_b = w.ln1_b; p.row_mask = mask;
-    if (launch_rowgemm(p, s)) return 1;
+    { ProfRange r(ES_K_ENC_GEMM, s); if (launch_rowgemm(p, s)) return 1; }
     // h = GELU(conv3(mlp1(x1)))  with mlp1 folded into the conv taps               blocks.py:23-27
     p = base_params(B, n, n, C, hC, e.x1, C, w.ffn1_w, e.h, hC);
     p.taps = 3; p.pad = 1; p.bias = w.ffn1_b; p.tap_bias = w.ffn1_tapb; p.act1 = ACT_GELU;
-    if (launch_rowgemm(p, s)) return 1;
+    { ProfRange r(ES_K_ENC_GEMM, s); if (launch_rowgemm(p, s)) return 1; }
     // feat = mask(LN2(mlp2(h) + x1))                                               blocks.py:28, networks.py:80-83
     p = base_params(B, n, n, hC, C, e.h, hC, w.ffn2_w, feat_out, C);
     p.bias = w.ffn2_b; p.res1 = e.x1; p.ldr1 = C; p.ln_g = w.ln2_g; p.ln_b = w.ln2_b; p.row_mask = mask;
+    ProfRange r(ES_K_ENC_GEMM, s);
     return launch_rowgemm(p, s);
 }
 
@@ -127,11 +154,12 @@ int predictor(const es_model* m, const es_predictor_w_t& w, int B, int N, const 
     RowGemmParams p = base_params(B, N, N, d, d, fused, d, w.conv1_w, y1, d);
     p.taps = 3; p.pad = 1; p.bias = w.conv1_b; p.act1 = ACT_RELU;
     p.ln_g = w.ln1_g; p.ln_b = w.ln1_b; p.act2 = ACT_RELU;
-    if (launch_rowgemm(p, s)) return 1;
+    { ProfRange r(ES_K_PREDICTOR, s); if (launch_rowgemm(p, s)) return 1; }
     p = base_params(B, N, N, d, d, y1, d, w.conv2_w, is_duration ? feat_out : nullptr, d);
     p.taps = 3; p.pad = 1; p.bias = w.conv2_b; p.act1 = ACT_RELU;
     p.dot_w = w.lin_w; p.dot_b = w.lin_b; p.dot_out = pred; p.dot_relu = is_duration ? 1 : 0;
     if (is_duration) { p.ln_g = w.ln2_g; p.ln_b = w.ln2_b; }   // norm2 output is only consumed for duration
+    ProfRange r(ES_K_PREDICTOR, s);
     return launch_rowgemm(p, s);
 }
 
@@ -145,6 +173,45 @@ extern "C" {
 int es_abi_version(void) { return ES_ABI_VERSION; }
 const char* es_last_error(void) { return es::g_error.c_str(); }
 uint64_t es_launch_count(void) { return es::g_launches.load(); }
+
+int es_profile_begin(int max_records) {
+    ES_CHECK(max_records > 0 && max_records <= (1 << 20), "bad record count");
+    auto& P = es::g_prof;
+    P.on = false;
+    for (size_t i = P.ev0.size(); i < (size_t)max_records; ++i) {
+        cudaEvent_t a, b;
+        ES_CUDA(cudaEventCreate(&a));
+        ES_CUDA(cudaEventCreate(&b));
+        P.ev0.push_back(a);
+        P.ev1.push_back(b);
+    }
+    P.kinds.assign(P.ev0.size(), 0);
+    P.cap = (size_t)max_records;
+    P.n = 0;
+    P.open = false;
+    P.on = true;
+    return 0;
+}
+
+int es_profile_end(void) {
+    es::g_prof.on = false;
+    return 0;
+}
+
+int es_profile_collect(int32_t* kinds_host, float* ms_host, int capacity, int* n_out) {
+    ES_CHECK(kinds_host && ms_host && n_out, "null argument");
+    auto& P = es::g_prof;
+    int n = (int)P.n < capacity ? (int)P.n : capacity;
+    for (int i = 0; i < n; ++i) {
+        ES_CUDA(cudaEventSynchronize(P.ev1[i]));
+        float ms = 0.f;
+        ES_CUDA(cudaEventElapsedTime(&ms, P.ev0[i], P.ev1[i]));
+        kinds_host[i] = P.kinds[i];
+        ms_host[i] = ms;
+    }
+    *n_out = n;
+    return 0;
+}
 
 int es_model_create(const es_config_t* cfg, const es_weights_t* w, es_model_t** out) {
     ES_CHECK(cfg && w && out, "null argument");
@@ -205,30 +272,33 @@ int es_encoder_forward(es_model_t* m, void* stream, int B, int N,
     const int d = m->d, n1 = enc_n1(m, N);
 
     // block 0: embedding + merge conv + 1x1 as k table gathers (networks.py:54,64-67)
-    if (launch_embed_merge(phoneme, m->w.enc[0].merge_w, e.x0, B, N, m->C[0], m->k[0], m->cfg.n_symbols, s)) return 1;
+    { ProfRange r(ES_K_EMBED, s); if (launch_embed_merge(phoneme, m->w.enc[0].merge_w, e.x0, B, N, m->C[0], m->k[0], m->cfg.n_symbols, s)) return 1; }
     if (encoder_block(m, 0, B, N, e.x0, phoneme_mask, e, e.feat0, s)) return 1;
     // block 1 merge: Conv1d(d,d,k-2,stride 2) . Conv1d(d,2d,1) folded (networks.py:64-67)
     {
         RowGemmParams p = base_params(B, N, n1, m->C[0], m->C[1], e.feat0, m->C[0], m->w.enc[1].merge_w, e.xm1, m->C[1]);
         p.taps = m->k[1]; p.stride = 2; p.pad = m->k[1] / 2;
+        ProfRange r(ES_K_ENC_GEMM, s);
         if (launch_rowgemm(p, s)) return 1;
     }
     const uint8_t* mask1 = nullptr;
     if (phoneme_mask) {
         // pool = round(N / n1), torch.round of an fp32 tensor: half-to-even (networks.py:69-70)
         const int pool = (int)nearbyintf((float)((double)N / (double)n1));
-        if (launch_pool_mask(phoneme_mask, e.mask1, B, N, n1, pool, s)) return 1;
+        { ProfRange r(ES_K_POOLMASK, s); if (launch_pool_mask(phoneme_mask, e.mask1, B, N, n1, pool, s)) return 1; }
         mask1 = e.mask1;
     }
     if (encoder_block(m, 1, B, n1, e.xm1, mask1, e, e.feat1, s)) return 1;
     // fuse (networks.py:189-219)
-    if (launch_fuse(e.feat0, e.feat1, m->w.fuse_a0, m->w.fuse_g, m->w.fuse_gb, m->w.fuse_c, phoneme_mask,
-                    e.fused, B, N, n1, d, m->k[0], s)) return 1;
+    { ProfRange r(ES_K_FUSE, s);
+      if (launch_fuse(e.feat0, e.feat1, m->w.fuse_a0, m->w.fuse_g, m->w.fuse_gb, m->w.fuse_c, phoneme_mask,
+                      e.fused, B, N, n1, d, m->k[0], s)) return 1; }
     // predictors (networks.py:349,357,366)
     if (predictor(m, m->w.pitch, B, N, e.fused, e.y1, pitch_pred, false, nullptr, s)) return 1;
     if (predictor(m, m->w.energy, B, N, e.fused, e.y1, energy_pred, false, nullptr, s)) return 1;
     if (predictor(m, m->w.duration, B, N, e.fused, e.y1, dur_pred, true, e.dur_feat, s)) return 1;
     // variance embeddings, concat, duration rounding, integer scan (networks.py:349-384, 234, 255)
+    ProfRange r(ES_K_VARIANCE, s);
     return launch_variance_scan(e.fused, e.dur_feat, pitch_pred, energy_pred, dur_pred, pitch_tgt, energy_tgt,
                                 dur_tgt, phoneme_mask, m->w.pitch, m->w.energy, fused4, dur_int, dur_cum,
                                 mel_len, B, N, d, s);
@@ -240,6 +310,7 @@ int es_length_regulate(es_model_t* m, void* stream, int B, int N, int T,
     ES_CHECK(m, "null model");
     ES_CHECK(B >= 1 && N >= 1 && T >= 0, "bad shape");
     ES_CHECK(dur_cum && (fused4 || !features), "null tensor");
+    ProfRange r(ES_K_LENREG, static_cast<cudaStream_t>(stream));
     return launch_length_regulate(fused4, dur_cum, phoneme_mask, features, frame_mask, src, B, N, T, m->dx4,
                                   static_cast<cudaStream_t>(stream));
 }
@@ -256,7 +327,7 @@ int es_decoder_forward(es_model_t* m, void* stream, int B, int T, const float* f
     // skip = LN(tanh(Linear(features)))                                           networks.py:292
     RowGemmParams p = base_params(B, T, T, m->dx4, m->dx2, features, m->dx4, m->w.dproj_w, db.buf[0], m->dx2);
     p.bias = m->w.dproj_b; p.act1 = ACT_TANH; p.ln_g = m->w.dproj_ln_g; p.ln_b = m->w.dproj_ln_b;
-    if (launch_rowgemm(p, s)) return 1;
+    { ProfRange r(ES_K_DEC_PROJ, s); if (launch_rowgemm(p, s)) return 1; }
     return decoder_layers(m, B, T, db, 0, nullptr, mel, s);
 }
 
@@ -274,7 +345,7 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
     RowGemmParams p = base_params(B, N, T, m->dx4, m->dx2, fused4, m->dx4, m->w.dproj_w, db.buf[0], m->dx2);
     p.mode = ROW_GATHER; p.cum = dur_cum; p.valid_len = mel_len;
     p.bias = m->w.dproj_b; p.act1 = ACT_TANH; p.ln_g = m->w.dproj_ln_g; p.ln_b = m->w.dproj_ln_b;
-    if (launch_rowgemm(p, s)) return 1;
+    { ProfRange r(ES_K_DEC_PROJ, s); if (launch_rowgemm(p, s)) return 1; }
     return decoder_layers(m, B, T, db, 0, zero_padded_frames ? mel_len : nullptr, mel, s);
 }
 
@@ -299,7 +370,7 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
             if (l == m->cfg.block_depth - 1) {       // skip = LN_blk(x + skip)   networks.py:299
                 p.res2 = db.buf[s_idx]; p.ldr2 = C; p.ln2_g = m->w.blk_ln_g[blk]; p.ln2_b = m->w.blk_ln_b[blk];
             }
-            if (launch_rowgemm(p, s)) return 1;
+            { ProfRange r(ES_K_DEC_LAYER, s); if (launch_rowgemm(p, s)) return 1; }
             in_idx = out_idx;
         }
         s_idx = in_idx;
@@ -307,6 +378,7 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
     // mel = Linear(skip); padded frames zeroed                                      networks.py:302, :424-427
     RowGemmParams p = base_params(B, T, T, C, m->cfg.n_mel, db.buf[s_idx], C, m->w.mel_w, mel, m->cfg.n_mel);
     p.bias = m->w.mel_b; p.zero_from = zero_from;
+    ProfRange r(ES_K_MEL, s);
     return launch_rowgemm(p, s);
 }
 

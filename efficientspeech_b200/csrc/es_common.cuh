@@ -42,6 +42,15 @@ extern std::atomic<uint64_t> g_launches;
         ES_CUDA(cudaGetLastError());                                          \
     } while (0)
 
+// ---- optional per-launch event timing (es_profile_*) --------------------------------------
+void prof_begin_range(int kind, cudaStream_t s);
+void prof_end_range(cudaStream_t s);
+struct ProfRange {
+    cudaStream_t s;
+    ProfRange(int kind, cudaStream_t st) : s(st) { prof_begin_range(kind, st); }
+    ~ProfRange() { prof_end_range(s); }
+};
+
 // ---- activations -----------------------------------------------------------------------
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_TANH = 3 };
 

@@ -24,6 +24,7 @@ namespace {
 constexpr int BM = 64;          // rows per CTA
 constexpr int NTHREADS = 256;   // 8 warps x 8 rows
 constexpr int RPW = 8;          // rows per warp
+constexpr int kMaxKChunk = 512; // K staged per pass in PLAIN mode
 
 template <int NJ>
 __global__ void __launch_bounds__(NTHREADS)
@@ -33,23 +34,17 @@ rowgemm_kernel(const RowGemmParams p) {
     const int b = blockIdx.z;
     const int t0 = blockIdx.x * BM;
     const int col_base = blockIdx.y * (32 * NJ);
-    const int K = p.K, K4 = K >> 2;
-    const int lds = K + 4;
+    const int K = p.K;
+    // PLAIN mode streams K in chunks of KC (one chunk for every layer but the widest projections);
+    // GATHER / DWCONV stage the whole K at once (their K is the decoder width, <= 512).
+    const int KC = (p.mode == ROW_PLAIN && K > kMaxKChunk) ? kMaxKChunk : K;
+    const int K4 = KC >> 2;
+    const int lds = KC + 4;
     float* As = smem;
 
     // ------------------------------------------------------------------ prologue
     if (p.mode == ROW_PLAIN) {
-        const int rows_in = (BM - 1) * p.stride + p.taps;
-        const int first = t0 * p.stride - p.pad;
-        const float* Ab = p.A + (size_t)b * p.n_in * p.lda;
-        for (int idx = tid; idx < rows_in * K4; idx += NTHREADS) {
-            const int r = idx / K4, c4 = idx - r * K4;
-            const int t_in = first + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t_in >= 0 && t_in < p.n_in)
-                v = __ldg(reinterpret_cast<const float4*>(Ab + (size_t)t_in * p.lda) + c4);
-            *reinterpret_cast<float4*>(As + r * lds + c4 * 4) = v;
-        }
+        // staged per K chunk inside the main loop
     } else if (p.mode == ROW_GATHER) {
         int* srcs = reinterpret_cast<int*>(smem + BM * lds);
         if (tid < BM) {
@@ -99,7 +94,6 @@ rowgemm_kernel(const RowGemmParams p) {
             As[r * lds + c] = acc;
         }
     }
-    __syncthreads();
 
     // ------------------------------------------------------------------ main loop
     float acc[RPW][NJ];
@@ -115,10 +109,26 @@ rowgemm_kernel(const RowGemmParams p) {
     const int r0 = warp * RPW;
     const int taps = (p.mode == ROW_PLAIN) ? p.taps : 1;
     const int stride = (p.mode == ROW_PLAIN) ? p.stride : 1;
+    for (int kc0 = 0; kc0 < K; kc0 += KC) {
+    if (p.mode == ROW_PLAIN) {
+        if (kc0 > 0) __syncthreads();              // previous chunk fully consumed
+        const int rows_in = (BM - 1) * p.stride + p.taps;
+        const int first = t0 * p.stride - p.pad;
+        const float* Ab = p.A + (size_t)b * p.n_in * p.lda + kc0;
+        for (int idx = tid; idx < rows_in * K4; idx += NTHREADS) {
+            const int r = idx / K4, c4 = idx - r * K4;
+            const int t_in = first + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t_in >= 0 && t_in < p.n_in)
+                v = __ldg(reinterpret_cast<const float4*>(Ab + (size_t)t_in * p.lda) + c4);
+            *reinterpret_cast<float4*>(As + r * lds + c4 * 4) = v;
+        }
+    }
+    __syncthreads();
     for (int tap = 0; tap < taps; ++tap) {
-        const float* Wt = p.W + (size_t)tap * K * p.ldw + col_base + lane;
+        const float* Wt = p.W + ((size_t)tap * K + kc0) * p.ldw + col_base + lane;
         const float* Arow = As + (r0 * stride + tap) * lds;
-        for (int k4 = 0; k4 < K; k4 += 4) {
+        for (int k4 = 0; k4 < KC; k4 += 4) {
             float4 a[RPW];
 #pragma unroll
             for (int r = 0; r < RPW; ++r)
@@ -138,6 +148,7 @@ rowgemm_kernel(const RowGemmParams p) {
             }
         }
     }
+    }  // K chunks
 
     // ------------------------------------------------------------------ epilogue (per row, in registers)
     float bias[NJ], g1[NJ], b1[NJ], g2[NJ], b2[NJ], dw[NJ];
@@ -255,7 +266,9 @@ int launch_rowgemm(const RowGemmParams& p, cudaStream_t stream) {
     const bool needs_full_row = p.ln_g || p.res2 || p.dot_out;
     ES_CHECK(!needs_full_row || col_tiles == 1, "LayerNorm / scalar head need Nout <= 256");
     ES_CHECK(!(p.res2 && !p.ln2_g), "res2 requires ln2");
-    const int lds = p.K + 4;
+    const int KC = (p.mode == ROW_PLAIN && p.K > kMaxKChunk) ? kMaxKChunk : p.K;
+    ES_CHECK(p.K % KC == 0, "K must be a multiple of 512 when larger than 512");
+    const int lds = KC + 4;
     size_t smem;
     if (p.mode == ROW_PLAIN) {
         ES_CHECK(p.taps >= 1 && p.taps <= ES_MAX_TAPS && (p.stride == 1 || p.stride == 2), "bad taps/stride");

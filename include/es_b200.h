@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ES_ABI_VERSION 3
+#define ES_ABI_VERSION 4
 #define ES_MAX_ENC_BLOCKS 2
 #define ES_MAX_DEC_LAYERS 24
 #define ES_MAX_DEC_BLOCKS 8
@@ -189,6 +189,25 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
 
 /* Number of kernels the library has launched since process start (bench.py's gpu_launches). */
 uint64_t es_launch_count(void);
+
+/* Per-kernel device timing for bench.py's roofline: between es_profile_begin and
+ * es_profile_end every launch is bracketed by CUDA events on the launching stream.
+ * es_profile_collect synchronises the recorded events and copies (kind, milliseconds)
+ * pairs to HOST arrays; kinds are the ES_K_* values below. */
+#define ES_K_EMBED      0
+#define ES_K_ENC_GEMM   1
+#define ES_K_ATTENTION  2
+#define ES_K_FUSE       3
+#define ES_K_PREDICTOR  4
+#define ES_K_VARIANCE   5
+#define ES_K_LENREG     6
+#define ES_K_DEC_PROJ   7
+#define ES_K_DEC_LAYER  8
+#define ES_K_MEL        9
+#define ES_K_POOLMASK   10
+int es_profile_begin(int max_records);
+int es_profile_end(void);
+int es_profile_collect(int32_t* kinds_host, float* ms_host, int capacity, int* n_out);
 
 /* Self-test of the tcgen05/TMA building block: C[M,N] = A[M,K] B[N,K]^T with split-fp16
  * operands (3 MMAs), M multiple of 128, N in {128,256}, K multiple of 64.  fp32 in/out. */
