@@ -8,7 +8,7 @@ from typing import Optional
 
 from . import build as _build
 
-ES_ABI_VERSION = 4
+ES_ABI_VERSION = 5
 ES_MAX_ENC_BLOCKS = 2
 ES_MAX_DEC_LAYERS = 24
 ES_MAX_DEC_BLOCKS = 8
@@ -48,7 +48,7 @@ class es_weights_t(C.Structure):
         ("dproj_w", _fp), ("dproj_b", _fp), ("dproj_ln_g", _fp), ("dproj_ln_b", _fp),
         ("dec", es_dec_layer_w_t * ES_MAX_DEC_LAYERS),
         ("blk_ln_g", _fp * ES_MAX_DEC_BLOCKS), ("blk_ln_b", _fp * ES_MAX_DEC_BLOCKS),
-        ("mel_w", _fp), ("mel_b", _fp),
+        ("mel_w", _fp), ("mel_b", _fp), ("dproj_w_h16", _fp), ("mel_w_h16", _fp),
     ]
 
 
@@ -65,6 +65,7 @@ PROTOTYPES = {
     "es_length_regulate": (_i, [_vp, _vp, _i, _i, _i] + [_vp] * 6),
     "es_decoder_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _sz]),
     "es_decoder_forward_gathered": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz]),
+    "es_check_async_errors": (_i, [_vp]),
     "es_launch_count": (C.c_uint64, []),
     "es_profile_begin": (_i, [_i]),
     "es_profile_end": (_i, []),

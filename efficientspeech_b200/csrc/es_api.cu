@@ -173,6 +173,7 @@ extern "C" {
 int es_abi_version(void) { return ES_ABI_VERSION; }
 const char* es_last_error(void) { return es::g_error.c_str(); }
 uint64_t es_launch_count(void) { return es::g_launches.load(); }
+int es_check_async_errors(void* stream) { return es::umma_dec_check_errors(static_cast<cudaStream_t>(stream)); }
 
 int es_profile_begin(int max_records) {
     ES_CHECK(max_records > 0 && max_records <= (1 << 20), "bad record count");
@@ -325,6 +326,14 @@ int es_decoder_forward(es_model_t* m, void* stream, int B, int T, const float* f
     Arena a(reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256)));
     DecBufs db = plan_decoder(m, a, B, T);
     // skip = LN(tanh(Linear(features)))                                           networks.py:292
+    if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx4 == 128 &&
+        umma_dec_supported(m->dx2, m->cfg.decoder_kernel_size, m->dx2)) {
+        { ProfRange r(ES_K_DEC_PROJ, s);
+          if (launch_umma_dec(2, B, T, m->dx2, 0, features, nullptr, nullptr, nullptr, nullptr, m->w.dproj_w_h16,
+                              m->w.dproj_b, 1, m->w.dproj_ln_g, m->w.dproj_ln_b, nullptr, nullptr, nullptr,
+                              nullptr, db.buf[0], s)) return 1; }
+        return decoder_layers(m, B, T, db, 0, nullptr, mel, s);
+    }
     RowGemmParams p = base_params(B, T, T, m->dx4, m->dx2, features, m->dx4, m->w.dproj_w, db.buf[0], m->dx2);
     p.bias = m->w.dproj_b; p.act1 = ACT_TANH; p.ln_g = m->w.dproj_ln_g; p.ln_b = m->w.dproj_ln_b;
     { ProfRange r(ES_K_DEC_PROJ, s); if (launch_rowgemm(p, s)) return 1; }
@@ -342,6 +351,14 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
     Arena a(reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256)));
     DecBufs db = plan_decoder(m, a, B, T);
     // length-regulator gather fused into the projection's operand load (networks.py:228-258, :292)
+    if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx4 == 128 &&
+        umma_dec_supported(m->dx2, m->cfg.decoder_kernel_size, m->dx2)) {
+        { ProfRange r(ES_K_DEC_PROJ, s);
+          if (launch_umma_dec(1, B, T, m->dx2, N, fused4, dur_cum, mel_len, nullptr, nullptr, m->w.dproj_w_h16,
+                              m->w.dproj_b, 1, m->w.dproj_ln_g, m->w.dproj_ln_b, nullptr, nullptr, nullptr,
+                              nullptr, db.buf[0], s)) return 1; }
+        return decoder_layers(m, B, T, db, 0, zero_padded_frames ? mel_len : nullptr, mel, s);
+    }
     RowGemmParams p = base_params(B, N, T, m->dx4, m->dx2, fused4, m->dx4, m->w.dproj_w, db.buf[0], m->dx2);
     p.mode = ROW_GATHER; p.cum = dur_cum; p.valid_len = mel_len;
     p.bias = m->w.dproj_b; p.act1 = ACT_TANH; p.ln_g = m->w.dproj_ln_g; p.ln_b = m->w.dproj_ln_b;
@@ -364,6 +381,16 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
             int out_idx = 0;
             while (out_idx == s_idx || out_idx == in_idx) ++out_idx;
             const es_dec_layer_w_t& w = m->w.dec[layer];
+            const bool last = (l == m->cfg.block_depth - 1);
+            if (m->use_tensor_core && w.pw_w_h16 && umma_dec_supported(C, m->cfg.decoder_kernel_size, C)) {
+                ProfRange r(ES_K_DEC_LAYER, s);
+                if (launch_umma_dec(0, B, T, C, 0, db.buf[in_idx], nullptr, nullptr, w.dw_w, w.dw_b, w.pw_w_h16,
+                                    w.pw_b, 1, w.ln_g, w.ln_b, last ? db.buf[s_idx] : nullptr,
+                                    last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
+                                    nullptr, db.buf[out_idx], s)) return 1;
+                in_idx = out_idx;
+                continue;
+            }
             RowGemmParams p = base_params(B, T, T, C, C, db.buf[in_idx], C, w.pw_w, db.buf[out_idx], C);
             p.mode = ROW_DWCONV; p.dw_w = w.dw_w; p.dw_b = w.dw_b; p.dw_k = m->cfg.decoder_kernel_size;
             p.bias = w.pw_b; p.act1 = ACT_TANH; p.ln_g = w.ln_g; p.ln_b = w.ln_b;
@@ -376,6 +403,13 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
         s_idx = in_idx;
     }
     // mel = Linear(skip); padded frames zeroed                                      networks.py:302, :424-427
+    if (m->use_tensor_core && m->w.mel_w_h16 && m->cfg.n_mel == 80 &&
+        umma_dec_supported(C, m->cfg.decoder_kernel_size, m->cfg.n_mel)) {
+        ProfRange r(ES_K_MEL, s);
+        return launch_umma_dec(2, B, T, m->cfg.n_mel, 0, db.buf[s_idx], nullptr, nullptr, nullptr, nullptr,
+                               m->w.mel_w_h16, m->w.mel_b, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                               zero_from, mel, s);
+    }
     RowGemmParams p = base_params(B, T, T, C, m->cfg.n_mel, db.buf[s_idx], C, m->w.mel_w, mel, m->cfg.n_mel);
     p.bias = m->w.mel_b; p.zero_from = zero_from;
     ProfRange r(ES_K_MEL, s);

@@ -20,4 +20,13 @@ int launch_variance_scan(const float* fused, const float* dur_feat, const float*
 int launch_length_regulate(const float* fused4, const int32_t* cum, const uint8_t* pmask, float* feats,
                            uint8_t* fmask, int32_t* src, int B, int N, int T, int C, cudaStream_t s);
 
+// tcgen05 decoder kernel (es_umma_dec.cu)
+bool umma_dec_supported(int C, int dw_k, int N);
+int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, const int* cum,
+                    const int* valid_len, const float* dw_w, const float* dw_b, const void* w_h16,
+                    const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
+                    const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
+                    float* Y, cudaStream_t s);
+int umma_dec_check_errors(cudaStream_t s);
+
 }  // namespace es

@@ -172,9 +172,11 @@ class _Backend:
         sd = self._state()
         folded = packing.fold_encoder(sd, self.cfg) if self.part == "encoder" else packing.fold_decoder(sd, self.cfg)
         if self.part == "decoder":
+            # B operands of the tcgen05 kernels: W as [N][K], split into fp16 hi/lo, canonical order
             for l in range(self.cfg.n_dec_layers):
-                w = folded[f"dec{l}.pw_w"][0].T          # [N][K], K contiguous: the UMMA B operand
-                folded[f"dec{l}.pw_w_h16"] = packing.split_fp16(np.ascontiguousarray(w))
+                folded[f"dec{l}.pw_w_h16"] = packing.canon_split_fp16(folded[f"dec{l}.pw_w"][0].T)
+            folded["dproj_w_h16"] = packing.canon_split_fp16(folded["dproj_w"][0].T)
+            folded["mel_w_h16"] = packing.canon_split_fp16(folded["mel_w"][0].T[:self.cfg.n_mel])
         flat_np, off = packing.pack(folded)
         self.flat = torch.from_numpy(flat_np).to(device)
         base = self.flat.data_ptr()
@@ -196,7 +198,7 @@ class _Backend:
                         continue
                     setattr(pw, f, at(f"{which}.{f}"))
         else:
-            for f in ("dproj_w", "dproj_b", "dproj_ln_g", "dproj_ln_b", "mel_w", "mel_b"):
+            for f in ("dproj_w", "dproj_b", "dproj_ln_g", "dproj_ln_b", "mel_w", "mel_b", "dproj_w_h16", "mel_w_h16"):
                 setattr(W, f, at(f))
             for l in range(self.cfg.n_dec_layers):
                 for f, _ in _cabi.es_dec_layer_w_t._fields_:
@@ -411,6 +413,14 @@ class Phoneme2Mel(nn.Module):
 
     def set_tensor_core(self, enable: bool) -> None:
         self.decoder.set_tensor_core(enable)
+
+    @staticmethod
+    def check_async_errors(device=None) -> None:
+        """Synchronise the current stream and raise if a tcgen05 kernel reported an mbarrier timeout
+        (the kernels bound every wait instead of hanging the GPU)."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.load().es_check_async_errors(_stream(dev)))
 
     def forward(self, x, train=False):
         if isinstance(x, list):                                         # networks.py:418

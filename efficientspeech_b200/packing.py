@@ -139,6 +139,19 @@ def split_fp16(w: np.ndarray) -> np.ndarray:
     return both.view(np.float32)
 
 
+def canon_split_fp16(w_nk: np.ndarray) -> np.ndarray:
+    """[N][K] fp32 weight -> split-fp16 image in the UMMA canonical K-major no-swizzle order
+    ``[2 (hi, lo)][K/8][N][8]`` (8x8 core matrices of 128 contiguous bytes; es_umma.cuh), so the
+    kernel's weight load is a straight bulk copy.  Returned as raw fp32 words for the flat buffer."""
+    w32 = np.ascontiguousarray(w_nk, dtype=np.float32)
+    n, k = w32.shape
+    assert k % 8 == 0
+    hi = w32.astype(np.float16)
+    lo = (w32 - hi.astype(np.float32)).astype(np.float16)
+    planes = np.stack([hi, lo]).reshape(2, n, k // 8, 8).transpose(0, 2, 1, 3)
+    return np.ascontiguousarray(planes).reshape(-1).view(np.float32)
+
+
 def pack(folded: Dict[str, np.ndarray]) -> Tuple[np.ndarray, Dict[str, int]]:
     """Concatenate the folded arrays (fp32, 256-byte aligned) -> (flat buffer, element offsets)."""
     offsets: Dict[str, int] = {}

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ES_ABI_VERSION 4
+#define ES_ABI_VERSION 5
 #define ES_MAX_ENC_BLOCKS 2
 #define ES_MAX_DEC_LAYERS 24
 #define ES_MAX_DEC_BLOCKS 8
@@ -94,8 +94,8 @@ typedef struct es_dec_layer_w {     /* networks.py:279-283 */
     const float* pw_b;
     const float* ln_g;
     const float* ln_b;
-    /* split-fp16 image of pw_w for the tcgen05 kernel: [2][dx2(N)][dx2(K)] halves, hi then lo,
-     * K contiguous (NULL -> SIMT kernel is used) */
+    /* split-fp16 image of pw_w for the tcgen05 kernel in the UMMA canonical K-major no-swizzle
+     * order: [2 (hi, lo)][K/8][N][8] halves (NULL -> the SIMT kernel is used) */
     const void*  pw_w_h16;
 } es_dec_layer_w_t;
 
@@ -119,6 +119,8 @@ typedef struct es_weights {
     const float* blk_ln_b[ES_MAX_DEC_BLOCKS];
     const float* mel_w;      /* [1][dx2][96] */
     const float* mel_b;      /* [96] */
+    const void*  dproj_w_h16; /* canonical split-fp16 image of dproj_w ([2][dx4/8][dx2][8]) or NULL */
+    const void*  mel_w_h16;   /* canonical split-fp16 image of mel_w   ([2][dx2/8][n_mel][8]) or NULL */
 } es_weights_t;
 
 typedef struct es_model es_model_t;   /* opaque */
@@ -186,6 +188,10 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
                                 const float* fused4, const int32_t* dur_cum, const int32_t* mel_len,
                                 int zero_padded_frames, float* mel,
                                 void* workspace, size_t workspace_bytes);
+
+/* The tcgen05 kernels bound every mbarrier wait; a timeout sets a device flag instead of hanging
+ * the GPU.  This call synchronises `stream` and returns non-zero if the flag was raised. */
+int es_check_async_errors(void* stream);
 
 /* Number of kernels the library has launched since process start (bench.py's gpu_launches). */
 uint64_t es_launch_count(void);

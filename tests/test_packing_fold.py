@@ -49,6 +49,10 @@ def test_pack_layout_and_split_fp16():
         assert off[k] % packing.ALIGN == 0
         assert np.array_equal(flat[off[k]:off[k] + v.size], np.asarray(v, np.float32).reshape(-1))
     assert F["mel_w"].shape == (1, cfg.dx2, 96) and F["mel_b"].shape == (96,)
-    w = F["dec0.pw_w"][0].astype(np.float32)
-    halves = packing.split_fp16(w).view(np.float16).reshape(2, *w.shape).astype(np.float64)
-    assert np.abs(halves[0] + halves[1] - w).max() < 2e-7
+    w = F["dec0.pw_w"][0].T.astype(np.float32)                    # [N][K]
+    n, k = w.shape
+    img = packing.canon_split_fp16(w).view(np.float16).reshape(2, k // 8, n, 8)
+    # canonical K-major no-swizzle order: element (row n, col kk) lives at [kk // 8][n][kk % 8]
+    back = img.transpose(0, 2, 1, 3).reshape(2, n, k).astype(np.float64)
+    assert np.abs(back[0] + back[1] - w).max() < 2e-7
+    assert np.array_equal(back[0].astype(np.float16), w.astype(np.float16))
