@@ -72,13 +72,15 @@ struct UmmaDecParams {
     int* err;                    // device error flag (mbarrier timeout)
 };
 
-__device__ __forceinline__ float tanh_fast(float x) {
-    // tanh(|x|) = (1 - e) / (1 + e), e = exp(-2|x|) = 2^(-2 log2(e) |x|); absolute error ~1e-7
-    const float ax = fabsf(x);
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * -2.8853900817779268f));
-    const float r = __fdividef(1.f - e, 1.f + e);
-    return copysignf(r, x);
+// tanh(x) = 1 - 2 / (1 + e^{2x}) with e^{2x} = 2^{x * 2 log2(e)}: two MUFU ops (ex2, rcp) and two FMAs.
+// The argument arrives pre-scaled (acc * c + bias * c, c = 2 log2 e).  Saturates correctly at
+// +-inf (ex2 -> inf -> rcp -> 0 -> 1; ex2 -> 0 -> rcp(1) -> -1); absolute error ~1.2e-7.
+constexpr float kTanhScale = 2.8853900817779268f;
+__device__ __forceinline__ float tanh_from_scaled(float arg) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    return fmaf(-2.f, r, 1.f);
 }
 
 __device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) {
@@ -125,7 +127,7 @@ umma_dec_kernel(const UmmaDecParams p) {
         fence_mbar_init();
     }
     for (int i = tid; i < 128; i += NTHR) {
-        par[i] = (i < N) ? __ldg(p.bias + i) : 0.f;
+        par[i] = (i < N) ? __ldg(p.bias + i) * (p.act_tanh ? kTanhScale : 1.f) : 0.f;   // pre-scaled for tanh
         par[128 + i] = (p.ln_g && i < N) ? __ldg(p.ln_g + i) : 0.f;
         par[256 + i] = (p.ln_g && i < N) ? __ldg(p.ln_b + i) : 0.f;
         par[384 + i] = (p.ln2_g && i < N) ? __ldg(p.ln2_g + i) : 0.f;
@@ -272,9 +274,16 @@ umma_dec_kernel(const UmmaDecParams p) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 bb = *reinterpret_cast<const float4*>(par + cq * 32 + j * 4);
-                    float4 v = make_float4(__uint_as_float(r[4 * j]) + bb.x, __uint_as_float(r[4 * j + 1]) + bb.y,
-                                           __uint_as_float(r[4 * j + 2]) + bb.z, __uint_as_float(r[4 * j + 3]) + bb.w);
-                    if (p.act_tanh) { v.x = tanh_fast(v.x); v.y = tanh_fast(v.y); v.z = tanh_fast(v.z); v.w = tanh_fast(v.w); }
+                    float4 v;
+                    if (p.act_tanh) {
+                        v.x = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j]), kTanhScale, bb.x));
+                        v.y = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j + 1]), kTanhScale, bb.y));
+                        v.z = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j + 2]), kTanhScale, bb.z));
+                        v.w = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j + 3]), kTanhScale, bb.w));
+                    } else {
+                        v = make_float4(__uint_as_float(r[4 * j]) + bb.x, __uint_as_float(r[4 * j + 1]) + bb.y,
+                                        __uint_as_float(r[4 * j + 2]) + bb.z, __uint_as_float(r[4 * j + 3]) + bb.w);
+                    }
                     const int chunk = cq * 8 + j;
                     *reinterpret_cast<float4*>(stg + (uint32_t)row * STG_ROW + (uint32_t)((chunk ^ (row & 7)) * 16)) = v;
                 }
@@ -284,40 +293,98 @@ umma_dec_kernel(const UmmaDecParams p) {
         __syncthreads();
         tc_fence_after_sync();
 
-        // ---------------------------------------------------------------- epilogue B: warp per row
+        // ---------------------------------------------------------------- epilogue B
+        // 4 rows per warp step, 8 lanes per row, 16 channels per lane (16-byte chunks part + 8j):
+        // LayerNorm statistics need 3 shuffle steps for 4 rows at once, every global access is a
+        // full 128-byte line per 8-lane group.
         {
-            const int nl = N >> 2;                            // active lanes (16-byte chunks per row)
-            const bool act = lane < nl;
+            const int rr = lane >> 3, part = lane & 7;
+            const int nl = N >> 2;                            // 16-byte chunks per row
             const float inv_n = 1.f / (float)N;
             const int zero_from = p.zero_from ? p.zero_from[b] : 0x7fffffff;
-            for (int row = warp; row < rows_valid; row += NTHR / 32) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (act) v = *reinterpret_cast<const float4*>(stg + (uint32_t)row * STG_ROW + (uint32_t)((lane ^ (row & 7)) * 16));
+#pragma unroll 1
+            for (int rbase = warp * 4; rbase < TM; rbase += (NTHR / 32) * 4) {
+                const int row = rbase + rr;
+                const bool rvalid = row < rows_valid;
                 const size_t grow = (size_t)b * p.T + t0 + row;
+                float4 v[4];
+                bool cv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    cv[j] = (part + 8 * j) < nl;
+                    v[j] = cv[j] ? *reinterpret_cast<const float4*>(stg + (uint32_t)row * STG_ROW +
+                                                                    (uint32_t)((8 * j + (part ^ (row & 7))) * 16))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 if (p.ln_g) {
-                    const float mean = warp_sum(v.x + v.y + v.z + v.w) * inv_n;
-                    float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dwv = v.w - mean;
-                    if (!act) { dx = dy = dz = dwv = 0.f; }
-                    const float rstd = 1.f / sqrtf(warp_sum(dx * dx + dy * dy + dz * dz + dwv * dwv) * inv_n + kLnEps);
-                    const float4 g = *reinterpret_cast<const float4*>(par + 128 + lane * 4);
-                    const float4 be = *reinterpret_cast<const float4*>(par + 256 + lane * 4);
-                    v = make_float4(dx * rstd * g.x + be.x, dy * rstd * g.y + be.y, dz * rstd * g.z + be.z, dwv * rstd * g.w + be.w);
+                    float sm = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sm += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+                    sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+                    sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+                    sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+                    const float mean = sm * inv_n;
+                    float q = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+                        if (!cv[j]) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        q = fmaf(v[j].x, v[j].x, q); q = fmaf(v[j].y, v[j].y, q);
+                        q = fmaf(v[j].z, v[j].z, q); q = fmaf(v[j].w, v[j].w, q);
+                    }
+                    q += __shfl_xor_sync(0xffffffffu, q, 1);
+                    q += __shfl_xor_sync(0xffffffffu, q, 2);
+                    q += __shfl_xor_sync(0xffffffffu, q, 4);
+                    const float rstd = rsqrtf(q * inv_n + kLnEps);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 g = *reinterpret_cast<const float4*>(par + 128 + (part + 8 * j) * 4);
+                        const float4 be = *reinterpret_cast<const float4*>(par + 256 + (part + 8 * j) * 4);
+                        v[j] = make_float4(fmaf(v[j].x * rstd, g.x, be.x), fmaf(v[j].y * rstd, g.y, be.y),
+                                           fmaf(v[j].z * rstd, g.z, be.z), fmaf(v[j].w * rstd, g.w, be.w));
+                    }
                 }
                 if (p.res2) {
-                    if (act) {
-                        const float4 s = __ldg(reinterpret_cast<const float4*>(p.res2 + grow * N) + lane);
-                        v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+                    float sm = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (cv[j] && rvalid) {
+                            const float4 sk = __ldg(reinterpret_cast<const float4*>(p.res2 + grow * N) + part + 8 * j);
+                            v[j].x += sk.x; v[j].y += sk.y; v[j].z += sk.z; v[j].w += sk.w;
+                        }
+                        sm += (v[j].x + v[j].y) + (v[j].z + v[j].w);
                     }
-                    const float mean = warp_sum(v.x + v.y + v.z + v.w) * inv_n;
-                    float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dwv = v.w - mean;
-                    if (!act) { dx = dy = dz = dwv = 0.f; }
-                    const float rstd = 1.f / sqrtf(warp_sum(dx * dx + dy * dy + dz * dz + dwv * dwv) * inv_n + kLnEps);
-                    const float4 g = *reinterpret_cast<const float4*>(par + 384 + lane * 4);
-                    const float4 be = *reinterpret_cast<const float4*>(par + 512 + lane * 4);
-                    v = make_float4(dx * rstd * g.x + be.x, dy * rstd * g.y + be.y, dz * rstd * g.z + be.z, dwv * rstd * g.w + be.w);
+                    sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+                    sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+                    sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+                    const float mean = sm * inv_n;
+                    float q = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+                        if (!cv[j]) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        q = fmaf(v[j].x, v[j].x, q); q = fmaf(v[j].y, v[j].y, q);
+                        q = fmaf(v[j].z, v[j].z, q); q = fmaf(v[j].w, v[j].w, q);
+                    }
+                    q += __shfl_xor_sync(0xffffffffu, q, 1);
+                    q += __shfl_xor_sync(0xffffffffu, q, 2);
+                    q += __shfl_xor_sync(0xffffffffu, q, 4);
+                    const float rstd = rsqrtf(q * inv_n + kLnEps);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 g = *reinterpret_cast<const float4*>(par + 384 + (part + 8 * j) * 4);
+                        const float4 be = *reinterpret_cast<const float4*>(par + 512 + (part + 8 * j) * 4);
+                        v[j] = make_float4(fmaf(v[j].x * rstd, g.x, be.x), fmaf(v[j].y * rstd, g.y, be.y),
+                                           fmaf(v[j].z * rstd, g.z, be.z), fmaf(v[j].w * rstd, g.w, be.w));
+                    }
                 }
-                if (t0 + row >= zero_from) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (act) reinterpret_cast<float4*>(p.Y + grow * N)[lane] = v;
+                if (rvalid) {
+                    const bool zero = (t0 + row) >= zero_from;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (cv[j]) reinterpret_cast<float4*>(p.Y + grow * N)[part + 8 * j] =
+                            zero ? make_float4(0.f, 0.f, 0.f, 0.f) : v[j];
+                }
             }
         }
         __syncthreads();                           // staging (== A region) free for the next tile
