@@ -1,22 +1,30 @@
-// Decoder-side fused tensor-core kernel (sm_100a, tcgen05 + TMEM + bulk-async copies).
+// Decoder-side fused tensor-core kernel (sm_100a: tcgen05 + TMEM + bulk-async copies),
+// warp-specialised and software-pipelined.
 //
-// One persistent CTA per SM walks 128-frame tiles of [B, T, 128] activations:
+// One persistent CTA per SM walks 128-frame tiles of [B, T, 128] activations.  Its 16 warps
+// form two groups that work on DIFFERENT tiles at the same time:
 //
-//   prologue   DWCONV  x tile (+2-frame halo) arrives by ONE bulk async copy (TMA 1-D, mbarrier
-//                      complete_tx); depthwise conv k=5 + bias in registers (sliding window)
-//              GATHER  the length regulator: row t <- fused4[b, upper_bound(cum[b], t)]
-//              PLAIN   rows copied as they are (mel head)
-//              -> split into fp16 hi/lo and written straight into the UMMA canonical K-major
-//                 no-swizzle operand layout (bank-conflict free, see es_umma.cuh)
-//   GEMM       24 x tcgen05.mma (M128 x N x K16, kind::f16; hi*hi + hi*lo + lo*hi) issued by one
-//              thread, fp32 accumulator in TMEM, completion signalled on an mbarrier by
-//              tcgen05.commit; the weights (split fp16, canonical layout prepared at pack time)
-//              are loaded ONCE per CTA and stay resident in shared memory
-//   epilogue A tcgen05.ld (thread = tile row) -> + bias -> tanh -> XOR-swizzled smem staging
-//   epilogue B warp per row: LayerNorm (shuffle reductions) [-> + skip -> LayerNorm] [-> zero
-//              padded frames] -> 512-byte coalesced global stores
+//   producer warps 8..15 (tile i+1)
+//       DWCONV  the x tile (+2-frame halo) arrives by ONE bulk async copy (TMA 1-D, mbarrier
+//               complete_tx); depthwise conv k=5 + bias in registers (sliding window)
+//       GATHER  the length regulator: row t <- fused4[b, upper_bound(cum[b], t)]
+//       PLAIN   rows copied as they are (mel head, stand-alone projection)
+//       -> split into fp16 hi/lo, written straight into the UMMA canonical K-major no-swizzle
+//          operand layout (bank-conflict free); then ONE thread issues 24 x tcgen05.mma
+//          (M128 x N x K16, kind::f16: hi*hi + hi*lo + lo*hi, fp32 accumulate) into one of
+//          TWO TMEM accumulators and commits to an mbarrier.  The split-fp16 weights (canonical
+//          layout prepared at pack time) are bulk-loaded ONCE per CTA and stay in shared memory.
+//   epilogue warps 0..7 (tile i)
+//       tcgen05.ld 16x256b: each warp owns 16 complete rows in the mma-fragment layout (4 threads
+//       per row), releases the accumulator right after the load, then runs bias -> tanh ->
+//       LayerNorm [-> + skip -> LayerNorm] [-> zero padded frames] in registers (2 shuffle steps
+//       per statistic) and stores 32-byte row segments straight to global memory.  No
+//       shared-memory staging, no CTA-wide barrier in steady state.
 //
-// The next tile's x is in flight (bulk copy) while the current tile runs its GEMM + epilogue.
+// mbarriers: bar_x (x tile landed), bar_mma[2] (accumulator s full == A operand free),
+// bar_tfree[2] (accumulator s drained by all 8 epilogue warps).  Every wait is bounded: a
+// timeout raises a device flag instead of hanging the GPU.
+//
 // HBM traffic per layer is exactly one read of x (+ skip on block-end layers) and one write of
 // y: the kernel is HBM-bound by design.
 #include "es_common.cuh"
@@ -33,23 +41,22 @@ constexpr int CK = 128;                 // K = input channels
 constexpr int DWK = 5;                  // depthwise taps
 constexpr int HALO = DWK / 2;
 constexpr int XROWS = TM + DWK - 1;     // 132
-constexpr int NTHR = 512;               // 16 warps
+constexpr int NTHR = 512;               // 16 warps: 0..7 epilogue, 8..15 producer
+constexpr int NPROD = 256;
 constexpr uint32_t A_LBO = 144;         // 128-byte core matrix + 16 B pad: conflict-free 8-byte lane stores
 constexpr uint32_t A_SBO = 16 * A_LBO;  // 2304: one 8-row group = 16 K-chunks
 constexpr uint32_t A_PLANE = 16 * A_SBO;            // 36864 bytes per fp16 plane (hi or lo)
 constexpr uint32_t XS_BYTES = XROWS * CK * 4;       // 67584
-constexpr uint32_t STG_ROW = 512;                   // staging row stride (bytes)
 
 // shared memory map (dynamic, 1024-aligned base)
 constexpr uint32_t OFF_XS = 0;
-constexpr uint32_t OFF_A = OFF_XS + XS_BYTES;                 // hi plane, then lo plane; reused as staging
+constexpr uint32_t OFF_A = OFF_XS + XS_BYTES;                 // hi plane, then lo plane
 constexpr uint32_t OFF_W = OFF_A + 2 * A_PLANE;               // W hi [K/8][N][8], then W lo
 constexpr uint32_t W_PLANE_MAX = 128 * CK * 2;                // 32768
 constexpr uint32_t OFF_PAR = OFF_W + 2 * W_PLANE_MAX;         // bias, ln g/b, ln2 g/b: 5 x 128 floats
 constexpr uint32_t OFF_SRC = OFF_PAR + 5 * 128 * 4;           // gather sources: 128 ints
-constexpr uint32_t OFF_BAR = OFF_SRC + 128 * 4;               // 3 mbarriers + tmem base
+constexpr uint32_t OFF_BAR = OFF_SRC + 128 * 4;               // 6 mbarriers + tmem base
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
-static_assert(2 * A_PLANE >= TM * STG_ROW, "staging must fit in the A operand region");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 enum { MODE_DWCONV = 0, MODE_GATHER = 1, MODE_PLAIN = 2 };
@@ -100,6 +107,38 @@ __device__ __forceinline__ void store_a4(uint8_t* a_hi, int row, int lane, float
     *reinterpret_cast<uint2*>(a_hi + A_PLANE + off) = lo;
 }
 
+// LayerNorm of two rows held in the 16x256b fragment layout: v[4j+2i+b] = row i, column 8j+2*t4+b.
+// The 4 threads of a quad (t4 = 0..3) hold one row: 2 xor-shuffles per statistic.
+template <int NJ>
+__device__ __forceinline__ void fragment_layernorm(float (&v)[64], const float* __restrict__ g,
+                                                   const float* __restrict__ be, int t4, float inv_n) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { s0 += v[4 * j] + v[4 * j + 1]; s1 += v[4 * j + 2] + v[4 * j + 3]; }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float m0 = s0 * inv_n, m1 = s1 * inv_n;
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        v[4 * j] -= m0; v[4 * j + 1] -= m0; v[4 * j + 2] -= m1; v[4 * j + 3] -= m1;
+        q0 = fmaf(v[4 * j], v[4 * j], q0); q0 = fmaf(v[4 * j + 1], v[4 * j + 1], q0);
+        q1 = fmaf(v[4 * j + 2], v[4 * j + 2], q1); q1 = fmaf(v[4 * j + 3], v[4 * j + 3], q1);
+    }
+    q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+    q0 += __shfl_xor_sync(0xffffffffu, q0, 2); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+    const float r0 = rsqrtf(q0 * inv_n + kLnEps), r1 = rsqrtf(q1 * inv_n + kLnEps);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const float2 gg = *reinterpret_cast<const float2*>(g + 8 * j + 2 * t4);
+        const float2 bb = *reinterpret_cast<const float2*>(be + 8 * j + 2 * t4);
+        v[4 * j] = fmaf(v[4 * j] * r0, gg.x, bb.x);
+        v[4 * j + 1] = fmaf(v[4 * j + 1] * r0, gg.y, bb.y);
+        v[4 * j + 2] = fmaf(v[4 * j + 2] * r1, gg.x, bb.x);
+        v[4 * j + 3] = fmaf(v[4 * j + 3] * r1, gg.y, bb.y);
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(NTHR, 1)
 umma_dec_kernel(const UmmaDecParams p) {
@@ -107,11 +146,12 @@ umma_dec_kernel(const UmmaDecParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float* Xs = reinterpret_cast<float*>(smem + OFF_XS);
     uint8_t* a_hi = smem + OFF_A;
-    uint8_t* stg = smem + OFF_A;
     float* par = reinterpret_cast<float*>(smem + OFF_PAR);
     int* srcs = reinterpret_cast<int*>(smem + OFF_SRC);
-    const uint32_t bar_x = smem_u32(smem + OFF_BAR), bar_w = bar_x + 8, bar_m = bar_x + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 24);
+    const uint32_t bar_x = smem_u32(smem + OFF_BAR), bar_w = bar_x + 8;
+    const uint32_t bar_mma = bar_x + 16;      // [2]
+    const uint32_t bar_tfree = bar_x + 32;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 48);
 
     const int N = p.N;
     const int tiles_per_utt = (p.T + TM - 1) / TM;
@@ -119,11 +159,14 @@ umma_dec_kernel(const UmmaDecParams p) {
     const uint32_t w_plane = (uint32_t)N * CK * 2u;
 
     // ---- one-time setup ---------------------------------------------------------------------
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 128);
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);      // two 128-column fp32 accumulators
     if (tid == 0) {
         mbar_init(bar_x, 1);
         mbar_init(bar_w, 1);
-        mbar_init(bar_m, 1);
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_mma + 8, 1);
+        mbar_init(bar_tfree, 8);
+        mbar_init(bar_tfree + 8, 8);
         fence_mbar_init();
     }
     for (int i = tid; i < 128; i += NTHR) {
@@ -137,263 +180,221 @@ umma_dec_kernel(const UmmaDecParams p) {
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-
-    // x-tile loader: rows [t0-HALO, t0+TM+HALO) clipped to the utterance, one bulk copy
-    auto issue_x = [&](int tile) {
-        const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
-        const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
-        const uint32_t bytes = (uint32_t)(hi - lo) * CK * 4u;
-        mbar_arrive_expect_tx(bar_x, bytes);
-        bulk_g2s(smem_u32(Xs) + (uint32_t)(lo - (t0 - HALO)) * CK * 4u,
-                 p.X + ((size_t)b * p.T + lo) * CK, bytes, bar_x);
-    };
-
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar_w, 2 * w_plane);
-        bulk_g2s(smem_u32(smem + OFF_W), p.w_h16, w_plane, bar_w);
-        bulk_g2s(smem_u32(smem + OFF_W) + w_plane, reinterpret_cast<const uint8_t*>(p.w_h16) + w_plane, w_plane, bar_w);
-        if (MODE == MODE_DWCONV && (int)blockIdx.x < n_tiles) issue_x(blockIdx.x);
-    }
-
-    // per-lane depthwise taps for channels 4*lane..4*lane+3 (persistent in registers)
-    float4 wdw[DWK], bdw;
-    if (MODE == MODE_DWCONV) {
-#pragma unroll
-        for (int t = 0; t < DWK; ++t) wdw[t] = __ldg(reinterpret_cast<const float4*>(p.dw_w + t * CK) + lane);
-        bdw = __ldg(reinterpret_cast<const float4*>(p.dw_b) + lane);
-    }
-
     bool failed = false;
-    if (!mbar_wait(bar_w, 0)) failed = true;
 
-    const uint32_t idesc = make_idesc_f16(TM, N);
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1) {
-        const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
-        const int rows_valid = min(TM, p.T - t0);
+    if (warp >= 8) {
+        // =========================================================================== producers
+        const int pw = warp - 8, ptid = tid - NPROD;
+        const bool leader = (ptid == 0);
 
-        // ---------------------------------------------------------------- prologue -> A operand
-        if (MODE == MODE_DWCONV) {
-            // zero the halo / tail rows the bulk copy does not cover (utterance boundaries only)
+        auto issue_x = [&](int tile) {     // rows [t0-HALO, t0+TM+HALO) clipped to the utterance, one bulk copy
+            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
             const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
-            const int head = lo - (t0 - HALO), tail0 = hi - (t0 - HALO);
-            if (head > 0 || tail0 < XROWS) {
-                for (int i = tid; i < (head + XROWS - tail0) * (CK / 4); i += NTHR) {
-                    int r = i / (CK / 4);
-                    const int c4 = i - r * (CK / 4);
-                    if (r >= head) r = tail0 + (r - head);
-                    reinterpret_cast<float4*>(Xs + r * CK)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-            if (!mbar_wait(bar_x, phase)) failed = true;
-            __syncthreads();                       // zero fill visible to every warp
-            // warp g -> output rows 8g..8g+7 (one 8-row core-matrix group); lane -> 4 channels
-            const int r0 = warp * 8;
-            float4 win[12];
+            const uint32_t bytes = (uint32_t)(hi - lo) * CK * 4u;
+            mbar_arrive_expect_tx(bar_x, bytes);
+            bulk_g2s(smem_u32(Xs) + (uint32_t)(lo - (t0 - HALO)) * CK * 4u,
+                     p.X + ((size_t)b * p.T + lo) * CK, bytes, bar_x);
+        };
+        if (leader) {
+            mbar_arrive_expect_tx(bar_w, 2 * w_plane);
+            bulk_g2s(smem_u32(smem + OFF_W), p.w_h16, w_plane, bar_w);
+            bulk_g2s(smem_u32(smem + OFF_W) + w_plane, reinterpret_cast<const uint8_t*>(p.w_h16) + w_plane, w_plane, bar_w);
+            if (MODE == MODE_DWCONV && (int)blockIdx.x < n_tiles) issue_x(blockIdx.x);
+        }
+        // per-lane depthwise taps for channels 4*lane..4*lane+3 (persistent in registers)
+        float4 wdw[DWK], bdw;
+        if (MODE == MODE_DWCONV) {
 #pragma unroll
-            for (int i = 0; i < 12; ++i) win[i] = reinterpret_cast<const float4*>(Xs + (r0 + i) * CK)[lane];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                float4 o = bdw;
-#pragma unroll
-                for (int t = 0; t < DWK; ++t) {
-                    o.x = fmaf(wdw[t].x, win[r + t].x, o.x);
-                    o.y = fmaf(wdw[t].y, win[r + t].y, o.y);
-                    o.z = fmaf(wdw[t].z, win[r + t].z, o.z);
-                    o.w = fmaf(wdw[t].w, win[r + t].w, o.w);
-                }
-                store_a4(a_hi, r0 + r, lane, o);
-            }
-        } else {
-            if (MODE == MODE_GATHER) {
-                if (tid < TM) {
-                    const int t = t0 + tid;
-                    int s = -1;
-                    if (t < p.T && t < p.valid_len[b]) {
-                        const int* c = p.cum + (size_t)b * p.n_src;
-                        int lo = 0, hi = p.n_src;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (__ldg(c + mid) > t) hi = mid; else lo = mid + 1;
-                        }
-                        s = lo < p.n_src ? lo : -1;
+            for (int t = 0; t < DWK; ++t) wdw[t] = __ldg(reinterpret_cast<const float4*>(p.dw_w + t * CK) + lane);
+            bdw = __ldg(reinterpret_cast<const float4*>(p.dw_b) + lane);
+        }
+        const uint32_t idesc = make_idesc_f16(TM, N);
+        const uint32_t lbo_b = (uint32_t)N * 16u;
+
+        int i = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
+            const int rows_valid = min(TM, p.T - t0);
+            const int s = i & 1, u = i >> 1;
+            // A operand free?  (MMA of the previous tile has read it)
+            if (i > 0 && !mbar_wait(bar_mma + 8 * ((i - 1) & 1), ((i - 1) >> 1) & 1)) failed = true;
+
+            if (MODE == MODE_DWCONV) {
+                // zero the halo / tail rows the bulk copy does not cover (utterance boundaries only)
+                const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
+                const int head = lo - (t0 - HALO), tail0 = hi - (t0 - HALO);
+                if (head > 0 || tail0 < XROWS) {
+                    for (int k = ptid; k < (head + XROWS - tail0) * (CK / 4); k += NPROD) {
+                        int r = k / (CK / 4);
+                        const int c4 = k - r * (CK / 4);
+                        if (r >= head) r = tail0 + (r - head);
+                        reinterpret_cast<float4*>(Xs + r * CK)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    srcs[tid] = s;
                 }
-                __syncthreads();
-            }
-            const int r0 = warp * 8;
+                if (!mbar_wait(bar_x, i & 1)) failed = true;
+                named_bar_sync(1, NPROD);              // zero fill visible to every producer warp
+#pragma unroll 1
+                for (int g = 0; g < 2; ++g) {          // warp pw -> output rows 16pw..16pw+15, 8 at a time
+                    const int r0 = pw * 16 + g * 8;
+                    float4 win[12];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int row = r0 + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int k = 0; k < 12; ++k) win[k] = reinterpret_cast<const float4*>(Xs + (r0 + k) * CK)[lane];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        float4 o = bdw;
+#pragma unroll
+                        for (int t = 0; t < DWK; ++t) {
+                            o.x = fmaf(wdw[t].x, win[r + t].x, o.x);
+                            o.y = fmaf(wdw[t].y, win[r + t].y, o.y);
+                            o.z = fmaf(wdw[t].z, win[r + t].z, o.z);
+                            o.w = fmaf(wdw[t].w, win[r + t].w, o.w);
+                        }
+                        store_a4(a_hi, r0 + r, lane, o);
+                    }
+                }
+            } else {
                 if (MODE == MODE_GATHER) {
-                    const int s = srcs[row];
-                    if (s >= 0) v = __ldg(reinterpret_cast<const float4*>(p.X + ((size_t)b * p.n_src + s) * CK) + lane);
-                } else if (row < rows_valid) {
-                    v = __ldg(reinterpret_cast<const float4*>(p.X + ((size_t)b * p.T + t0 + row) * CK) + lane);
-                }
-                store_a4(a_hi, row, lane, v);
-            }
-        }
-        fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core
-        tc_fence_before_sync();
-        __syncthreads();
-        tc_fence_after_sync();
-
-        // ---------------------------------------------------------------- GEMM (one thread issues)
-        if (tid == 0) {
-            const uint32_t a0 = smem_u32(a_hi), w0 = smem_u32(smem + OFF_W);
-            const uint32_t lbo_b = (uint32_t)N * 16u;
-#pragma unroll 1
-            for (int s = 0; s < CK / 16; ++s) {
-                const uint64_t dah = make_smem_desc(a0 + (uint32_t)(2 * s) * A_LBO, A_LBO, A_SBO);
-                const uint64_t dal = make_smem_desc(a0 + A_PLANE + (uint32_t)(2 * s) * A_LBO, A_LBO, A_SBO);
-                const uint64_t dbh = make_smem_desc(w0 + (uint32_t)(2 * s) * lbo_b, lbo_b, 128u);
-                const uint64_t dbl = make_smem_desc(w0 + w_plane + (uint32_t)(2 * s) * lbo_b, lbo_b, 128u);
-                mma_f16_ss(tmem, dah, dbh, idesc, s > 0 ? 1u : 0u);
-                mma_f16_ss(tmem, dah, dbl, idesc, 1u);
-                mma_f16_ss(tmem, dal, dbh, idesc, 1u);
-            }
-            mma_commit(bar_m);
-            // x of the next tile streams in while the GEMM and the epilogue run (Xs is free: every
-            // warp passed the barrier above after its last read)
-            if (MODE == MODE_DWCONV && tile + (int)gridDim.x < n_tiles) issue_x(tile + gridDim.x);
-        }
-        if (!mbar_wait(bar_m, phase)) failed = true;
-        tc_fence_after_sync();
-
-        // ---------------------------------------------------------------- epilogue A: TMEM -> staging
-        {
-            const int q = warp & 3, cq = warp >> 2;          // TMEM lane quarter (rows), column quarter
-            const int row = q * 32 + lane;
-            if (cq * 32 < N) {
-                uint32_t r[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 32), r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 bb = *reinterpret_cast<const float4*>(par + cq * 32 + j * 4);
-                    float4 v;
-                    if (p.act_tanh) {
-                        v.x = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j]), kTanhScale, bb.x));
-                        v.y = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j + 1]), kTanhScale, bb.y));
-                        v.z = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j + 2]), kTanhScale, bb.z));
-                        v.w = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j + 3]), kTanhScale, bb.w));
-                    } else {
-                        v = make_float4(__uint_as_float(r[4 * j]) + bb.x, __uint_as_float(r[4 * j + 1]) + bb.y,
-                                        __uint_as_float(r[4 * j + 2]) + bb.z, __uint_as_float(r[4 * j + 3]) + bb.w);
-                    }
-                    const int chunk = cq * 8 + j;
-                    *reinterpret_cast<float4*>(stg + (uint32_t)row * STG_ROW + (uint32_t)((chunk ^ (row & 7)) * 16)) = v;
-                }
-            }
-        }
-        tc_fence_before_sync();
-        __syncthreads();
-        tc_fence_after_sync();
-
-        // ---------------------------------------------------------------- epilogue B
-        // 4 rows per warp step, 8 lanes per row, 16 channels per lane (16-byte chunks part + 8j):
-        // LayerNorm statistics need 3 shuffle steps for 4 rows at once, every global access is a
-        // full 128-byte line per 8-lane group.
-        {
-            const int rr = lane >> 3, part = lane & 7;
-            const int nl = N >> 2;                            // 16-byte chunks per row
-            const float inv_n = 1.f / (float)N;
-            const int zero_from = p.zero_from ? p.zero_from[b] : 0x7fffffff;
-#pragma unroll 1
-            for (int rbase = warp * 4; rbase < TM; rbase += (NTHR / 32) * 4) {
-                const int row = rbase + rr;
-                const bool rvalid = row < rows_valid;
-                const size_t grow = (size_t)b * p.T + t0 + row;
-                float4 v[4];
-                bool cv[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    cv[j] = (part + 8 * j) < nl;
-                    v[j] = cv[j] ? *reinterpret_cast<const float4*>(stg + (uint32_t)row * STG_ROW +
-                                                                    (uint32_t)((8 * j + (part ^ (row & 7))) * 16))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if (p.ln_g) {
-                    float sm = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) sm += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-                    sm += __shfl_xor_sync(0xffffffffu, sm, 1);
-                    sm += __shfl_xor_sync(0xffffffffu, sm, 2);
-                    sm += __shfl_xor_sync(0xffffffffu, sm, 4);
-                    const float mean = sm * inv_n;
-                    float q = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
-                        if (!cv[j]) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        q = fmaf(v[j].x, v[j].x, q); q = fmaf(v[j].y, v[j].y, q);
-                        q = fmaf(v[j].z, v[j].z, q); q = fmaf(v[j].w, v[j].w, q);
-                    }
-                    q += __shfl_xor_sync(0xffffffffu, q, 1);
-                    q += __shfl_xor_sync(0xffffffffu, q, 2);
-                    q += __shfl_xor_sync(0xffffffffu, q, 4);
-                    const float rstd = rsqrtf(q * inv_n + kLnEps);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 g = *reinterpret_cast<const float4*>(par + 128 + (part + 8 * j) * 4);
-                        const float4 be = *reinterpret_cast<const float4*>(par + 256 + (part + 8 * j) * 4);
-                        v[j] = make_float4(fmaf(v[j].x * rstd, g.x, be.x), fmaf(v[j].y * rstd, g.y, be.y),
-                                           fmaf(v[j].z * rstd, g.z, be.z), fmaf(v[j].w * rstd, g.w, be.w));
-                    }
-                }
-                if (p.res2) {
-                    float sm = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (cv[j] && rvalid) {
-                            const float4 sk = __ldg(reinterpret_cast<const float4*>(p.res2 + grow * N) + part + 8 * j);
-                            v[j].x += sk.x; v[j].y += sk.y; v[j].z += sk.z; v[j].w += sk.w;
+                    if (ptid < TM) {
+                        const int t = t0 + ptid;
+                        int sidx = -1;
+                        if (t < p.T && t < p.valid_len[b]) {
+                            const int* c = p.cum + (size_t)b * p.n_src;
+                            int lo = 0, hi = p.n_src;
+                            while (lo < hi) {
+                                const int mid = (lo + hi) >> 1;
+                                if (__ldg(c + mid) > t) hi = mid; else lo = mid + 1;
+                            }
+                            sidx = lo < p.n_src ? lo : -1;
                         }
-                        sm += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+                        srcs[ptid] = sidx;
                     }
-                    sm += __shfl_xor_sync(0xffffffffu, sm, 1);
-                    sm += __shfl_xor_sync(0xffffffffu, sm, 2);
-                    sm += __shfl_xor_sync(0xffffffffu, sm, 4);
-                    const float mean = sm * inv_n;
-                    float q = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
-                        if (!cv[j]) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        q = fmaf(v[j].x, v[j].x, q); q = fmaf(v[j].y, v[j].y, q);
-                        q = fmaf(v[j].z, v[j].z, q); q = fmaf(v[j].w, v[j].w, q);
-                    }
-                    q += __shfl_xor_sync(0xffffffffu, q, 1);
-                    q += __shfl_xor_sync(0xffffffffu, q, 2);
-                    q += __shfl_xor_sync(0xffffffffu, q, 4);
-                    const float rstd = rsqrtf(q * inv_n + kLnEps);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 g = *reinterpret_cast<const float4*>(par + 384 + (part + 8 * j) * 4);
-                        const float4 be = *reinterpret_cast<const float4*>(par + 512 + (part + 8 * j) * 4);
-                        v[j] = make_float4(fmaf(v[j].x * rstd, g.x, be.x), fmaf(v[j].y * rstd, g.y, be.y),
-                                           fmaf(v[j].z * rstd, g.z, be.z), fmaf(v[j].w * rstd, g.w, be.w));
-                    }
+                    named_bar_sync(1, NPROD);
                 }
-                if (rvalid) {
-                    const bool zero = (t0 + row) >= zero_from;
+#pragma unroll 4
+                for (int r = 0; r < 16; ++r) {
+                    const int row = pw * 16 + r;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (MODE == MODE_GATHER) {
+                        const int sidx = srcs[row];
+                        if (sidx >= 0) v = __ldg(reinterpret_cast<const float4*>(p.X + ((size_t)b * p.n_src + sidx) * CK) + lane);
+                    } else if (row < rows_valid) {
+                        v = __ldg(reinterpret_cast<const float4*>(p.X + ((size_t)b * p.T + t0 + row) * CK) + lane);
+                    }
+                    store_a4(a_hi, row, lane, v);
+                }
+            }
+            fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core
+            tc_fence_before_sync();
+            named_bar_sync(1, NPROD);
+
+            if (leader) {
+                tc_fence_after_sync();
+                // x of the next tile streams in while this tile's GEMM / epilogue run (Xs is free:
+                // every producer warp passed the barrier above after its last read)
+                if (MODE == MODE_DWCONV && tile + (int)gridDim.x < n_tiles) issue_x(tile + gridDim.x);
+                if (i == 0 && !mbar_wait(bar_w, 0)) failed = true;
+                // accumulator s drained by the epilogue warps (its previous use was tile i-2)?
+                if (u > 0 && !mbar_wait(bar_tfree + 8 * s, (u - 1) & 1)) failed = true;
+                tc_fence_after_sync();
+                const uint32_t a0 = smem_u32(a_hi), w0 = smem_u32(smem + OFF_W);
+                const uint32_t acc = tmem + (uint32_t)(s * 128);
+#pragma unroll 1
+                for (int k = 0; k < CK / 16; ++k) {
+                    const uint64_t dah = make_smem_desc(a0 + (uint32_t)(2 * k) * A_LBO, A_LBO, A_SBO);
+                    const uint64_t dal = make_smem_desc(a0 + A_PLANE + (uint32_t)(2 * k) * A_LBO, A_LBO, A_SBO);
+                    const uint64_t dbh = make_smem_desc(w0 + (uint32_t)(2 * k) * lbo_b, lbo_b, 128u);
+                    const uint64_t dbl = make_smem_desc(w0 + w_plane + (uint32_t)(2 * k) * lbo_b, lbo_b, 128u);
+                    mma_f16_ss(acc, dah, dbh, idesc, k > 0 ? 1u : 0u);
+                    mma_f16_ss(acc, dah, dbl, idesc, 1u);
+                    mma_f16_ss(acc, dal, dbh, idesc, 1u);
+                }
+                mma_commit(bar_mma + 8 * s);
+            }
+        }
+    } else {
+        // =========================================================================== epilogue
+        const int q = warp & 3, half = warp >> 2;             // TMEM lane quarter, 16-row half
+        const int rbase = q * 32 + half * 16;
+        const int t4 = lane & 3, tr = lane >> 2;
+        const float inv_n = 1.f / (float)N;
+        const int nj = N >> 3;                                // 8-column groups
+
+        int i = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
+            const int rows_valid = min(TM, p.T - t0);
+            const int s = i & 1, u = i >> 1;
+            const int row0 = rbase + tr, row1 = row0 + 8;
+            const size_t g0 = (size_t)b * p.T + t0 + row0, g1 = g0 + 8;
+            const bool ok0 = row0 < rows_valid, ok1 = row1 < rows_valid;
+
+            if (p.res2) {   // pull this warp's 16 skip rows (8 KB) towards L2 while the GEMM runs
+                const int pr = rbase + (lane >> 1);
+                if (pr < rows_valid) {
+                    const float* sp = p.res2 + ((size_t)b * p.T + t0 + pr) * N + (lane & 1) * 64;
+                    prefetch_l2(sp);
+                    prefetch_l2(sp + 32);
+                }
+            }
+            if (!mbar_wait(bar_mma + 8 * s, u & 1)) failed = true;
+            tc_fence_after_sync();
+            uint32_t r[64];
+            tmem_ld_16x256b_x16(tmem + (uint32_t)(s * 128) + ((uint32_t)rbase << 16), r);
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tfree + 8 * s);     // accumulator drained: the GEMM of tile i+2 may start
+
+            float v[64];
+            if (p.act_tanh) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (cv[j]) reinterpret_cast<float4*>(p.Y + grow * N)[part + 8 * j] =
-                            zero ? make_float4(0.f, 0.f, 0.f, 0.f) : v[j];
+                for (int j = 0; j < 16; ++j) {
+                    const float2 bb = *reinterpret_cast<const float2*>(par + 8 * j + 2 * t4);
+                    v[4 * j] = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j]), kTanhScale, bb.x));
+                    v[4 * j + 1] = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j + 1]), kTanhScale, bb.y));
+                    v[4 * j + 2] = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j + 2]), kTanhScale, bb.x));
+                    v[4 * j + 3] = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j + 3]), kTanhScale, bb.y));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float2 bb = *reinterpret_cast<const float2*>(par + 8 * j + 2 * t4);
+                    v[4 * j] = __uint_as_float(r[4 * j]) + bb.x;
+                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.x;
+                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.y;
+                }
+            }
+            if (p.ln_g) fragment_layernorm<16>(v, par + 128, par + 256, t4, inv_n);   // LayerNorm only with N == 128
+            if (p.res2) {
+                const float* s0 = p.res2 + g0 * N + 2 * t4;
+                const float* s1 = p.res2 + g1 * N + 2 * t4;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float2 a = ok0 ? __ldg(reinterpret_cast<const float2*>(s0 + 8 * j)) : make_float2(0.f, 0.f);
+                    const float2 c = ok1 ? __ldg(reinterpret_cast<const float2*>(s1 + 8 * j)) : make_float2(0.f, 0.f);
+                    v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += c.x; v[4 * j + 3] += c.y;
+                }
+                fragment_layernorm<16>(v, par + 384, par + 512, t4, inv_n);
+            }
+            const int zero_from = p.zero_from ? p.zero_from[b] : 0x7fffffff;
+            const bool z0 = (t0 + row0) >= zero_from, z1 = (t0 + row1) >= zero_from;
+            float* y0 = p.Y + g0 * N + 2 * t4;
+            float* y1 = p.Y + g1 * N + 2 * t4;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (j < nj) {
+                    if (ok0) *reinterpret_cast<float2*>(y0 + 8 * j) = z0 ? make_float2(0.f, 0.f) : make_float2(v[4 * j], v[4 * j + 1]);
+                    if (ok1) *reinterpret_cast<float2*>(y1 + 8 * j) = z1 ? make_float2(0.f, 0.f) : make_float2(v[4 * j + 2], v[4 * j + 3]);
                 }
             }
         }
-        __syncthreads();                           // staging (== A region) free for the next tile
     }
 
-    if (failed && lane == 0) atomicExch(p.err, 1);
+    if (failed) atomicExch(p.err, 1);
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 int* g_err_flag = nullptr;
@@ -424,6 +425,7 @@ int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, co
                     float* Y, cudaStream_t s) {
     ES_CHECK(w_h16 && X && Y && bias, "null tensor");
     ES_CHECK(N % 16 == 0 && N >= 32 && N <= 128, "N must be a multiple of 16 in [32,128]");
+    ES_CHECK(!(ln_g || res2) || N == 128, "LayerNorm epilogue needs N == 128");
     if (!g_err_flag) {
         ES_CUDA(cudaMalloc(&g_err_flag, sizeof(int)));
         ES_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
