@@ -66,6 +66,7 @@ PROTOTYPES = {
     "es_decoder_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _sz]),
     "es_decoder_forward_gathered": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz]),
     "es_check_async_errors": (_i, [_vp]),
+    "es_debug_set_trace": (_i, [_vp]),
     "es_launch_count": (C.c_uint64, []),
     "es_profile_begin": (_i, [_i]),
     "es_profile_end": (_i, []),

@@ -28,5 +28,6 @@ int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, co
                     const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
                     float* Y, cudaStream_t s);
 int umma_dec_check_errors(cudaStream_t s);
+void umma_dec_set_trace(long long* buf);
 
 }  // namespace es

@@ -58,6 +58,19 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     return false;
 }
 
+// One lane of a fully converged warp (elect.sync).  Code guarded by it stays warp-uniform for the
+// compiler, so UMMA descriptors / barrier addresses are computed in UNIFORM registers instead of
+// being moved there (R2UR) one by one in front of every tcgen05.mma.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- proxies / fences -------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {      // generic st.shared -> visible to UMMA/TMA
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

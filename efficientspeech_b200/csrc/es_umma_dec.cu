@@ -1,32 +1,40 @@
 // Decoder-side fused tensor-core kernel (sm_100a: tcgen05 + TMEM + bulk-async copies),
 // warp-specialised and software-pipelined.
 //
-// One persistent CTA per SM walks 128-frame tiles of [B, T, 128] activations.  Its 16 warps
-// form two groups that work on DIFFERENT tiles at the same time:
+// One persistent CTA per SM walks 64-frame tiles of [B, T, 128] activations.  Its 13 warps
+// have four roles and work on DIFFERENT tiles at the same time:
 //
-//   producer warps 8..15 (tile i+1)
+//   issue warp 12 (one elected lane): bulk x loads into the ring, tcgen05.mma issue + commit
+//   producer warps 8..11 (tile i)
 //       DWCONV  the x tile (+2-frame halo) arrives by ONE bulk async copy (TMA 1-D, mbarrier
-//               complete_tx); depthwise conv k=5 + bias in registers (sliding window)
-//       GATHER  the length regulator: row t <- fused4[b, upper_bound(cum[b], t)]
-//       PLAIN   rows copied as they are (mel head, stand-alone projection)
-//       -> split into fp16 hi/lo, written straight into the UMMA canonical K-major no-swizzle
-//          operand layout (bank-conflict free); then ONE thread issues 24 x tcgen05.mma
-//          (M128 x N x K16, kind::f16: hi*hi + hi*lo + lo*hi, fp32 accumulate) into one of
-//          TWO TMEM accumulators and commits to an mbarrier.  The split-fp16 weights (canonical
-//          layout prepared at pack time) are bulk-loaded ONCE per CTA and stay in shared memory.
-//   epilogue warps 0..7 (tile i)
+//               complete_tx) into a 3-deep ring, so two tiles (70 KB) are always in flight per
+//               SM; depthwise conv k=5 + bias in registers (sliding window)
+//       PLAIN   same ring without halo / conv (mel head, stand-alone projection)
+//       GATHER  the length regulator: row t <- fused4[b, upper_bound(cum[b], t)] (L2-resident)
+//       The results are held in registers while the previous tile's GEMM still reads the A
+//       operand, then split into fp16 hi/lo and stored straight into the UMMA canonical K-major
+//       no-swizzle operand layout (bank-conflict free); the issue warp then launches 24 x
+//       tcgen05.mma (M64 x N x K16, kind::f16: hi*hi + hi*lo + lo*hi, fp32 accumulate) and
+//       commits to an mbarrier (a dedicated warp: the blocking MMA issue never stalls a producer).  Two M=64 accumulators interleave in the same 128 TMEM columns (lanes
+//       {0-15,32-47,..} and {16-31,48-63,..}), so tile i+1's GEMM never waits for tile i's
+//       epilogue.  The split-fp16 weights (canonical layout prepared at pack time) are
+//       bulk-loaded ONCE per CTA and stay in shared memory.
+//   epilogue warps 0..3 (even tiles) and 4..7 (odd tiles)
 //       tcgen05.ld 16x256b: each warp owns 16 complete rows in the mma-fragment layout (4 threads
 //       per row), releases the accumulator right after the load, then runs bias -> tanh ->
 //       LayerNorm [-> + skip -> LayerNorm] [-> zero padded frames] in registers (2 shuffle steps
 //       per statistic) and stores 32-byte row segments straight to global memory.  No
 //       shared-memory staging, no CTA-wide barrier in steady state.
 //
-// mbarriers: bar_x (x tile landed), bar_mma[2] (accumulator s full == A operand free),
-// bar_tfree[2] (accumulator s drained by all 8 epilogue warps).  Every wait is bounded: a
+// mbarriers: bar_x[3] (x tile landed in ring slot), bar_xfree[3] (slot consumed by the producers),
+// bar_aready (A operand written), bar_mma[2] (accumulator g full == A operand free),
+// bar_tfree[2] (accumulator g drained by its 4 epilogue warps).  Every wait is bounded: a
 // timeout raises a device flag instead of hanging the GPU.
 //
 // HBM traffic per layer is exactly one read of x (+ skip on block-end layers) and one write of
 // y: the kernel is HBM-bound by design.
+#include <stdlib.h>
+
 #include "es_common.cuh"
 #include "es_kernels.cuh"
 #include "es_umma.cuh"
@@ -36,27 +44,27 @@ namespace {
 
 using namespace umma;
 
-constexpr int TM = 128;                 // frames per tile (UMMA M)
+constexpr int TM = 64;                  // frames per tile (UMMA M)
 constexpr int CK = 128;                 // K = input channels
 constexpr int DWK = 5;                  // depthwise taps
-constexpr int HALO = DWK / 2;
-constexpr int XROWS = TM + DWK - 1;     // 132
-constexpr int NTHR = 512;               // 16 warps: 0..7 epilogue, 8..15 producer
-constexpr int NPROD = 256;
+constexpr int NTHR = 416;               // 13 warps: 0..7 epilogue, 8..11 producer, 12 issue
+constexpr int NPROD = 128;
+constexpr int NSTAGE = 3;               // x ring depth
 constexpr uint32_t A_LBO = 144;         // 128-byte core matrix + 16 B pad: conflict-free 8-byte lane stores
 constexpr uint32_t A_SBO = 16 * A_LBO;  // 2304: one 8-row group = 16 K-chunks
-constexpr uint32_t A_PLANE = 16 * A_SBO;            // 36864 bytes per fp16 plane (hi or lo)
-constexpr uint32_t XS_BYTES = XROWS * CK * 4;       // 67584
+constexpr uint32_t A_PLANE = (TM / 8) * A_SBO;      // 18432 bytes per fp16 plane (hi or lo)
+constexpr uint32_t X_STAGE = (TM + DWK - 1) * CK * 4;   // 34816 bytes per ring slot (68 rows)
 
 // shared memory map (dynamic, 1024-aligned base)
 constexpr uint32_t OFF_XS = 0;
-constexpr uint32_t OFF_A = OFF_XS + XS_BYTES;                 // hi plane, then lo plane
+constexpr uint32_t OFF_A = OFF_XS + NSTAGE * X_STAGE;         // hi plane, then lo plane
 constexpr uint32_t OFF_W = OFF_A + 2 * A_PLANE;               // W hi [K/8][N][8], then W lo
 constexpr uint32_t W_PLANE_MAX = 128 * CK * 2;                // 32768
 constexpr uint32_t OFF_PAR = OFF_W + 2 * W_PLANE_MAX;         // bias, ln g/b, ln2 g/b: 5 x 128 floats
-constexpr uint32_t OFF_SRC = OFF_PAR + 5 * 128 * 4;           // gather sources: 128 ints
-constexpr uint32_t OFF_BAR = OFF_SRC + 128 * 4;               // 6 mbarriers + tmem base
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 64;
+constexpr uint32_t OFF_DW = OFF_PAR + 5 * 128 * 4;            // depthwise taps + bias: 6 x 128 floats
+constexpr uint32_t OFF_SRC = OFF_DW + 6 * 128 * 4;            // gather sources: 64 ints
+constexpr uint32_t OFF_BAR = OFF_SRC + TM * 4;                // 12 mbarriers + tmem base
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 enum { MODE_DWCONV = 0, MODE_GATHER = 1, MODE_PLAIN = 2 };
@@ -77,6 +85,7 @@ struct UmmaDecParams {
     const int* zero_from;        // [B] rows t >= zero_from[b] zeroed, or null
     float* Y;                    // [B,T,N]
     int* err;                    // device error flag (mbarrier timeout)
+    long long* trace;            // debug: per-role clock64 stamps of CTA 0 ([4 roles][32 tiles][8 events]) or null
 };
 
 // tanh(x) = 1 - 2 / (1 + e^{2x}) with e^{2x} = 2^{x * 2 log2(e)}: two MUFU ops (ex2, rcp) and two FMAs.
@@ -90,68 +99,104 @@ __device__ __forceinline__ float tanh_from_scaled(float arg) {
     return fmaf(-2.f, r, 1.f);
 }
 
-__device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) {
-    const __half2 p = __floats2half2_rn(a, b), q = __floats2half2_rn(c, d);
-    return make_uint2(*reinterpret_cast<const uint32_t*>(&p), *reinterpret_cast<const uint32_t*>(&q));
-}
-
-// writes 4 consecutive channels (4*lane .. 4*lane+3) of tile row `row` as split fp16 into the A planes
-__device__ __forceinline__ void store_a4(uint8_t* a_hi, int row, int lane, float4 v) {
+// 4 consecutive channels -> split fp16: hi = fp16(v), lo = fp16(v - hi)
+__device__ __forceinline__ void split4(float4 v, uint2& hi, uint2& lo) {
     const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
     const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
-    const uint2 hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-    const uint2 lo = pack_half4(v.x - b0.x, v.y - b0.y, v.z - b1.x, v.w - b1.y);
-    const uint32_t off = (uint32_t)(lane >> 1) * A_LBO + (uint32_t)(row >> 3) * A_SBO + (uint32_t)(row & 7) * 16u +
-                         (uint32_t)(lane & 1) * 8u;
-    *reinterpret_cast<uint2*>(a_hi + off) = hi;
-    *reinterpret_cast<uint2*>(a_hi + A_PLANE + off) = lo;
+    const __half2 l0 = __floats2half2_rn(v.x - b0.x, v.y - b0.y), l1 = __floats2half2_rn(v.z - b1.x, v.w - b1.y);
+    hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
 }
 
-// LayerNorm of two rows held in the 16x256b fragment layout: v[4j+2i+b] = row i, column 8j+2*t4+b.
-// The 4 threads of a quad (t4 = 0..3) hold one row: 2 xor-shuffles per statistic.
-template <int NJ>
-__device__ __forceinline__ void fragment_layernorm(float (&v)[64], const float* __restrict__ g,
-                                                   const float* __restrict__ be, int t4, float inv_n) {
-    float s0 = 0.f, s1 = 0.f;
+// byte offset of channels 4*lane..4*lane+3 of tile row `row` inside an A plane
+__device__ __forceinline__ uint32_t a_off(int row, int lane) {
+    return (uint32_t)(lane >> 1) * A_LBO + (uint32_t)(row >> 3) * A_SBO + (uint32_t)(row & 7) * 16u +
+           (uint32_t)(lane & 1) * 8u;
+}
+
+// LayerNorm in the 16x256b fragment layout: v[4j+2*row+b] = column 8j+2*t4+b of this thread's row
+// `row`; the 4 threads of a quad (t4 = 0..3) hold one row.  Single pass (sum and sum of squares in
+// two independent chains each -- the inputs are tanh / LayerNorm outputs of O(1) magnitude, so
+// E[x^2]-m^2 loses nothing at fp32), 2 xor-shuffles per statistic, then y = ((v*r - m*r) * g + b):
+// 4 FMA-pipe instructions per element.
+__device__ __forceinline__ void quad_stats(float s, float q, float inv_n, float& r, float& nm) {
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    const float m = s * inv_n;
+    r = rsqrtf(fmaf(q, inv_n, -m * m) + kLnEps);
+    nm = -m * r;
+}
+
+// both rows of the thread (shares the gamma/beta loads)
+__device__ __forceinline__ void fragment_layernorm2(float (&v)[64], const float* __restrict__ g,
+                                                    const float* __restrict__ be, int t4, float inv_n) {
+    float s0a = 0.f, s0b = 0.f, q0a = 0.f, q0b = 0.f, s1a = 0.f, s1b = 0.f, q1a = 0.f, q1b = 0.f;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) { s0 += v[4 * j] + v[4 * j + 1]; s1 += v[4 * j + 2] + v[4 * j + 3]; }
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-    const float m0 = s0 * inv_n, m1 = s1 * inv_n;
-    float q0 = 0.f, q1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        v[4 * j] -= m0; v[4 * j + 1] -= m0; v[4 * j + 2] -= m1; v[4 * j + 3] -= m1;
-        q0 = fmaf(v[4 * j], v[4 * j], q0); q0 = fmaf(v[4 * j + 1], v[4 * j + 1], q0);
-        q1 = fmaf(v[4 * j + 2], v[4 * j + 2], q1); q1 = fmaf(v[4 * j + 3], v[4 * j + 3], q1);
+    for (int j = 0; j < 16; ++j) {
+        s0a += v[4 * j]; s0b += v[4 * j + 1]; q0a = fmaf(v[4 * j], v[4 * j], q0a); q0b = fmaf(v[4 * j + 1], v[4 * j + 1], q0b);
+        s1a += v[4 * j + 2]; s1b += v[4 * j + 3]; q1a = fmaf(v[4 * j + 2], v[4 * j + 2], q1a); q1b = fmaf(v[4 * j + 3], v[4 * j + 3], q1b);
     }
-    q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
-    q0 += __shfl_xor_sync(0xffffffffu, q0, 2); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
-    const float r0 = rsqrtf(q0 * inv_n + kLnEps), r1 = rsqrtf(q1 * inv_n + kLnEps);
+    float r0, n0, r1, n1;
+    quad_stats(s0a + s0b, q0a + q0b, inv_n, r0, n0);
+    quad_stats(s1a + s1b, q1a + q1b, inv_n, r1, n1);
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
+    for (int j = 0; j < 16; ++j) {
         const float2 gg = *reinterpret_cast<const float2*>(g + 8 * j + 2 * t4);
         const float2 bb = *reinterpret_cast<const float2*>(be + 8 * j + 2 * t4);
-        v[4 * j] = fmaf(v[4 * j] * r0, gg.x, bb.x);
-        v[4 * j + 1] = fmaf(v[4 * j + 1] * r0, gg.y, bb.y);
-        v[4 * j + 2] = fmaf(v[4 * j + 2] * r1, gg.x, bb.x);
-        v[4 * j + 3] = fmaf(v[4 * j + 3] * r1, gg.y, bb.y);
+        v[4 * j] = fmaf(fmaf(v[4 * j], r0, n0), gg.x, bb.x);
+        v[4 * j + 1] = fmaf(fmaf(v[4 * j + 1], r0, n0), gg.y, bb.y);
+        v[4 * j + 2] = fmaf(fmaf(v[4 * j + 2], r1, n1), gg.x, bb.x);
+        v[4 * j + 3] = fmaf(fmaf(v[4 * j + 3], r1, n1), gg.y, bb.y);
     }
 }
+
+// one row (ROW = 0 | 1) of the thread
+template <int ROW>
+__device__ __forceinline__ void fragment_layernorm_row(float (&v)[64], const float* __restrict__ g,
+                                                       const float* __restrict__ be, int t4, float inv_n) {
+    float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        sa += v[4 * j + 2 * ROW]; sb += v[4 * j + 2 * ROW + 1];
+        qa = fmaf(v[4 * j + 2 * ROW], v[4 * j + 2 * ROW], qa);
+        qb = fmaf(v[4 * j + 2 * ROW + 1], v[4 * j + 2 * ROW + 1], qb);
+    }
+    float r, nm;
+    quad_stats(sa + sb, qa + qb, inv_n, r, nm);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float2 gg = *reinterpret_cast<const float2*>(g + 8 * j + 2 * t4);
+        const float2 bb = *reinterpret_cast<const float2*>(be + 8 * j + 2 * t4);
+        v[4 * j + 2 * ROW] = fmaf(fmaf(v[4 * j + 2 * ROW], r, nm), gg.x, bb.x);
+        v[4 * j + 2 * ROW + 1] = fmaf(fmaf(v[4 * j + 2 * ROW + 1], r, nm), gg.y, bb.y);
+    }
+}
+
+// debug time stamps (CTA 0 only, one lane per role); compiled in, one predictable branch when off
+#define ES_TRACE(role, iter, ev)                                                             \
+    do {                                                                                     \
+        if (p.trace && blockIdx.x == 0 && (iter) < 32) p.trace[((role) * 32 + (iter)) * 8 + (ev)] = clock64(); \
+    } while (0)
 
 template <int MODE>
 __global__ void __launch_bounds__(NTHR, 1)
 umma_dec_kernel(const UmmaDecParams p) {
+    constexpr int HALO = (MODE == MODE_DWCONV) ? DWK / 2 : 0;
+    constexpr int XROWS = TM + 2 * HALO;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float* Xs = reinterpret_cast<float*>(smem + OFF_XS);
     uint8_t* a_hi = smem + OFF_A;
     float* par = reinterpret_cast<float*>(smem + OFF_PAR);
     int* srcs = reinterpret_cast<int*>(smem + OFF_SRC);
-    const uint32_t bar_x = smem_u32(smem + OFF_BAR), bar_w = bar_x + 8;
-    const uint32_t bar_mma = bar_x + 16;      // [2]
-    const uint32_t bar_tfree = bar_x + 32;    // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 48);
+    const uint32_t bar_x = smem_u32(smem + OFF_BAR);          // [3] x tile landed
+    const uint32_t bar_w = bar_x + 24;                        //     weights landed
+    const uint32_t bar_mma = bar_x + 32;                      // [2] accumulator g full / A operand free
+    const uint32_t bar_tfree = bar_x + 48;                    // [2] accumulator g drained
+    const uint32_t bar_xfree = bar_x + 64;                    // [3] ring slot consumed
+    const uint32_t bar_aready = bar_x + 88;                   //     A operand written by the 4 producer warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 96);
 
     const int N = p.N;
     const int tiles_per_utt = (p.T + TM - 1) / TM;
@@ -159,14 +204,16 @@ umma_dec_kernel(const UmmaDecParams p) {
     const uint32_t w_plane = (uint32_t)N * CK * 2u;
 
     // ---- one-time setup ---------------------------------------------------------------------
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);      // two 128-column fp32 accumulators
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 128);      // 128 fp32 columns x 128 lanes = two M64 accumulators
     if (tid == 0) {
-        mbar_init(bar_x, 1);
+        for (int k = 0; k < NSTAGE; ++k) mbar_init(bar_x + 8 * k, 1);
         mbar_init(bar_w, 1);
         mbar_init(bar_mma, 1);
         mbar_init(bar_mma + 8, 1);
-        mbar_init(bar_tfree, 8);
-        mbar_init(bar_tfree + 8, 8);
+        mbar_init(bar_tfree, 4);
+        mbar_init(bar_tfree + 8, 4);
+        for (int k = 0; k < NSTAGE; ++k) mbar_init(bar_xfree + 8 * k, 4);
+        mbar_init(bar_aready, 4);
         fence_mbar_init();
     }
     for (int i = tid; i < 128; i += NTHR) {
@@ -176,54 +223,101 @@ umma_dec_kernel(const UmmaDecParams p) {
         par[384 + i] = (p.ln2_g && i < N) ? __ldg(p.ln2_g + i) : 0.f;
         par[512 + i] = (p.ln2_g && i < N) ? __ldg(p.ln2_b + i) : 0.f;
     }
+    if (MODE == MODE_DWCONV) {
+        float* dws = reinterpret_cast<float*>(smem + OFF_DW);
+        for (int i = tid; i < (DWK + 1) * CK; i += NTHR) dws[i] = i < DWK * CK ? __ldg(p.dw_w + i) : __ldg(p.dw_b + i - DWK * CK);
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     bool failed = false;
 
-    if (warp >= 8) {
-        // =========================================================================== producers
-        const int pw = warp - 8, ptid = tid - NPROD;
-        const bool leader = (ptid == 0);
-
-        auto issue_x = [&](int tile) {     // rows [t0-HALO, t0+TM+HALO) clipped to the utterance, one bulk copy
+    if (warp == 12) {
+        // =========================================================================== issue warp
+        // rows [t0-HALO, t0+TM+HALO) clipped to the utterance -> ring slot, one bulk copy
+        auto issue_x = [&](int tile, int slot) {
             const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
             const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
             const uint32_t bytes = (uint32_t)(hi - lo) * CK * 4u;
-            mbar_arrive_expect_tx(bar_x, bytes);
-            bulk_g2s(smem_u32(Xs) + (uint32_t)(lo - (t0 - HALO)) * CK * 4u,
-                     p.X + ((size_t)b * p.T + lo) * CK, bytes, bar_x);
+            mbar_arrive_expect_tx(bar_x + 8 * slot, bytes);
+            bulk_g2s(smem_u32(smem + OFF_XS) + (uint32_t)slot * X_STAGE + (uint32_t)(lo - (t0 - HALO)) * CK * 4u,
+                     p.X + ((size_t)b * p.T + lo) * CK, bytes, bar_x + 8 * slot);
         };
-        if (leader) {
+        const uint32_t idesc = make_idesc_f16(TM, N);
+        const uint32_t lbo_b = (uint32_t)N * 16u;
+        // UMMA shared-memory descriptors of K step 0 (A: padded canonical tile; B: resident weights);
+        // they advance by a constant per K step (start-address field, 16-byte units)
+        const uint64_t dah0 = make_smem_desc(smem_u32(a_hi), A_LBO, A_SBO);
+        const uint64_t dal0 = make_smem_desc(smem_u32(a_hi) + A_PLANE, A_LBO, A_SBO);
+        const uint64_t dbh0 = make_smem_desc(smem_u32(smem + OFF_W), lbo_b, 128u);
+        const uint64_t dbl0 = make_smem_desc(smem_u32(smem + OFF_W) + w_plane, lbo_b, 128u);
+        const uint64_t db_step = (uint64_t)((2u * lbo_b) >> 4);
+        const bool elected = elect_one();                    // one lane issues on behalf of the CTA; the
+                                                             // control flow stays warp-uniform
+        if (elected) {
             mbar_arrive_expect_tx(bar_w, 2 * w_plane);
             bulk_g2s(smem_u32(smem + OFF_W), p.w_h16, w_plane, bar_w);
             bulk_g2s(smem_u32(smem + OFF_W) + w_plane, reinterpret_cast<const uint8_t*>(p.w_h16) + w_plane, w_plane, bar_w);
-            if (MODE == MODE_DWCONV && (int)blockIdx.x < n_tiles) issue_x(blockIdx.x);
         }
-        // per-lane depthwise taps for channels 4*lane..4*lane+3 (persistent in registers)
-        float4 wdw[DWK], bdw;
-        if (MODE == MODE_DWCONV) {
+        if (MODE != MODE_GATHER) {
+            for (int k = 0; k < NSTAGE; ++k) {
+                const int tile = blockIdx.x + k * gridDim.x;
+                if (tile < n_tiles && elected) issue_x(tile, k);
+            }
+        }
+        if (!mbar_wait(bar_w, 0)) failed = true;
+        __syncwarp();
+        int i = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+            const int g = i & 1, u = i >> 1, slot = i % NSTAGE;
+            if (elected) ES_TRACE(0, i, 0);
+            if (!mbar_wait(bar_aready, i & 1)) failed = true;            // A operand of tile i written
+            if (elected) ES_TRACE(0, i, 1);
+            // accumulator g drained by its epilogue warps (its previous use was tile i-2)?
+            if (u > 0 && !mbar_wait(bar_tfree + 8 * g, (u - 1) & 1)) failed = true;
+            tc_fence_after_sync();
+            if (elected) ES_TRACE(0, i, 2);
+            const uint32_t acc = tmem + ((uint32_t)(16 * g) << 16);    // M64 accumulators interleave by 16 lanes
 #pragma unroll
-            for (int t = 0; t < DWK; ++t) wdw[t] = __ldg(reinterpret_cast<const float4*>(p.dw_w + t * CK) + lane);
-            bdw = __ldg(reinterpret_cast<const float4*>(p.dw_b) + lane);
+            for (int k = 0; k < CK / 16; ++k) {
+                const uint64_t da = (uint64_t)((uint32_t)(2 * k) * A_LBO >> 4);
+                const uint64_t db = (uint64_t)k * db_step;
+                if (elected) {
+                    mma_f16_ss(acc, dah0 + da, dbh0 + db, idesc, k > 0 ? 1u : 0u);
+                    mma_f16_ss(acc, dah0 + da, dbl0 + db, idesc, 1u);
+                    mma_f16_ss(acc, dal0 + da, dbh0 + db, idesc, 1u);
+                }
+            }
+            if (elected) { mma_commit(bar_mma + 8 * g); ES_TRACE(0, i, 3); }
+            // ring slot of tile i was released by the producers before they signalled bar_aready:
+            // the tile three steps ahead starts streaming into it
+            if (MODE != MODE_GATHER && tile + NSTAGE * (int)gridDim.x < n_tiles) {
+                if (!mbar_wait(bar_xfree + 8 * slot, (i / NSTAGE) & 1)) failed = true;
+                if (elected) issue_x(tile + NSTAGE * gridDim.x, slot);
+            }
+            if (elected) ES_TRACE(0, i, 4);
+            __syncwarp();
         }
-        const uint32_t idesc = make_idesc_f16(TM, N);
-        const uint32_t lbo_b = (uint32_t)N * 16u;
+    } else if (warp >= 8) {
+        // =========================================================================== producers
+        const int pw = warp - 8, ptid = tid - 256;
+        const float4* dwp = reinterpret_cast<const float4*>(smem + OFF_DW);   // [5 taps + bias][32 lanes] float4
 
         int i = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
             const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
-            const int rows_valid = min(TM, p.T - t0);
-            const int s = i & 1, u = i >> 1;
-            // A operand free?  (MMA of the previous tile has read it)
-            if (i > 0 && !mbar_wait(bar_mma + 8 * ((i - 1) & 1), ((i - 1) >> 1) & 1)) failed = true;
+            const int slot = i % NSTAGE;
+            float* Xs = reinterpret_cast<float*>(smem + OFF_XS + (uint32_t)slot * X_STAGE);
+            const bool tr_on = (pw == 0 && lane == 0);
+            if (tr_on) ES_TRACE(1, i, 0);
 
-            if (MODE == MODE_DWCONV) {
+            if (MODE != MODE_GATHER) {
                 // zero the halo / tail rows the bulk copy does not cover (utterance boundaries only)
                 const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
                 const int head = lo - (t0 - HALO), tail0 = hi - (t0 - HALO);
-                if (head > 0 || tail0 < XROWS) {
+                const bool edge = head > 0 || tail0 < XROWS;
+                if (edge) {
                     for (int k = ptid; k < (head + XROWS - tail0) * (CK / 4); k += NPROD) {
                         int r = k / (CK / 4);
                         const int c4 = k - r * (CK / 4);
@@ -231,103 +325,114 @@ umma_dec_kernel(const UmmaDecParams p) {
                         reinterpret_cast<float4*>(Xs + r * CK)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
-                if (!mbar_wait(bar_x, i & 1)) failed = true;
-                named_bar_sync(1, NPROD);              // zero fill visible to every producer warp
-#pragma unroll 1
-                for (int g = 0; g < 2; ++g) {          // warp pw -> output rows 16pw..16pw+15, 8 at a time
-                    const int r0 = pw * 16 + g * 8;
-                    float4 win[12];
+                if (!mbar_wait(bar_x + 8 * slot, (i / NSTAGE) & 1)) failed = true;
+                if (edge) named_bar_sync(1, NPROD);          // zero fill visible to every producer warp
+                if (tr_on) ES_TRACE(1, i, 1);
+            } else {
+                if (ptid < TM) {
+                    const int t = t0 + ptid;
+                    int sidx = -1;
+                    if (t < p.T && t < p.valid_len[b]) {
+                        const int* c = p.cum + (size_t)b * p.n_src;
+                        int lo = 0, hi = p.n_src;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (__ldg(c + mid) > t) hi = mid; else lo = mid + 1;
+                        }
+                        sidx = lo < p.n_src ? lo : -1;
+                    }
+                    srcs[ptid] = sidx;
+                }
+                named_bar_sync(1, NPROD);
+            }
+            // warp pw -> tile rows 16pw..16pw+15 (two 8-row core-matrix groups).  Both groups are computed
+            // into registers BEFORE waiting for the A operand to be released, so that after the previous
+            // GEMM completes only the 32 shared-memory stores remain on the critical path.
+            uint2 ahi[16], alo[16];                          // this lane's share: 16 rows x 4 channels, split fp16
 #pragma unroll
-                    for (int k = 0; k < 12; ++k) win[k] = reinterpret_cast<const float4*>(Xs + (r0 + k) * CK)[lane];
+            for (int pass = 0; pass < 2; ++pass) {
+                const int r0 = pw * 16 + pass * 8;
+                if (MODE != MODE_GATHER) {
+                    // per-lane depthwise taps for channels 4*lane..4*lane+3 (3 KB in shared memory; kept out of
+                    // the persistent register set so the staged A rows fit without spilling)
+                    float4 wdw[DWK], bdw;
+                    if (MODE == MODE_DWCONV) {
+#pragma unroll
+                        for (int t = 0; t < DWK; ++t) wdw[t] = dwp[t * 32 + lane];
+                        bdw = dwp[DWK * 32 + lane];
+                    }
+                    float4 win[8 + 2 * HALO];
+#pragma unroll
+                    for (int k = 0; k < 8 + 2 * HALO; ++k) win[k] = reinterpret_cast<const float4*>(Xs + (r0 + k) * CK)[lane];
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        float4 o = bdw;
+                        float4 o;
+                        if (MODE == MODE_DWCONV) {
+                            o = bdw;
 #pragma unroll
-                        for (int t = 0; t < DWK; ++t) {
-                            o.x = fmaf(wdw[t].x, win[r + t].x, o.x);
-                            o.y = fmaf(wdw[t].y, win[r + t].y, o.y);
-                            o.z = fmaf(wdw[t].z, win[r + t].z, o.z);
-                            o.w = fmaf(wdw[t].w, win[r + t].w, o.w);
-                        }
-                        store_a4(a_hi, r0 + r, lane, o);
-                    }
-                }
-            } else {
-                if (MODE == MODE_GATHER) {
-                    if (ptid < TM) {
-                        const int t = t0 + ptid;
-                        int sidx = -1;
-                        if (t < p.T && t < p.valid_len[b]) {
-                            const int* c = p.cum + (size_t)b * p.n_src;
-                            int lo = 0, hi = p.n_src;
-                            while (lo < hi) {
-                                const int mid = (lo + hi) >> 1;
-                                if (__ldg(c + mid) > t) hi = mid; else lo = mid + 1;
+                            for (int t = 0; t < DWK; ++t) {
+                                o.x = fmaf(wdw[t].x, win[r + t].x, o.x);
+                                o.y = fmaf(wdw[t].y, win[r + t].y, o.y);
+                                o.z = fmaf(wdw[t].z, win[r + t].z, o.z);
+                                o.w = fmaf(wdw[t].w, win[r + t].w, o.w);
                             }
-                            sidx = lo < p.n_src ? lo : -1;
+                        } else {
+                            o = win[r];
                         }
-                        srcs[ptid] = sidx;
+                        split4(o, ahi[pass * 8 + r], alo[pass * 8 + r]);
                     }
-                    named_bar_sync(1, NPROD);
-                }
-#pragma unroll 4
-                for (int r = 0; r < 16; ++r) {
-                    const int row = pw * 16 + r;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (MODE == MODE_GATHER) {
-                        const int sidx = srcs[row];
-                        if (sidx >= 0) v = __ldg(reinterpret_cast<const float4*>(p.X + ((size_t)b * p.n_src + sidx) * CK) + lane);
-                    } else if (row < rows_valid) {
-                        v = __ldg(reinterpret_cast<const float4*>(p.X + ((size_t)b * p.T + t0 + row) * CK) + lane);
+                } else {
+                    float4 rowv[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const int sidx = srcs[r0 + r];
+                        rowv[r] = sidx >= 0 ? __ldg(reinterpret_cast<const float4*>(p.X + ((size_t)b * p.n_src + sidx) * CK) + lane)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    store_a4(a_hi, row, lane, v);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) split4(rowv[r], ahi[pass * 8 + r], alo[pass * 8 + r]);
                 }
             }
+            // this warp has read everything it needs from ring slot `slot` (and from srcs)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_xfree + 8 * slot);
+            if (tr_on) ES_TRACE(1, i, 2);
+            // A operand free?  (the GEMM of the previous tile has read it)
+            if (i > 0 && !mbar_wait(bar_mma + 8 * ((i - 1) & 1), ((i - 1) >> 1) & 1)) failed = true;
+            if (tr_on) ES_TRACE(1, i, 3);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const uint32_t off = a_off(pw * 16 + r, lane);
+                *reinterpret_cast<uint2*>(a_hi + off) = ahi[r];
+                *reinterpret_cast<uint2*>(a_hi + A_PLANE + off) = alo[r];
+            }
+            if (tr_on) ES_TRACE(1, i, 4);
             fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core
             tc_fence_before_sync();
-            named_bar_sync(1, NPROD);
-
-            if (leader) {
-                tc_fence_after_sync();
-                // x of the next tile streams in while this tile's GEMM / epilogue run (Xs is free:
-                // every producer warp passed the barrier above after its last read)
-                if (MODE == MODE_DWCONV && tile + (int)gridDim.x < n_tiles) issue_x(tile + gridDim.x);
-                if (i == 0 && !mbar_wait(bar_w, 0)) failed = true;
-                // accumulator s drained by the epilogue warps (its previous use was tile i-2)?
-                if (u > 0 && !mbar_wait(bar_tfree + 8 * s, (u - 1) & 1)) failed = true;
-                tc_fence_after_sync();
-                const uint32_t a0 = smem_u32(a_hi), w0 = smem_u32(smem + OFF_W);
-                const uint32_t acc = tmem + (uint32_t)(s * 128);
-#pragma unroll 1
-                for (int k = 0; k < CK / 16; ++k) {
-                    const uint64_t dah = make_smem_desc(a0 + (uint32_t)(2 * k) * A_LBO, A_LBO, A_SBO);
-                    const uint64_t dal = make_smem_desc(a0 + A_PLANE + (uint32_t)(2 * k) * A_LBO, A_LBO, A_SBO);
-                    const uint64_t dbh = make_smem_desc(w0 + (uint32_t)(2 * k) * lbo_b, lbo_b, 128u);
-                    const uint64_t dbl = make_smem_desc(w0 + w_plane + (uint32_t)(2 * k) * lbo_b, lbo_b, 128u);
-                    mma_f16_ss(acc, dah, dbh, idesc, k > 0 ? 1u : 0u);
-                    mma_f16_ss(acc, dah, dbl, idesc, 1u);
-                    mma_f16_ss(acc, dal, dbh, idesc, 1u);
-                }
-                mma_commit(bar_mma + 8 * s);
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_aready);
+            if (tr_on) ES_TRACE(1, i, 5);
+            if (MODE == MODE_GATHER) named_bar_sync(1, NPROD);   // srcs reusable
         }
     } else {
         // =========================================================================== epilogue
-        const int q = warp & 3, half = warp >> 2;             // TMEM lane quarter, 16-row half
-        const int rbase = q * 32 + half * 16;
+        const int q = warp & 3, g = warp >> 2;                // TMEM lane quarter; tile parity served by this warp
+        const int rbase = q * 16;                             // tile rows 16q..16q+15 live in lanes 32q+16g..+15
         const int t4 = lane & 3, tr = lane >> 2;
         const float inv_n = 1.f / (float)N;
         const int nj = N >> 3;                                // 8-column groups
 
-        int i = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+        int i = g;
+        for (int tile = blockIdx.x + g * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, i += 2) {
             const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
             const int rows_valid = min(TM, p.T - t0);
-            const int s = i & 1, u = i >> 1;
+            const int u = i >> 1;
             const int row0 = rbase + tr, row1 = row0 + 8;
             const size_t g0 = (size_t)b * p.T + t0 + row0, g1 = g0 + 8;
             const bool ok0 = row0 < rows_valid, ok1 = row1 < rows_valid;
 
+            const bool tr_on = (q == 0 && lane == 0);
+            if (tr_on) ES_TRACE(2 + g, u, 0);
             if (p.res2) {   // pull this warp's 16 skip rows (8 KB) towards L2 while the GEMM runs
                 const int pr = rbase + (lane >> 1);
                 if (pr < rows_valid) {
@@ -336,15 +441,27 @@ umma_dec_kernel(const UmmaDecParams p) {
                     prefetch_l2(sp + 32);
                 }
             }
-            if (!mbar_wait(bar_mma + 8 * s, u & 1)) failed = true;
+            if (!mbar_wait(bar_mma + 8 * g, u & 1)) failed = true;
             tc_fence_after_sync();
+            if (tr_on) ES_TRACE(2 + g, u, 1);
             uint32_t r[64];
-            tmem_ld_16x256b_x16(tmem + (uint32_t)(s * 128) + ((uint32_t)rbase << 16), r);
+            tmem_ld_16x256b_x16(tmem + ((uint32_t)(32 * q + 16 * g) << 16), r);
             tmem_ld_wait();
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tfree + 8 * s);     // accumulator drained: the GEMM of tile i+2 may start
-
+            if (lane == 0) mbar_arrive(bar_tfree + 8 * g);     // accumulator drained: the GEMM of tile i+2 may start
+            if (tr_on) ES_TRACE(2 + g, u, 2);
+            // block-end layers: the 32 skip values of this thread's first row are requested NOW (L2-prefetched
+            // above) and land while the tanh / LayerNorm math below runs; the second row's follow while the
+            // first row is normalised (keeps the live set at 64 + 32 registers)
+            float2 sk[16];
+            const float* s0 = p.res2 + g0 * N + 2 * t4;
+            const float* s1 = p.res2 + g1 * N + 2 * t4;
+            if (p.res2) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    sk[j] = ok0 ? __ldg(reinterpret_cast<const float2*>(s0 + 8 * j)) : make_float2(0.f, 0.f);
+            }
             float v[64];
             if (p.act_tanh) {
 #pragma unroll
@@ -365,18 +482,20 @@ umma_dec_kernel(const UmmaDecParams p) {
                     v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.y;
                 }
             }
-            if (p.ln_g) fragment_layernorm<16>(v, par + 128, par + 256, t4, inv_n);   // LayerNorm only with N == 128
+            if (p.ln_g) fragment_layernorm2(v, par + 128, par + 256, t4, inv_n);   // LayerNorm only with N == 128
+            if (tr_on) ES_TRACE(2 + g, u, 3);
             if (p.res2) {
-                const float* s0 = p.res2 + g0 * N + 2 * t4;
-                const float* s1 = p.res2 + g1 * N + 2 * t4;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float2 a = ok0 ? __ldg(reinterpret_cast<const float2*>(s0 + 8 * j)) : make_float2(0.f, 0.f);
-                    const float2 c = ok1 ? __ldg(reinterpret_cast<const float2*>(s1 + 8 * j)) : make_float2(0.f, 0.f);
-                    v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += c.x; v[4 * j + 3] += c.y;
-                }
-                fragment_layernorm<16>(v, par + 384, par + 512, t4, inv_n);
+                for (int j = 0; j < 16; ++j) { v[4 * j] += sk[j].x; v[4 * j + 1] += sk[j].y; }
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    sk[j] = ok1 ? __ldg(reinterpret_cast<const float2*>(s1 + 8 * j)) : make_float2(0.f, 0.f);
+                fragment_layernorm_row<0>(v, par + 384, par + 512, t4, inv_n);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { v[4 * j + 2] += sk[j].x; v[4 * j + 3] += sk[j].y; }
+                fragment_layernorm_row<1>(v, par + 384, par + 512, t4, inv_n);
             }
+            if (tr_on) ES_TRACE(2 + g, u, 4);
             const int zero_from = p.zero_from ? p.zero_from[b] : 0x7fffffff;
             const bool z0 = (t0 + row0) >= zero_from, z1 = (t0 + row1) >= zero_from;
             float* y0 = p.Y + g0 * N + 2 * t4;
@@ -388,16 +507,19 @@ umma_dec_kernel(const UmmaDecParams p) {
                     if (ok1) *reinterpret_cast<float2*>(y1 + 8 * j) = z1 ? make_float2(0.f, 0.f) : make_float2(v[4 * j + 2], v[4 * j + 3]);
                 }
             }
+            if (tr_on) ES_TRACE(2 + g, u, 5);
         }
     }
 
     if (failed) atomicExch(p.err, 1);
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
 int* g_err_flag = nullptr;
+long long* g_trace = nullptr;
+int g_trace_pick = 0, g_trace_count = 0;   // which launch after es_debug_set_trace is stamped (env ES_TRACE_LAUNCH)
 
 template <int MODE>
 int launch_mode(const UmmaDecParams& p, int grid, cudaStream_t s) {
@@ -440,7 +562,7 @@ int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, co
     p.B = B; p.T = T; p.N = N; p.n_src = n_src; p.X = X; p.cum = cum; p.valid_len = valid_len;
     p.dw_w = dw_w; p.dw_b = dw_b; p.w_h16 = w_h16; p.bias = bias; p.act_tanh = act_tanh;
     p.ln_g = ln_g; p.ln_b = ln_b; p.res2 = res2; p.ln2_g = ln2_g; p.ln2_b = ln2_b;
-    p.zero_from = zero_from; p.Y = Y; p.err = g_err_flag;
+    p.zero_from = zero_from; p.Y = Y; p.err = g_err_flag; p.trace = (g_trace && g_trace_count++ == g_trace_pick) ? g_trace : nullptr;
     const int n_tiles = B * ((T + TM - 1) / TM);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
     switch (mode) {
@@ -448,6 +570,14 @@ int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, co
         case MODE_GATHER: return launch_mode<MODE_GATHER>(p, grid, s);
         default: return launch_mode<MODE_PLAIN>(p, grid, s);
     }
+}
+
+// debug: subsequent tcgen05 decoder launches stamp clock64() per role/tile/event into buf (CTA 0)
+void umma_dec_set_trace(long long* buf) {
+    g_trace = buf;
+    g_trace_count = 0;
+    const char* e = getenv("ES_TRACE_LAUNCH");
+    g_trace_pick = e ? atoi(e) : 0;
 }
 
 // Reads (and clears) the device-side mbarrier-timeout flag; synchronises the stream.

@@ -193,6 +193,10 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
  * the GPU.  This call synchronises `stream` and returns non-zero if the flag was raised. */
 int es_check_async_errors(void* stream);
 
+/* Debug aid: when non-NULL, CTA 0 of every subsequent tcgen05 decoder launch writes clock64() stamps
+ * [4 roles][32 tiles][8 events] (int64, device memory) -- tools/trace_decoder.py.  NULL turns it off. */
+int es_debug_set_trace(void* dev_buf_i64);
+
 /* Number of kernels the library has launched since process start (bench.py's gpu_launches). */
 uint64_t es_launch_count(void);
 
