@@ -76,7 +76,7 @@ inline int enc_n1(const es_model* m, int N) {
 }
 
 struct EncBufs {
-    float *x0, *qkv, *att, *x1, *h, *feat0, *xm1, *feat1, *fused, *y1, *dur_feat;
+    float *x0, *qkv, *att, *x1, *h, *feat0, *xm1, *feat1, *fused, *y1[3], *dur_feat;
     uint8_t* mask1;
 };
 
@@ -94,7 +94,7 @@ EncBufs plan_encoder(const es_model* m, Arena& a, int B, int N) {
     e.xm1 = a.take<float>(r1 * m->C[1]);
     e.feat1 = a.take<float>(r1 * m->C[1]);
     e.fused = a.take<float>(r0 * m->d);
-    e.y1 = a.take<float>(r0 * m->d);
+    for (int i = 0; i < 3; ++i) e.y1[i] = a.take<float>(r0 * m->d);
     e.dur_feat = a.take<float>(r0 * m->d);
     e.mask1 = a.take<uint8_t>(r1);
     return e;
@@ -147,20 +147,50 @@ int encoder_block(const es_model* m, int i, int B, int n, const float* x_in, con
     return launch_rowgemm(p, s);
 }
 
-// AcousticDecoder.forward (networks.py:151-165)
-int predictor(const es_model* m, const es_predictor_w_t& w, int B, int N, const float* fused, float* y1,
-              float* pred, bool is_duration, float* feat_out, cudaStream_t s) {
+// AcousticDecoder.forward (networks.py:151-165), stage 1: y1 = ReLU(LN1(ReLU(conv1(fused))))
+RowGemmParams predictor_stage1(const es_model* m, const es_predictor_w_t& w, int B, int N, const float* fused, float* y1) {
     const int d = m->d;
     RowGemmParams p = base_params(B, N, N, d, d, fused, d, w.conv1_w, y1, d);
     p.taps = 3; p.pad = 1; p.bias = w.conv1_b; p.act1 = ACT_RELU;
     p.ln_g = w.ln1_g; p.ln_b = w.ln1_b; p.act2 = ACT_RELU;
-    { ProfRange r(ES_K_PREDICTOR, s); if (launch_rowgemm(p, s)) return 1; }
-    p = base_params(B, N, N, d, d, y1, d, w.conv2_w, is_duration ? feat_out : nullptr, d);
+    return p;
+}
+// stage 2: y = ReLU(conv2(y1)); pred = (ReLU)(y . w + b); duration only: feat = LN2(y)
+RowGemmParams predictor_stage2(const es_model* m, const es_predictor_w_t& w, int B, int N, const float* y1, float* pred,
+                               bool is_duration, float* feat_out) {
+    const int d = m->d;
+    RowGemmParams p = base_params(B, N, N, d, d, y1, d, w.conv2_w, is_duration ? feat_out : nullptr, d);
     p.taps = 3; p.pad = 1; p.bias = w.conv2_b; p.act1 = ACT_RELU;
     p.dot_w = w.lin_w; p.dot_b = w.lin_b; p.dot_out = pred; p.dot_relu = is_duration ? 1 : 0;
     if (is_duration) { p.ln_g = w.ln2_g; p.ln_b = w.ln2_b; }   // norm2 output is only consumed for duration
-    ProfRange r(ES_K_PREDICTOR, s);
-    return launch_rowgemm(p, s);
+    return p;
+}
+
+// The three predictors are independent: each stage runs as ONE batched launch when the narrow kernel
+// applies (d <= 96), else as three launches.
+int predictors(const es_model* m, int B, int N, const float* fused, float* const y1[3], float* pitch_pred,
+               float* energy_pred, float* dur_pred, float* dur_feat, cudaStream_t s) {
+    const es_predictor_w_t* w[3] = {&m->w.pitch, &m->w.energy, &m->w.duration};
+    float* preds[3] = {pitch_pred, energy_pred, dur_pred};
+    RowGemmParams st1[3], st2[3];
+    for (int i = 0; i < 3; ++i) {
+        st1[i] = predictor_stage1(m, *w[i], B, N, fused, y1[i]);
+        st2[i] = predictor_stage2(m, *w[i], B, N, y1[i], preds[i], i == 2, i == 2 ? dur_feat : nullptr);
+    }
+    // stage 2 differs between predictors only in pointers / LN2 / relu flags; geometry is identical
+    {
+        ProfRange r(ES_K_PREDICTOR, s);
+        const int rc = launch_rowgemm_narrow_batch(st1, 3, s);
+        if (rc > 0) return 1;
+        if (rc < 0) for (int i = 0; i < 3; ++i) if (launch_rowgemm(st1[i], s)) return 1;
+    }
+    {
+        ProfRange r(ES_K_PREDICTOR, s);
+        const int rc = launch_rowgemm_narrow_batch(st2, 3, s);
+        if (rc > 0) return 1;
+        if (rc < 0) for (int i = 0; i < 3; ++i) if (launch_rowgemm(st2[i], s)) return 1;
+    }
+    return 0;
 }
 
 int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, const int* zero_from,
@@ -296,9 +326,7 @@ int es_encoder_forward(es_model_t* m, void* stream, int B, int N,
       if (launch_fuse(e.feat0, e.feat1, m->w.fuse_a0, m->w.fuse_g, m->w.fuse_gb, m->w.fuse_c, phoneme_mask,
                       e.fused, B, N, n1, d, m->k[0], s)) return 1; }
     // predictors (networks.py:349,357,366)
-    if (predictor(m, m->w.pitch, B, N, e.fused, e.y1, pitch_pred, false, nullptr, s)) return 1;
-    if (predictor(m, m->w.energy, B, N, e.fused, e.y1, energy_pred, false, nullptr, s)) return 1;
-    if (predictor(m, m->w.duration, B, N, e.fused, e.y1, dur_pred, true, e.dur_feat, s)) return 1;
+    if (predictors(m, B, N, e.fused, e.y1, pitch_pred, energy_pred, dur_pred, e.dur_feat, s)) return 1;
     // variance embeddings, concat, duration rounding, integer scan (networks.py:349-384, 234, 255)
     ProfRange r(ES_K_VARIANCE, s);
     return launch_variance_scan(e.fused, e.dur_feat, pitch_pred, energy_pred, dur_pred, pitch_tgt, energy_tgt,

@@ -119,5 +119,7 @@ struct RowGemmParams {
 };
 
 int launch_rowgemm(const RowGemmParams& p, cudaStream_t stream);
+int launch_rowgemm_narrow(const RowGemmParams& p, cudaStream_t stream);   // -1: not applicable
+int launch_rowgemm_narrow_batch(const RowGemmParams* ps, int count, cudaStream_t stream);   // -1: not applicable
 
 }  // namespace es

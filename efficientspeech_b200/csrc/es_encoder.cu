@@ -247,11 +247,98 @@ fuse_kernel(const float* __restrict__ f0, const float* __restrict__ f1, const fl
         if (j < nj) out[row * d + lane + 32 * j] = zero ? 0.f : acc[j];
 }
 
+// Thread-per-row variant for d <= 64: all folded weights in shared memory (warp-wide broadcast
+// reads), the d accumulators of a row in registers.
+template <int D>
+__global__ void __launch_bounds__(128)
+fuse_narrow_kernel(const float* __restrict__ f0, const float* __restrict__ f1, const float* __restrict__ a0,
+                   const float* __restrict__ g, const float* __restrict__ gb, const float* __restrict__ cst,
+                   const uint8_t* __restrict__ mask, float* __restrict__ out, int B, int N, int n1, int k) {
+    extern __shared__ __align__(16) float sw[];
+    float* sA0 = sw;                       // [D][D]
+    float* sG = sA0 + D * D;               // [k][2D][D]
+    float* sGb = sG + k * 2 * D * D;       // [k][D]
+    float* sC = sGb + k * D;               // [D]
+    for (int i = threadIdx.x; i < D * D; i += 128) sA0[i] = __ldg(a0 + i);
+    for (int i = threadIdx.x; i < k * 2 * D * D; i += 128) sG[i] = __ldg(g + i);
+    for (int i = threadIdx.x; i < k * D; i += 128) sGb[i] = __ldg(gb + i);
+    for (int i = threadIdx.x; i < D; i += 128) sC[i] = __ldg(cst + i);
+    __syncthreads();
+    const long long row = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (row >= (long long)B * N) return;
+    const int t = (int)(row % N);
+    const long long b = row / N;
+    float acc[D];
+#pragma unroll
+    for (int n = 0; n < D; ++n) acc[n] = sC[n];
+    {
+        const float4* x4 = reinterpret_cast<const float4*>(f0 + row * D);
+#pragma unroll 2
+        for (int k4 = 0; k4 < D / 4; ++k4) {
+            const float4 xv = __ldg(x4 + k4);
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4* w4 = reinterpret_cast<const float4*>(sA0 + (k4 * 4 + kk) * D);
+#pragma unroll
+                for (int n4 = 0; n4 < D / 4; ++n4) {
+                    const float4 w = w4[n4];
+                    acc[4 * n4] = fmaf(xs[kk], w.x, acc[4 * n4]); acc[4 * n4 + 1] = fmaf(xs[kk], w.y, acc[4 * n4 + 1]);
+                    acc[4 * n4 + 2] = fmaf(xs[kk], w.z, acc[4 * n4 + 2]); acc[4 * n4 + 3] = fmaf(xs[kk], w.w, acc[4 * n4 + 3]);
+                }
+            }
+        }
+    }
+    for (int tau = (t & 1); tau < k; tau += 2) {      // 2j + tau = t  ->  tau has the parity of t
+        const int j1 = (t - tau) >> 1;
+        if (t - tau < 0 || j1 >= n1) continue;
+#pragma unroll
+        for (int n = 0; n < D; ++n) acc[n] += sGb[tau * D + n];
+        const float4* x4 = reinterpret_cast<const float4*>(f1 + ((size_t)b * n1 + j1) * (2 * D));
+        const float* gt = sG + (size_t)tau * 2 * D * D;
+#pragma unroll 2
+        for (int k4 = 0; k4 < (2 * D) / 4; ++k4) {
+            const float4 xv = __ldg(x4 + k4);
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4* w4 = reinterpret_cast<const float4*>(gt + (k4 * 4 + kk) * D);
+#pragma unroll
+                for (int n4 = 0; n4 < D / 4; ++n4) {
+                    const float4 w = w4[n4];
+                    acc[4 * n4] = fmaf(xs[kk], w.x, acc[4 * n4]); acc[4 * n4 + 1] = fmaf(xs[kk], w.y, acc[4 * n4 + 1]);
+                    acc[4 * n4 + 2] = fmaf(xs[kk], w.z, acc[4 * n4 + 2]); acc[4 * n4 + 3] = fmaf(xs[kk], w.w, acc[4 * n4 + 3]);
+                }
+            }
+        }
+    }
+    const bool zero = mask && mask[row];
+    float4* o4 = reinterpret_cast<float4*>(out + row * D);
+#pragma unroll
+    for (int n4 = 0; n4 < D / 4; ++n4)
+        o4[n4] = zero ? make_float4(0.f, 0.f, 0.f, 0.f)
+                      : make_float4(acc[4 * n4], acc[4 * n4 + 1], acc[4 * n4 + 2], acc[4 * n4 + 3]);
+}
+
 int launch_fuse(const float* f0, const float* f1, const float* a0, const float* g, const float* gb,
                 const float* cst, const uint8_t* mask, float* out, int B, int N, int n1, int d, int k,
                 cudaStream_t s) {
     ES_CHECK(d % 32 == 0 && d <= 128, "fuse width must be 32..128");
     const long long rows = (long long)B * N;
+    const size_t smem = ((size_t)d * d + (size_t)k * 2 * d * d + (size_t)k * d + d) * sizeof(float);
+    if ((d == 32 || d == 64) && smem <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            ES_CUDA(cudaFuncSetAttribute(fuse_narrow_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ES_CUDA(cudaFuncSetAttribute(fuse_narrow_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        const unsigned grid = (unsigned)((rows + 127) / 128);
+        if (d == 32) fuse_narrow_kernel<32><<<grid, 128, smem, s>>>(f0, f1, a0, g, gb, cst, mask, out, B, N, n1, k);
+        else fuse_narrow_kernel<64><<<grid, 128, smem, s>>>(f0, f1, a0, g, gb, cst, mask, out, B, N, n1, k);
+        ES_LAUNCH_OK();
+        return 0;
+    }
     fuse_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(f0, f1, a0, g, gb, cst, mask, out, B, N, n1, d, k);
     ES_LAUNCH_OK();
     return 0;

@@ -21,7 +21,7 @@ from torch import nn
 from . import _cabi, packing
 from .config import ESConfig, N_SYMBOLS
 
-__all__ = ["PhonemeEncoder", "MelDecoder", "Phoneme2Mel", "Encoder", "Fuse", "AcousticDecoder",
+__all__ = ["PhonemeEncoder", "MelDecoder", "Phoneme2Mel", "GraphedForward", "Encoder", "Fuse", "AcousticDecoder",
            "FeatureUpsampler", "SelfAttention", "MixFFN"]
 
 
@@ -422,6 +422,16 @@ class Phoneme2Mel(nn.Module):
         with torch.cuda.device(dev):
             _cabi.check(_cabi.load().es_check_async_errors(_stream(dev)))
 
+    def capture(self, x, train=True):
+        """CUDA-graph the whole forward for a fixed batch geometry (B, N, T).
+
+        The path is ~30 small launches; replaying one graph removes the per-launch host cost.
+        Needs a host-sync-free call: teacher-forced (``train=True``) with ``x["max_mel_len"]``
+        given.  Returns a ``GraphedForward``: call it with a batch dict of the same shapes (its
+        tensors are copied into static buffers) or with no argument to replay on the static
+        inputs; the outputs live in static buffers that are overwritten by the next replay."""
+        return GraphedForward(self, x, train)
+
     def forward(self, x, train=False):
         if isinstance(x, list):                                         # networks.py:418
             x = x[0]
@@ -441,3 +451,32 @@ class Phoneme2Mel(nn.Module):
                 self.encoder._expand(pred)
             return pred
         return mel, pred["mel_len"], pred["duration"]
+
+
+class GraphedForward:
+    """One captured CUDA graph of ``Phoneme2Mel.forward`` (see ``Phoneme2Mel.capture``)."""
+
+    def __init__(self, model, x, train=True):
+        if not train or x.get("max_mel_len") is None:
+            raise ValueError("graph capture needs the sync-free call: train=True and x['max_mel_len']")
+        self.model, self.train = model, train
+        self.static_in = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in x.items()}
+        dev = self.static_in["phoneme"].device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                      # packs weights, sets kernel attributes, sizes the workspace
+                model(self.static_in, train=train)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = model(self.static_in, train=train)
+
+    def __call__(self, x=None):
+        if x is not None:
+            for k, v in x.items():
+                if torch.is_tensor(v):
+                    self.static_in[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
