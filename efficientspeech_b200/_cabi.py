@@ -8,7 +8,7 @@ from typing import Optional
 
 from . import build as _build
 
-ES_ABI_VERSION = 5
+ES_ABI_VERSION = 6
 ES_MAX_ENC_BLOCKS = 2
 ES_MAX_DEC_LAYERS = 24
 ES_MAX_DEC_BLOCKS = 8
@@ -27,13 +27,13 @@ class es_config_t(C.Structure):
 class es_enc_block_w_t(C.Structure):
     _fields_ = [(n, _fp) for n in (
         "merge_w", "qkv_w", "proj_w", "proj_b", "ln1_g", "ln1_b", "ffn1_w", "ffn1_tapb", "ffn1_b",
-        "ffn2_w", "ffn2_b", "ln2_g", "ln2_b")]
+        "ffn2_w", "ffn2_b", "ln2_g", "ln2_b", "merge_w_h16", "qkv_w_h16", "proj_w_h16", "ffn1_w_h16", "ffn2_w_h16")]
 
 
 class es_predictor_w_t(C.Structure):
     _fields_ = [(n, _fp) for n in (
         "conv1_w", "conv1_b", "ln1_g", "ln1_b", "conv2_w", "conv2_b", "ln2_g", "ln2_b", "lin_w", "lin_b",
-        "bins", "table")]
+        "bins", "table", "conv1_w_h16", "conv2_w_h16")]
 
 
 class es_dec_layer_w_t(C.Structure):

@@ -121,6 +121,15 @@ RowGemmParams base_params(int B, int n_in, int n_out, int K, int Nout, const flo
     return p;
 }
 
+// Dense layer: tcgen05 row GEMM when the layer is inside its envelope, fp32 SIMT otherwise.
+int gemm(const es_model* m, const RowGemmParams& p, const void* w_h16, cudaStream_t s) {
+    if (m->use_tensor_core && w_h16) {
+        const int rc = launch_umma_rowgemm(p, w_h16, s);
+        if (rc >= 0) return rc;
+    }
+    return launch_rowgemm(p, s);
+}
+
 // One encoder block after its merge conv (networks.py:72-85).
 int encoder_block(const es_model* m, int i, int B, int n, const float* x_in, const uint8_t* mask,
                   const EncBufs& e, float* feat_out, cudaStream_t s) {
@@ -128,23 +137,23 @@ int encoder_block(const es_model* m, int i, int B, int n, const float* x_in, con
     const int C = m->C[i], H = m->H[i], hC = m->hC[i];
     // qkv = x Wqkv^T                                                            blocks.py:45
     RowGemmParams p = base_params(B, n, n, C, 3 * H * C, x_in, C, w.qkv_w, e.qkv, 3 * H * C);
-    { ProfRange r(ES_K_ENC_GEMM, s); if (launch_rowgemm(p, s)) return 1; }
+    { ProfRange r(ES_K_ENC_GEMM, s); if (gemm(m, p, w.qkv_w_h16, s)) return 1; }
     // softmax(QK^T scale) V, all keys (mask never applied)                         blocks.py:49-65
     const float scale = 1.0f / sqrtf((float)(C / H));
     { ProfRange r(ES_K_ATTENTION, s); if (launch_attention(e.qkv, e.att, B, n, C, H, scale, s)) return 1; }
     // x1 = mask(LN1(proj(att) + x))                                                blocks.py:66, networks.py:73-75
     p = base_params(B, n, n, H * C, C, e.att, H * C, w.proj_w, e.x1, C);
     p.bias = w.proj_b; p.res1 = x_in; p.ldr1 = C; p.ln_g = w.ln1_g; p.ln_b = w.ln1_b; p.row_mask = mask;
-    { ProfRange r(ES_K_ENC_GEMM, s); if (launch_rowgemm(p, s)) return 1; }
+    { ProfRange r(ES_K_ENC_GEMM, s); if (gemm(m, p, w.proj_w_h16, s)) return 1; }
     // h = GELU(conv3(mlp1(x1)))  with mlp1 folded into the conv taps               blocks.py:23-27
     p = base_params(B, n, n, C, hC, e.x1, C, w.ffn1_w, e.h, hC);
     p.taps = 3; p.pad = 1; p.bias = w.ffn1_b; p.tap_bias = w.ffn1_tapb; p.act1 = ACT_GELU;
-    { ProfRange r(ES_K_ENC_GEMM, s); if (launch_rowgemm(p, s)) return 1; }
+    { ProfRange r(ES_K_ENC_GEMM, s); if (gemm(m, p, w.ffn1_w_h16, s)) return 1; }
     // feat = mask(LN2(mlp2(h) + x1))                                               blocks.py:28, networks.py:80-83
     p = base_params(B, n, n, hC, C, e.h, hC, w.ffn2_w, feat_out, C);
     p.bias = w.ffn2_b; p.res1 = e.x1; p.ldr1 = C; p.ln_g = w.ln2_g; p.ln_b = w.ln2_b; p.row_mask = mask;
     ProfRange r(ES_K_ENC_GEMM, s);
-    return launch_rowgemm(p, s);
+    return gemm(m, p, w.ffn2_w_h16, s);
 }
 
 // AcousticDecoder.forward (networks.py:151-165), stage 1: y1 = ReLU(LN1(ReLU(conv1(fused))))
@@ -176,6 +185,24 @@ int predictors(const es_model* m, int B, int N, const float* fused, float* const
     for (int i = 0; i < 3; ++i) {
         st1[i] = predictor_stage1(m, *w[i], B, N, fused, y1[i]);
         st2[i] = predictor_stage2(m, *w[i], B, N, y1[i], preds[i], i == 2, i == 2 ? dur_feat : nullptr);
+    }
+    // tensor-core path: six small launches (one per predictor and stage); the three predictors share
+    // their geometry, so the envelope check of the first decides for all
+    if (m->use_tensor_core && w[0]->conv1_w_h16 && w[0]->conv2_w_h16) {
+        int rc;
+        { ProfRange r(ES_K_PREDICTOR, s); rc = launch_umma_rowgemm(st1[0], w[0]->conv1_w_h16, s); }
+        if (rc > 0) return 1;
+        if (rc == 0) {
+            for (int i = 1; i < 3; ++i) {
+                ProfRange r(ES_K_PREDICTOR, s);
+                if (gemm(m, st1[i], w[i]->conv1_w_h16, s)) return 1;
+            }
+            for (int i = 0; i < 3; ++i) {
+                ProfRange r(ES_K_PREDICTOR, s);
+                if (gemm(m, st2[i], w[i]->conv2_w_h16, s)) return 1;
+            }
+            return 0;
+        }
     }
     // stage 2 differs between predictors only in pointers / LN2 / relu flags; geometry is identical
     {
@@ -311,7 +338,7 @@ int es_encoder_forward(es_model_t* m, void* stream, int B, int N,
         RowGemmParams p = base_params(B, N, n1, m->C[0], m->C[1], e.feat0, m->C[0], m->w.enc[1].merge_w, e.xm1, m->C[1]);
         p.taps = m->k[1]; p.stride = 2; p.pad = m->k[1] / 2;
         ProfRange r(ES_K_ENC_GEMM, s);
-        if (launch_rowgemm(p, s)) return 1;
+        if (gemm(m, p, m->w.enc[1].merge_w_h16, s)) return 1;
     }
     const uint8_t* mask1 = nullptr;
     if (phoneme_mask) {

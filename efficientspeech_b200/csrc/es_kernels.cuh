@@ -29,5 +29,9 @@ int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, co
                     float* Y, cudaStream_t s);
 int umma_dec_check_errors(cudaStream_t s);
 void umma_dec_set_trace(long long* buf);
+int* umma_err_flag();
+
+// tcgen05 row GEMM for the phoneme-side layers (es_umma_enc.cu); -1: outside its envelope
+int launch_umma_rowgemm(const RowGemmParams& p, const void* w_h16, cudaStream_t s);
 
 }  // namespace es

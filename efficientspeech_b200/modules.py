@@ -171,6 +171,20 @@ class _Backend:
         lib = _cabi.load()
         sd = self._state()
         folded = packing.fold_encoder(sd, self.cfg) if self.part == "encoder" else packing.fold_decoder(sd, self.cfg)
+        if self.part == "encoder":
+            # B operands of the tcgen05 row GEMM (layers inside its envelope: K <= 128, multiples of 16)
+            c = self.cfg
+            for i in range(2):
+                ci, hi, hci = c.enc_dims[i], c.enc_heads[i], c.enc_dims[i] * c.expansion
+                if i == 1:
+                    folded["enc1.merge_w_h16"] = packing.canon_split_taps(folded["enc1.merge_w"], ci)
+                folded[f"enc{i}.qkv_w_h16"] = packing.canon_split_taps(folded[f"enc{i}.qkv_w"], 3 * hi * ci)
+                folded[f"enc{i}.proj_w_h16"] = packing.canon_split_taps(folded[f"enc{i}.proj_w"], ci)
+                folded[f"enc{i}.ffn1_w_h16"] = packing.canon_split_taps(folded[f"enc{i}.ffn1_w"], hci)
+                folded[f"enc{i}.ffn2_w_h16"] = packing.canon_split_taps(folded[f"enc{i}.ffn2_w"], ci)
+            for which in ("pitch", "energy", "duration"):
+                for cv in ("conv1", "conv2"):
+                    folded[f"{which}.{cv}_w_h16"] = packing.canon_split_taps(folded[f"{which}.{cv}_w"], c.dim)
         if self.part == "decoder":
             # B operands of the tcgen05 kernels: W as [N][K], split into fp16 hi/lo, canonical order
             for l in range(self.cfg.n_dec_layers):
@@ -188,7 +202,8 @@ class _Backend:
         if self.part == "encoder":
             for i in range(2):
                 for f, _ in _cabi.es_enc_block_w_t._fields_:
-                    setattr(W.enc[i], f, at(f"enc{i}.{f}"))
+                    if f"enc{i}.{f}" in off:
+                        setattr(W.enc[i], f, at(f"enc{i}.{f}"))
             for f in ("fuse_a0", "fuse_g", "fuse_gb", "fuse_c"):
                 setattr(W, f, at(f))
             for which in ("pitch", "energy", "duration"):

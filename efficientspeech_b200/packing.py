@@ -152,6 +152,13 @@ def canon_split_fp16(w_nk: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(planes).reshape(-1).view(np.float32)
 
 
+def canon_split_taps(w_tkn: np.ndarray, n: int) -> np.ndarray:
+    """Folded conv weight [taps][K][N_padded] -> per-tap canonical split-fp16 images
+    ``[taps][2 (hi, lo)][K/8][N][8]`` for the tcgen05 row GEMM (es_umma_enc.cu)."""
+    taps = w_tkn.shape[0]
+    return np.concatenate([canon_split_fp16(np.ascontiguousarray(w_tkn[t].T[:n])) for t in range(taps)])
+
+
 def pack(folded: Dict[str, np.ndarray]) -> Tuple[np.ndarray, Dict[str, int]]:
     """Concatenate the folded arrays (fp32, 256-byte aligned) -> (flat buffer, element offsets)."""
     offsets: Dict[str, int] = {}

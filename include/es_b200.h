@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ES_ABI_VERSION 5
+#define ES_ABI_VERSION 6
 #define ES_MAX_ENC_BLOCKS 2
 #define ES_MAX_DEC_LAYERS 24
 #define ES_MAX_DEC_BLOCKS 8
@@ -70,6 +70,13 @@ typedef struct es_enc_block_w {
     const float* ffn2_b;
     const float* ln2_g;      /* networks.py:80 */
     const float* ln2_b;
+    /* split-fp16 images for the tcgen05 row GEMM, UMMA canonical K-major no-swizzle order
+     * [taps][2 (hi, lo)][K/8][N][8] halves; NULL -> the fp32 SIMT kernel is used */
+    const void*  merge_w_h16;   /* block 1 only */
+    const void*  qkv_w_h16;
+    const void*  proj_w_h16;
+    const void*  ffn1_w_h16;
+    const void*  ffn2_w_h16;
 } es_enc_block_w_t;
 
 typedef struct es_predictor_w {     /* AcousticDecoder, networks.py:98-122,151-165 */
@@ -85,6 +92,8 @@ typedef struct es_predictor_w {     /* AcousticDecoder, networks.py:98-122,151-1
     const float* lin_b;      /* [1] */
     const float* bins;       /* [d-1]  (pitch / energy) or NULL */
     const float* table;      /* [d][d] (pitch / energy) or NULL */
+    const void*  conv1_w_h16; /* [3][2][d/8][d][8] halves or NULL */
+    const void*  conv2_w_h16;
 } es_predictor_w_t;
 
 typedef struct es_dec_layer_w {     /* networks.py:279-283 */
