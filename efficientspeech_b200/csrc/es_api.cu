@@ -140,7 +140,12 @@ int encoder_block(const es_model* m, int i, int B, int n, const float* x_in, con
     { ProfRange r(ES_K_ENC_GEMM, s); if (gemm(m, p, w.qkv_w_h16, s)) return 1; }
     // softmax(QK^T scale) V, all keys (mask never applied)                         blocks.py:49-65
     const float scale = 1.0f / sqrtf((float)(C / H));
-    { ProfRange r(ES_K_ATTENTION, s); if (launch_attention(e.qkv, e.att, B, n, C, H, scale, s)) return 1; }
+    {
+        ProfRange r(ES_K_ATTENTION, s);
+        int rc = m->use_tensor_core ? launch_umma_attention(e.qkv, e.att, B, n, C, H, scale, s) : -1;
+        if (rc > 0) return 1;
+        if (rc < 0 && launch_attention(e.qkv, e.att, B, n, C, H, scale, s)) return 1;
+    }
     // x1 = mask(LN1(proj(att) + x))                                                blocks.py:66, networks.py:73-75
     p = base_params(B, n, n, H * C, C, e.att, H * C, w.proj_w, e.x1, C);
     p.bias = w.proj_b; p.res1 = x_in; p.ldr1 = C; p.ln_g = w.ln1_g; p.ln_b = w.ln1_b; p.row_mask = mask;

@@ -427,7 +427,9 @@ class Phoneme2Mel(nn.Module):
         self.return_features = True
 
     def set_tensor_core(self, enable: bool) -> None:
+        """True (default): tcgen05 kernels wherever a layer is inside their envelope; False: fp32 SIMT only."""
         self.decoder.set_tensor_core(enable)
+        self.encoder._backend.tensor_core = bool(enable)
 
     @staticmethod
     def check_async_errors(device=None) -> None:
