@@ -374,12 +374,17 @@ def run_b200_arm(a):
     layer_flops = B * T * (2 * cfg.dx2 * cfg.dx2 + 2 * cfg.decoder_kernel_size * cfg.dx2)
     dl = per_kind.get("dec_layer", [])
     roof = None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.isfile(tpath) and a.variant == "tiny" and B == 256 and T == 768 and not a.simt:
+        with open(tpath) as f:
+            traffic = float(json.load(f)["dram_bytes_per_launch"])      # one ncu --set full capture (same shape)
     if dl:
         avg_ms = float(np.mean(dl))
         achieved = layer_bytes / (avg_ms * 1e-3) / 1e9
         roof = {"kernel": "decoder layer (dwconv k5 + 1x1 GEMM + bias + tanh + LN [+ skip + LN])",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": avg_ms, "launches_timed": len(dl),
                 "algorithmic_bytes_per_launch": layer_bytes,
                 "tensor_frac_algorithmic": layer_flops / (avg_ms * 1e-3) / 1e12 / tf_peak,
