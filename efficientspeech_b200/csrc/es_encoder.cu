@@ -410,18 +410,20 @@ variance_scan_kernel(const float* __restrict__ fused, const float* __restrict__ 
         __syncthreads();
     }
     if (tid == 0) mel_len[b] = carry_s;
-    // ---- concat rows (coalesced over the 4d channels)
-    const int d4 = 4 * d;
-    for (int idx = tid; idx < N * d4; idx += 256) {
-        const int n = idx / d4, c = idx - n * d4;
+    // ---- concat rows: 4 channels (one float4) per thread step; group boundaries are multiples of d (>= 32)
+    const int d4 = 4 * d, q4 = d4 >> 2;
+    for (int idx = tid; idx < N * q4; idx += 256) {
+        const int n = idx / q4, c = (idx - n * q4) * 4;
         const bool pad = mask && mask[rb + n];
         const int grp = c / d, cc = c - grp * d;
-        float v;
-        if (grp == 0) v = fused[(rb + n) * d + cc];                       // already masked by the fuse stage
-        else if (grp == 1) v = pad ? 0.f : __ldg(ptab + (size_t)sidx[n] * d + cc);
-        else if (grp == 2) v = pad ? 0.f : __ldg(etab + (size_t)sidx[N + n] * d + cc);
-        else v = pad ? 0.f : dur_feat[(rb + n) * d + cc];
-        fused4[(rb + n) * d4 + c] = v;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (grp == 0) v = *reinterpret_cast<const float4*>(fused + (rb + n) * d + cc);        // already masked by the fuse stage
+        else if (!pad) {
+            if (grp == 1) v = __ldg(reinterpret_cast<const float4*>(ptab + (size_t)sidx[n] * d + cc));
+            else if (grp == 2) v = __ldg(reinterpret_cast<const float4*>(etab + (size_t)sidx[N + n] * d + cc));
+            else v = *reinterpret_cast<const float4*>(dur_feat + (rb + n) * d + cc);
+        }
+        *reinterpret_cast<float4*>(fused4 + (rb + n) * d4 + c) = v;
     }
 }
 

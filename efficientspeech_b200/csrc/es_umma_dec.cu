@@ -260,6 +260,15 @@ umma_dec_kernel(const UmmaDecParams p) {
                 if (edge) named_bar_sync(1, NPROD);          // zero fill visible to every producer warp
                 if (tr_on) ES_TRACE(1, i, 1);
             } else {
+                // length regulator: stage this utterance's duration prefix sums in shared memory (the x
+                // ring is unused in this mode), then every frame of the tile finds its source phoneme
+                // by an upper_bound in shared memory instead of ~8 dependent L2 round trips
+                int* scum = reinterpret_cast<int*>(smem + OFF_XS);
+                const bool cum_in_smem = p.n_src <= 8192;
+                if (cum_in_smem) {
+                    for (int k = ptid; k < p.n_src; k += NPROD) scum[k] = __ldg(p.cum + (size_t)b * p.n_src + k);
+                    named_bar_sync(1, NPROD);
+                }
                 if (ptid < TM) {
                     const int t = t0 + ptid;
                     int sidx = -1;
@@ -268,7 +277,8 @@ umma_dec_kernel(const UmmaDecParams p) {
                         int lo = 0, hi = p.n_src;
                         while (lo < hi) {
                             const int mid = (lo + hi) >> 1;
-                            if (__ldg(c + mid) > t) hi = mid; else lo = mid + 1;
+                            const int cv = cum_in_smem ? scum[mid] : __ldg(c + mid);
+                            if (cv > t) hi = mid; else lo = mid + 1;
                         }
                         sidx = lo < p.n_src ? lo : -1;
                     }
