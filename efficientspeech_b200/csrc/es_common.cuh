@@ -42,6 +42,22 @@ extern std::atomic<uint64_t> g_launches;
         ES_CUDA(cudaGetLastError());                                          \
     } while (0)
 
+// ---- launch with programmatic stream serialization (PDL); the kernel must call griddepcontrol.wait --
+template <typename Param>
+inline cudaError_t launch_pdl(void (*kernel)(Param), int grid, int block, size_t smem, cudaStream_t s, const Param& p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 // ---- optional per-launch event timing (es_profile_*) --------------------------------------
 void prof_begin_range(int kind, cudaStream_t s);
 void prof_end_range(cudaStream_t s);

@@ -71,6 +71,14 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor in the stream is still draining; everything before pdl_wait() (TMEM allocation,
+// barrier init, parameter / weight staging) overlaps the predecessor's tail, everything after sees
+// the predecessor's global writes.  pdl_launch_dependents() lets the successor start its own prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- proxies / fences -------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {      // generic st.shared -> visible to UMMA/TMA
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -27,7 +27,6 @@ using namespace umma;
 
 constexpr int AT_M = 128;                        // query rows per item (TMEM lanes)
 constexpr uint32_t PANEL = AT_M * 16;            // 2048: one K panel (8 elements) of 128 rows
-constexpr uint32_t QK_PLANE_MAX = 8 * PANEL;     // C = 64 -> 8 panels
 constexpr uint32_t P_PLANE = 16 * PANEL;         // 128 keys -> 16 panels = 32768
 // region R0 holds {Q hi, Q lo, K hi, K lo} (<= 64 KB) and is later overwritten by {P hi, P lo} (64 KB)
 constexpr uint32_t OFF_R0 = 0;
@@ -66,6 +65,8 @@ umma_attention_kernel(const AttnParams p) {
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();      // the next kernel may start its prologue
+    pdl_wait();                   // the QKV projection's output is complete and visible from here on
     const bool elected_warp = (warp == 0);
     bool failed = false;
     uint32_t phase = 0;
@@ -266,7 +267,7 @@ int launch_umma_attention(const float* qkv, float* out, int B, int n, int C, int
     p.err = err_flag;
     const int items = B * H;
     const int grid = items < 2 * n_sm ? items : 2 * n_sm;
-    umma_attention_kernel<<<grid, 128, ATT_SMEM, s>>>(p);
+    ES_CUDA(launch_pdl(umma_attention_kernel, grid, 128, ATT_SMEM, s, p));
     ES_LAUNCH_OK();
     return 0;
 }

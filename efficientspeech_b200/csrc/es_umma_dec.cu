@@ -146,6 +146,10 @@ umma_dec_kernel(const UmmaDecParams p) {
         for (int k = 0; k < NSTAGE; ++k) mbar_init(bar_xfree + 8 * k, 4);
         mbar_init(bar_aready, 4);
         fence_mbar_init();
+        // the weights do not depend on the predecessor kernel: their bulk load starts before pdl_wait()
+        mbar_arrive_expect_tx(bar_w, 2 * w_plane);
+        bulk_g2s(smem_u32(smem + OFF_W), p.w_h16, w_plane, bar_w);
+        bulk_g2s(smem_u32(smem + OFF_W) + w_plane, reinterpret_cast<const uint8_t*>(p.w_h16) + w_plane, w_plane, bar_w);
     }
     for (int i = tid; i < 128; i += NTHR) {
         par[i] = (i < N) ? __ldg(p.bias + i) * (p.act_tanh ? kTanhScale : 1.f) : 0.f;   // pre-scaled for tanh
@@ -163,6 +167,8 @@ umma_dec_kernel(const UmmaDecParams p) {
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     bool failed = false;
+    pdl_launch_dependents();      // the next kernel may start its prologue
+    pdl_wait();                   // the previous kernel's output is complete and visible from here on
 
     if (warp == 12) {
         // =========================================================================== issue warp
@@ -186,11 +192,6 @@ umma_dec_kernel(const UmmaDecParams p) {
         const uint64_t db_step = (uint64_t)((2u * lbo_b) >> 4);
         const bool elected = elect_one();                    // one lane issues on behalf of the CTA; the
                                                              // control flow stays warp-uniform
-        if (elected) {
-            mbar_arrive_expect_tx(bar_w, 2 * w_plane);
-            bulk_g2s(smem_u32(smem + OFF_W), p.w_h16, w_plane, bar_w);
-            bulk_g2s(smem_u32(smem + OFF_W) + w_plane, reinterpret_cast<const uint8_t*>(p.w_h16) + w_plane, w_plane, bar_w);
-        }
         if (MODE != MODE_GATHER) {
             for (int k = 0; k < NSTAGE; ++k) {
                 const int tile = blockIdx.x + k * gridDim.x;
@@ -469,7 +470,7 @@ int launch_mode(const UmmaDecParams& p, int grid, cudaStream_t s) {
         ES_CUDA(cudaFuncSetAttribute(umma_dec_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    umma_dec_kernel<MODE><<<grid, NTHR, SMEM_BYTES, s>>>(p);
+    ES_CUDA(launch_pdl(umma_dec_kernel<MODE>, grid, NTHR, SMEM_BYTES, s, p));
     ES_LAUNCH_OK();
     return 0;
 }

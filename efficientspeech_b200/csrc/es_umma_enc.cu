@@ -99,6 +99,11 @@ umma_rowgemm_kernel(const UrgParams up) {
         mbar_init(bar_tfree, 4);
         mbar_init(bar_tfree + 8, 4);
         fence_mbar_init();
+        // the weights do not depend on the predecessor kernel: their bulk load starts before pdl_wait()
+        mbar_arrive_expect_tx(bar_w, (uint32_t)taps * 2u * w_plane);
+        for (int k = 0; k < taps * 2; ++k)
+            bulk_g2s(smem_u32(smem + OFF_W) + (uint32_t)k * w_plane,
+                     reinterpret_cast<const uint8_t*>(up.w_h16) + (size_t)k * w_plane, w_plane, bar_w);
     }
     for (int i = tid; i < NPAR; i += NTHR) {
         s_bias[i] = (p.bias && i < N) ? __ldg(p.bias + i) : 0.f;
@@ -115,6 +120,8 @@ umma_rowgemm_kernel(const UrgParams up) {
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     bool failed = false;
+    pdl_launch_dependents();      // the next kernel may start its prologue
+    pdl_wait();                   // the previous kernel's output is complete and visible from here on
 
     if (warp == 12) {
         // =========================================================================== issue warp
@@ -122,14 +129,6 @@ umma_rowgemm_kernel(const UrgParams up) {
         const uint32_t idesc_full = make_idesc_f16(TM, N >= 128 ? 128 : N);
         const uint32_t idesc_last = make_idesc_f16(TM, (N & 127) ? (N & 127) : 128);
         const uint32_t lbo_b = (uint32_t)N * 16u;
-        if (elected) {
-            const uint32_t wbytes = (uint32_t)taps * 2u * w_plane;
-            mbar_arrive_expect_tx(bar_w, wbytes);
-            // bulk copies are limited in size only by the mbarrier tx count; split per plane
-            for (int k = 0; k < taps * 2; ++k)
-                bulk_g2s(smem_u32(smem + OFF_W) + (uint32_t)k * w_plane,
-                         reinterpret_cast<const uint8_t*>(up.w_h16) + (size_t)k * w_plane, w_plane, bar_w);
-        }
         if (!mbar_wait(bar_w, 0)) failed = true;
         __syncwarp();
         int i = 0;
@@ -391,10 +390,10 @@ int launch_umma_rowgemm(const RowGemmParams& p, const void* w_h16, cudaStream_t 
     const int n_tiles = p.B * ((p.n_out + TM - 1) / TM);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
     switch (nj) {
-        case 4: umma_rowgemm_kernel<4><<<grid, NTHR, SMEM_BYTES, s>>>(up); break;
-        case 8: umma_rowgemm_kernel<8><<<grid, NTHR, SMEM_BYTES, s>>>(up); break;
-        case 12: umma_rowgemm_kernel<12><<<grid, NTHR, SMEM_BYTES, s>>>(up); break;
-        default: umma_rowgemm_kernel<16><<<grid, NTHR, SMEM_BYTES, s>>>(up); break;
+        case 4: ES_CUDA(launch_pdl(umma_rowgemm_kernel<4>, grid, NTHR, SMEM_BYTES, s, up)); break;
+        case 8: ES_CUDA(launch_pdl(umma_rowgemm_kernel<8>, grid, NTHR, SMEM_BYTES, s, up)); break;
+        case 12: ES_CUDA(launch_pdl(umma_rowgemm_kernel<12>, grid, NTHR, SMEM_BYTES, s, up)); break;
+        default: ES_CUDA(launch_pdl(umma_rowgemm_kernel<16>, grid, NTHR, SMEM_BYTES, s, up)); break;
     }
     ES_LAUNCH_OK();
     return 0;
