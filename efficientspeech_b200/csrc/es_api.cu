@@ -191,21 +191,18 @@ int predictors(const es_model* m, int B, int N, const float* fused, float* const
         st1[i] = predictor_stage1(m, *w[i], B, N, fused, y1[i]);
         st2[i] = predictor_stage2(m, *w[i], B, N, y1[i], preds[i], i == 2, i == 2 ? dur_feat : nullptr);
     }
-    // tensor-core path: six small launches (one per predictor and stage); the three predictors share
-    // their geometry, so the envelope check of the first decides for all
+    // tensor-core path: the three predictors share their geometry, so each stage is ONE batched launch
+    // (consecutive CTAs serve different predictors, each keeps its own weights resident)
     if (m->use_tensor_core && w[0]->conv1_w_h16 && w[0]->conv2_w_h16) {
+        const void* w1[3] = {w[0]->conv1_w_h16, w[1]->conv1_w_h16, w[2]->conv1_w_h16};
+        const void* w2[3] = {w[0]->conv2_w_h16, w[1]->conv2_w_h16, w[2]->conv2_w_h16};
         int rc;
-        { ProfRange r(ES_K_PREDICTOR, s); rc = launch_umma_rowgemm(st1[0], w[0]->conv1_w_h16, s); }
+        { ProfRange r(ES_K_PREDICTOR, s); rc = launch_umma_rowgemm_batch(st1, w1, 3, s); }
         if (rc > 0) return 1;
         if (rc == 0) {
-            for (int i = 1; i < 3; ++i) {
-                ProfRange r(ES_K_PREDICTOR, s);
-                if (gemm(m, st1[i], w[i]->conv1_w_h16, s)) return 1;
-            }
-            for (int i = 0; i < 3; ++i) {
-                ProfRange r(ES_K_PREDICTOR, s);
-                if (gemm(m, st2[i], w[i]->conv2_w_h16, s)) return 1;
-            }
+            { ProfRange r(ES_K_PREDICTOR, s); rc = launch_umma_rowgemm_batch(st2, w2, 3, s); }
+            if (rc > 0) return 1;
+            if (rc < 0) for (int i = 0; i < 3; ++i) if (launch_rowgemm(st2[i], s)) return 1;
             return 0;
         }
     }

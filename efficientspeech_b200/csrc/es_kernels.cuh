@@ -33,6 +33,7 @@ int* umma_err_flag();
 
 // tcgen05 row GEMM for the phoneme-side layers (es_umma_enc.cu); -1: outside its envelope
 int launch_umma_rowgemm(const RowGemmParams& p, const void* w_h16, cudaStream_t s);
+int launch_umma_rowgemm_batch(const RowGemmParams* ps, const void* const* w_h16, int count, cudaStream_t s);
 // tcgen05 attention (es_umma_attn.cu); -1: outside its envelope (n > 128 or C not in {32, 64})
 int launch_umma_attention(const float* qkv, float* out, int B, int n, int C, int H, float scale, cudaStream_t s);
 

@@ -291,10 +291,21 @@ umma_dec_kernel(const UmmaDecParams p) {
             // into registers BEFORE waiting for the A operand to be released, so that after the previous
             // GEMM completes only the 32 shared-memory stores remain on the critical path.
             uint2 ahi[16], alo[16];                          // this lane's share: 16 rows x 4 channels, split fp16
+            if (MODE == MODE_GATHER) {
+                // all 16 source rows of this warp are requested at once (one L2 round trip, not two)
+                float4 rowv[16];
 #pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int r0 = pw * 16 + pass * 8;
-                if (MODE != MODE_GATHER) {
+                for (int r = 0; r < 16; ++r) {
+                    const int sidx = srcs[pw * 16 + r];
+                    rowv[r] = sidx >= 0 ? __ldg(reinterpret_cast<const float4*>(p.X + ((size_t)b * p.n_src + sidx) * CK) + lane)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int r = 0; r < 16; ++r) split4(rowv[r], ahi[r], alo[r]);
+            } else {
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int r0 = pw * 16 + pass * 8;
                     // per-lane depthwise taps for channels 4*lane..4*lane+3 (3 KB in shared memory; kept out of
                     // the persistent register set so the staged A rows fit without spilling)
                     float4 wdw[DWK], bdw;
@@ -323,16 +334,6 @@ umma_dec_kernel(const UmmaDecParams p) {
                         }
                         split4(o, ahi[pass * 8 + r], alo[pass * 8 + r]);
                     }
-                } else {
-                    float4 rowv[8];
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const int sidx = srcs[r0 + r];
-                        rowv[r] = sidx >= 0 ? __ldg(reinterpret_cast<const float4*>(p.X + ((size_t)b * p.n_src + sidx) * CK) + lane)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) split4(rowv[r], ahi[pass * 8 + r], alo[pass * 8 + r]);
                 }
             }
             // this warp has read everything it needs from ring slot `slot` (and from srcs)

@@ -56,8 +56,9 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 __device__ __noinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 struct UrgParams {
-    RowGemmParams g;
-    const void* w_h16;
+    RowGemmParams g[3];          // up to 3 independent problems of identical geometry (the three predictors)
+    const void* w_h16[3];
+    int nprob;
     int* err;
 };
 
@@ -66,7 +67,11 @@ struct UrgParams {
 template <int NJ>
 __global__ void __launch_bounds__(NTHR, 1)
 umma_rowgemm_kernel(const UrgParams up) {
-    const RowGemmParams& p = up.g;
+    // CTA -> problem: consecutive CTAs serve different problems; each keeps its own weights resident
+    const int prob = blockIdx.x % up.nprob;
+    const int cta = blockIdx.x / up.nprob, ncta = gridDim.x / up.nprob;
+    const RowGemmParams& p = up.g[prob];
+    const void* w_h16 = up.w_h16[prob];
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float* par = reinterpret_cast<float*>(smem + OFF_PAR);
@@ -103,7 +108,7 @@ umma_rowgemm_kernel(const UrgParams up) {
         mbar_arrive_expect_tx(bar_w, (uint32_t)taps * 2u * w_plane);
         for (int k = 0; k < taps * 2; ++k)
             bulk_g2s(smem_u32(smem + OFF_W) + (uint32_t)k * w_plane,
-                     reinterpret_cast<const uint8_t*>(up.w_h16) + (size_t)k * w_plane, w_plane, bar_w);
+                     reinterpret_cast<const uint8_t*>(w_h16) + (size_t)k * w_plane, w_plane, bar_w);
     }
     for (int i = tid; i < NPAR; i += NTHR) {
         s_bias[i] = (p.bias && i < N) ? __ldg(p.bias + i) : 0.f;
@@ -132,7 +137,7 @@ umma_rowgemm_kernel(const UrgParams up) {
         if (!mbar_wait(bar_w, 0)) failed = true;
         __syncwarp();
         int i = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+        for (int tile = cta; tile < n_tiles; tile += ncta, ++i) {
             const int g = i & 1, u = i >> 1;
             if (!mbar_wait(bar_aready + 8 * g, u & 1)) failed = true;
             if (u > 0 && !mbar_wait(bar_tfree + 8 * g, (u - 1) & 1)) failed = true;
@@ -170,7 +175,7 @@ umma_rowgemm_kernel(const UrgParams up) {
         const int ptid = tid - 256;
         const int K4 = K >> 2;
         int i = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+        for (int tile = cta; tile < n_tiles; tile += ncta, ++i) {
             const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
             const int g = i & 1, u = i >> 1;
             uint8_t* a_hi = smem + OFF_A + (uint32_t)g * A_STAGE;
@@ -222,7 +227,7 @@ umma_rowgemm_kernel(const UrgParams up) {
         const bool full_epi = (N <= 128);
 
         int i = g;
-        for (int tile = blockIdx.x + g * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, i += 2) {
+        for (int tile = cta + g * ncta; tile < n_tiles; tile += 2 * ncta, i += 2) {
             const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
             const int rows_valid = min(TM, p.n_out - t0);
             const int u = i >> 1;
@@ -354,14 +359,25 @@ umma_rowgemm_kernel(const UrgParams up) {
 }  // namespace
 
 // Returns -1 when the layer is outside the tensor-core kernel's envelope (caller uses the SIMT path).
-int launch_umma_rowgemm(const RowGemmParams& p, const void* w_h16, cudaStream_t s) {
-    if (!w_h16 || p.mode != ROW_PLAIN || p.res2) return -1;
+// `count` (1..3) problems of identical geometry share ONE launch.
+int launch_umma_rowgemm_batch(const RowGemmParams* ps, const void* const* w_h16, int count, cudaStream_t s) {
+    if (count < 1 || count > 3) return -1;
+    const RowGemmParams& p = ps[0];
+    for (int i = 0; i < count; ++i) {
+        const RowGemmParams& o = ps[i];
+        if (!w_h16[i] || o.mode != ROW_PLAIN || o.res2) return -1;
+        if (o.B != p.B || o.n_in != p.n_in || o.n_out != p.n_out || o.K != p.K || o.Nout != p.Nout || o.taps != p.taps ||
+            o.stride != p.stride || o.pad != p.pad) return -1;
+        if (o.Nout > 128 && (o.ln_g || o.dot_out || o.res1 || o.act2 != ACT_NONE)) return -1;
+        if (o.lda % 4 || (o.Y && o.ldy % 2) || (o.res1 && o.ldr1 % 2)) return -1;
+        if (o.act2 != ACT_NONE && o.act2 != ACT_RELU) return -1;
+        if (o.act1 == ACT_TANH) return -1;
+    }
     if (p.K % 16 || p.K > KMAX || p.K < 16) return -1;
     if (!((p.stride == 1 && (p.taps == 1 || p.taps == 3)) || (p.stride == 2 && p.taps == 1))) return -1;
     if (p.Nout % 8 || p.Nout < 16 || p.Nout > NPAR) return -1;
-    if (p.Nout > 128 && (p.Nout % 128 || p.ln_g || p.dot_out || p.res1 || p.act2 != ACT_NONE)) return -1;
+    if (p.Nout > 128 && p.Nout % 128) return -1;
     if ((size_t)p.taps * p.Nout * p.K * 4 > W_MAX) return -1;
-    if (p.lda % 4 || (p.Y && p.ldy % 2) || (p.res1 && p.ldr1 % 2)) return -1;
     if (p.stride == 1 && p.n_in != p.n_out) return -1;       // 'same' convs only (pad = taps / 2)
     int* err_flag = umma_err_flag();
     ES_CHECK(err_flag, "cannot allocate the device error flag");
@@ -371,8 +387,6 @@ int launch_umma_rowgemm(const RowGemmParams& p, const void* w_h16, cudaStream_t 
         ES_CUDA(cudaGetDevice(&dev));
         ES_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    if (p.act2 != ACT_NONE && p.act2 != ACT_RELU) return -1;
-    if (p.act1 == ACT_TANH) return -1;
     const int nj = p.Nout > 128 ? 16 : p.Nout / 8;
     if (nj != 4 && nj != 8 && nj != 12 && nj != 16) return -1;
     static bool attr_set = false;
@@ -384,11 +398,16 @@ int launch_umma_rowgemm(const RowGemmParams& p, const void* w_h16, cudaStream_t 
         attr_set = true;
     }
     UrgParams up;
-    up.g = p;
-    up.w_h16 = w_h16;
+    for (int i = 0; i < 3; ++i) {
+        up.g[i] = ps[i < count ? i : 0];
+        up.w_h16[i] = w_h16[i < count ? i : 0];
+    }
+    up.nprob = count;
     up.err = err_flag;
     const int n_tiles = p.B * ((p.n_out + TM - 1) / TM);
-    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    int per_prob = n_sm / count;
+    if (per_prob > n_tiles) per_prob = n_tiles;
+    const int grid = per_prob * count;
     switch (nj) {
         case 4: ES_CUDA(launch_pdl(umma_rowgemm_kernel<4>, grid, NTHR, SMEM_BYTES, s, up)); break;
         case 8: ES_CUDA(launch_pdl(umma_rowgemm_kernel<8>, grid, NTHR, SMEM_BYTES, s, up)); break;
@@ -397,6 +416,10 @@ int launch_umma_rowgemm(const RowGemmParams& p, const void* w_h16, cudaStream_t 
     }
     ES_LAUNCH_OK();
     return 0;
+}
+
+int launch_umma_rowgemm(const RowGemmParams& p, const void* w_h16, cudaStream_t s) {
+    return launch_umma_rowgemm_batch(&p, &w_h16, 1, s);
 }
 
 }  // namespace es
