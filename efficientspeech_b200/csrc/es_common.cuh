@@ -70,13 +70,16 @@ struct ProfRange {
 // ---- activations -----------------------------------------------------------------------
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_TANH = 3 };
 
+// Out-of-line transcendental activations: epilogue loops stay fully unrolled (values in registers)
+// without replicating the erf / tanh expansions per element (instruction-cache footprint).
+static __device__ __noinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }  // blocks.py:19
+static __device__ __noinline__ float tanh_f(float v) { return tanhf(v); }
+
 __device__ __forceinline__ float apply_act(float v, int act) {
-    switch (act) {
-        case ACT_RELU: return fmaxf(v, 0.f);
-        case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));  // exact erf GELU (blocks.py:19)
-        case ACT_TANH: return tanhf(v);
-        default: return v;
-    }
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_GELU) return gelu_erf_f(v);
+    if (act == ACT_TANH) return tanh_f(v);
+    return v;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

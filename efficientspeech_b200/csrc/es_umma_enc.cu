@@ -51,10 +51,6 @@ constexpr uint32_t OFF_BAR = OFF_PAR + PAR_FLOATS * 4;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
-// one out-of-line copy of erff: the epilogue loops stay fully unrolled (values in registers) without
-// replicating the erf expansion per element
-__device__ __noinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
-
 struct UrgParams {
     RowGemmParams g[3];          // up to 3 independent problems of identical geometry (the three predictors)
     const void* w_h16[3];
@@ -274,7 +270,7 @@ umma_rowgemm_kernel(const UrgParams up) {
                     for (int k = 0; k < 4 * NJ; ++k) v[k] = fmaxf(v[k], 0.f);
                 } else if (p.act1 == ACT_GELU) {               // exact erf GELU (blocks.py:19)
 #pragma unroll
-                    for (int k = 0; k < 4 * NJ; ++k) v[k] = gelu_exact(v[k]);
+                    for (int k = 0; k < 4 * NJ; ++k) v[k] = gelu_erf_f(v[k]);
                 }
                 if (full_epi) {
                     if (p.dot_out) {
