@@ -392,6 +392,13 @@ int es_decoder_forward(es_model_t* m, void* stream, int B, int T, const float* f
                               nullptr, db.buf[0], s)) return 1; }
         return decoder_layers(m, B, T, db, 0, nullptr, mel, s);
     }
+    if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx2 == 256 && umma_dec256_supported(m->dx4, 5, 256, 2)) {
+        { ProfRange r(ES_K_DEC_PROJ, s);
+          if (launch_umma_dec256(2, B, T, m->dx4, m->dx2, 0, features, nullptr, nullptr, nullptr, nullptr, m->w.dproj_w_h16,
+                                 m->w.dproj_b, 1, m->w.dproj_ln_g, m->w.dproj_ln_b, nullptr, nullptr, nullptr,
+                                 nullptr, db.buf[0], s)) return 1; }
+        return decoder_layers(m, B, T, db, 0, nullptr, mel, s);
+    }
     RowGemmParams p = base_params(B, T, T, m->dx4, m->dx2, features, m->dx4, m->w.dproj_w, db.buf[0], m->dx2);
     p.bias = m->w.dproj_b; p.act1 = ACT_TANH; p.ln_g = m->w.dproj_ln_g; p.ln_b = m->w.dproj_ln_b;
     { ProfRange r(ES_K_DEC_PROJ, s); if (launch_rowgemm(p, s)) return 1; }
@@ -415,6 +422,13 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
           if (launch_umma_dec(1, B, T, m->dx2, N, fused4, dur_cum, mel_len, nullptr, nullptr, m->w.dproj_w_h16,
                               m->w.dproj_b, 1, m->w.dproj_ln_g, m->w.dproj_ln_b, nullptr, nullptr, nullptr,
                               nullptr, db.buf[0], s)) return 1; }
+        return decoder_layers(m, B, T, db, 0, zero_padded_frames ? mel_len : nullptr, mel, s);
+    }
+    if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx2 == 256 && umma_dec256_supported(m->dx4, 5, 256, 1)) {
+        { ProfRange r(ES_K_DEC_PROJ, s);
+          if (launch_umma_dec256(1, B, T, m->dx4, m->dx2, N, fused4, dur_cum, mel_len, nullptr, nullptr, m->w.dproj_w_h16,
+                                 m->w.dproj_b, 1, m->w.dproj_ln_g, m->w.dproj_ln_b, nullptr, nullptr, nullptr,
+                                 nullptr, db.buf[0], s)) return 1; }
         return decoder_layers(m, B, T, db, 0, zero_padded_frames ? mel_len : nullptr, mel, s);
     }
     RowGemmParams p = base_params(B, N, T, m->dx4, m->dx2, fused4, m->dx4, m->w.dproj_w, db.buf[0], m->dx2);
@@ -449,6 +463,15 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
                 in_idx = out_idx;
                 continue;
             }
+            if (m->use_tensor_core && w.pw_w_h16 && C == 256 && umma_dec256_supported(C, m->cfg.decoder_kernel_size, C, 0)) {
+                ProfRange r(ES_K_DEC_LAYER, s);
+                if (launch_umma_dec256(0, B, T, C, C, 0, db.buf[in_idx], nullptr, nullptr, w.dw_w, w.dw_b, w.pw_w_h16,
+                                       w.pw_b, 1, w.ln_g, w.ln_b, last ? db.buf[s_idx] : nullptr,
+                                       last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
+                                       nullptr, db.buf[out_idx], s)) return 1;
+                in_idx = out_idx;
+                continue;
+            }
             RowGemmParams p = base_params(B, T, T, C, C, db.buf[in_idx], C, w.pw_w, db.buf[out_idx], C);
             p.mode = ROW_DWCONV; p.dw_w = w.dw_w; p.dw_b = w.dw_b; p.dw_k = m->cfg.decoder_kernel_size;
             p.bias = w.pw_b; p.act1 = ACT_TANH; p.ln_g = w.ln_g; p.ln_b = w.ln_b;
@@ -467,6 +490,13 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
         return launch_umma_dec(2, B, T, m->cfg.n_mel, 0, db.buf[s_idx], nullptr, nullptr, nullptr, nullptr,
                                m->w.mel_w_h16, m->w.mel_b, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
                                zero_from, mel, s);
+    }
+    if (m->use_tensor_core && m->w.mel_w_h16 && C == 256 && m->cfg.n_mel == 80 &&
+        umma_dec256_supported(C, m->cfg.decoder_kernel_size, 80, 2)) {
+        ProfRange r(ES_K_MEL, s);
+        return launch_umma_dec256(2, B, T, C, m->cfg.n_mel, 0, db.buf[s_idx], nullptr, nullptr, nullptr, nullptr,
+                                  m->w.mel_w_h16, m->w.mel_b, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                  zero_from, mel, s);
     }
     RowGemmParams p = base_params(B, T, T, C, m->cfg.n_mel, db.buf[s_idx], C, m->w.mel_w, mel, m->cfg.n_mel);
     p.bias = m->w.mel_b; p.zero_from = zero_from;

@@ -1,0 +1,538 @@
+// Decoder-side tensor-core kernel for the WIDE decoders (small / base: dx2 = 256 channels).
+//
+// The split-fp16 image of a 256x256 pointwise weight is 256 KB -- it cannot stay resident next to
+// the activations as in es_umma_dec.cu.  This kernel therefore streams EVERYTHING along K:
+// a 128-frame tile is processed in chunks of 32 input channels, and three rings run in lock step
+//
+//   x ring   (4 stages)  [132 rows][32 ch] fp32, filled by the producers with 16-byte cp.async
+//                        (zero-fill outside the utterance / for padded frames; in GATHER mode the
+//                        rows come from the length-regulator source indices), 3 chunks in flight
+//   A ring   (3 stages)  the producers' depthwise conv (k=5, sliding window in registers) of the
+//                        chunk, split fp16 hi/lo, UMMA canonical K-major no-swizzle panels
+//   W ring   (3 stages)  the matching [N][32] slice of the split weights (pre-chunked at pack
+//                        time), one bulk async copy (TMA 1-D) per chunk, from L2
+//
+// and the issue warp launches 6 x tcgen05.mma (M128 x N x K16: hi*hi + hi*lo + lo*hi for two K
+// steps) per chunk into one of two 256-column TMEM accumulators; one tcgen05.commit per chunk
+// releases the A/W stage, the last chunk's commit hands the accumulator to the epilogue.
+//
+// Epilogue (8 warps, 16 rows each, mma-fragment layout, 4 threads per row): a 256-channel row is
+// 2 x 64 values per thread -- too many to hold -- so the row statistics are taken in passes over
+// the accumulator, which is used as scratch: tanh(acc + bias) is written back with tcgen05.st,
+// normalised (+ skip, second statistics, written back again on block-end layers) and finally
+// stored with 8-byte accesses (8 rows x 32 contiguous bytes per warp instruction).
+//
+// Same modes as es_umma_dec.cu: DWCONV (decoder layer), GATHER (length regulator + projection,
+// K = 4d up to 512), PLAIN (mel head, N = 80).
+#include <stdlib.h>
+
+#include "es_common.cuh"
+#include "es_kernels.cuh"
+#include "es_umma.cuh"
+
+namespace es {
+namespace {
+
+using namespace umma;
+
+constexpr int TM2 = 128;                  // frames per tile (UMMA M)
+constexpr int KC = 32;                    // channels per K chunk
+constexpr int DWK = 5;
+constexpr int NTHR = 416;                 // 13 warps: 0..7 epilogue, 8..11 producer, 12 issue
+constexpr int NPROD = 128;
+constexpr int NXS = 4;                    // x ring depth
+constexpr int NAS = 3;                    // A / W ring depth
+constexpr int NMAX = 256;
+constexpr uint32_t X_STAGE = (TM2 + DWK - 1) * KC * 4;      // 16896
+constexpr uint32_t A_PANEL = TM2 * 16;                      // 2048: 8 channels of all 128 rows
+constexpr uint32_t A_PLANE = (KC / 8) * A_PANEL;            // 8192
+constexpr uint32_t A_STAGE = 2 * A_PLANE;                   // 16384 (hi, lo)
+constexpr uint32_t W_STAGE = 2 * (KC / 8) * NMAX * 16;      // 32768 (hi, lo)
+
+constexpr uint32_t OFF_X = 0;
+constexpr uint32_t OFF_A = OFF_X + NXS * X_STAGE;           // 67584
+constexpr uint32_t OFF_W = OFF_A + NAS * A_STAGE;           // 116736
+constexpr uint32_t OFF_PAR = OFF_W + NAS * W_STAGE;         // 215040: bias, ln g/b, ln2 g/b (5 x 256 floats)
+constexpr uint32_t OFF_DW = OFF_PAR + 5 * NMAX * 4;         // 220160: depthwise taps + bias (6 x 256 floats)
+constexpr uint32_t OFF_SRC = OFF_DW + 6 * NMAX * 4;         // 226304: gather sources, 2 x 128 ints
+constexpr uint32_t OFF_CUM = OFF_SRC + 2 * TM2 * 4;         // 227328: duration prefix sums of the utterance (<= 1024)
+constexpr uint32_t OFF_BAR = OFF_CUM + 1024 * 4;            // 231424
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;              // 231552
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+enum { MODE_DWCONV = 0, MODE_GATHER = 1, MODE_PLAIN = 2 };
+
+struct Dec256Params {
+    int B, T, K, N;              // K input channels (multiple of 32, <= 512), N output channels (256 | 80)
+    int n_src;
+    const float* X;              // DWCONV/PLAIN: [B,T,K]; GATHER: fused4 [B,n_src,K]
+    const int* cum;
+    const int* valid_len;
+    const float* dw_w;           // [5][K]
+    const float* dw_b;           // [K]
+    const void* w_chunks;        // [K/32][2 (hi,lo)][4][N][8] halves
+    const float* bias;
+    int act_tanh;
+    const float* ln_g; const float* ln_b;
+    const float* res2; const float* ln2_g; const float* ln2_b;
+    const int* zero_from;
+    float* Y;
+    int* err;
+};
+
+constexpr float kTanhScale2 = 2.8853900817779268f;
+__device__ __forceinline__ float tanh_scaled2(float arg) {     // see es_umma_dec.cu
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    return fmaf(-2.f, r, 1.f);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHR, 1)
+umma_dec256_kernel(const Dec256Params p) {
+    constexpr int HALO = (MODE == MODE_DWCONV) ? DWK / 2 : 0;
+    constexpr int XROWS = TM2 + 2 * HALO;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* par = reinterpret_cast<float*>(smem + OFF_PAR);
+    float* dws = reinterpret_cast<float*>(smem + OFF_DW);
+    int* srcs = reinterpret_cast<int*>(smem + OFF_SRC);
+    int* scum = reinterpret_cast<int*>(smem + OFF_CUM);
+    const uint32_t bar0 = smem_u32(smem + OFF_BAR);
+    const uint32_t bar_wfull = bar0;            // [3] W chunk landed
+    const uint32_t bar_cfree = bar0 + 24;       // [3] chunk stage (A and W) consumed by its MMAs
+    const uint32_t bar_aready = bar0 + 48;      // [3] A chunk written by the 4 producer warps
+    const uint32_t bar_accfull = bar0 + 72;     // [2]
+    const uint32_t bar_accfree = bar0 + 88;     // [2] accumulator drained by the 8 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 112);
+
+    const int N = p.N, K = p.K;
+    const int nchunks = K / KC;
+    const int tiles_per_utt = (p.T + TM2 - 1) / TM2;
+    const int n_tiles = p.B * tiles_per_utt;
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_chunks = my_tiles * nchunks;
+    const uint32_t w_plane = (uint32_t)(KC / 8) * N * 16u;     // bytes of one fp16 plane of one chunk
+    const uint32_t w_chunk_bytes = 2 * w_plane;
+
+    // ---- one-time setup ---------------------------------------------------------------------
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);      // two 256-column fp32 accumulators
+    if (tid == 0) {
+        for (int k = 0; k < NAS; ++k) {
+            mbar_init(bar_wfull + 8 * k, 1);
+            mbar_init(bar_cfree + 8 * k, 1);
+            mbar_init(bar_aready + 8 * k, 4);
+        }
+        for (int k = 0; k < 2; ++k) {
+            mbar_init(bar_accfull + 8 * k, 1);
+            mbar_init(bar_accfree + 8 * k, 8);
+        }
+        fence_mbar_init();
+    }
+    for (int i = tid; i < NMAX; i += NTHR) {
+        par[i] = (i < N) ? __ldg(p.bias + i) * (p.act_tanh ? kTanhScale2 : 1.f) : 0.f;
+        par[NMAX + i] = (p.ln_g && i < N) ? __ldg(p.ln_g + i) : 0.f;
+        par[2 * NMAX + i] = (p.ln_g && i < N) ? __ldg(p.ln_b + i) : 0.f;
+        par[3 * NMAX + i] = (p.ln2_g && i < N) ? __ldg(p.ln2_g + i) : 0.f;
+        par[4 * NMAX + i] = (p.ln2_g && i < N) ? __ldg(p.ln2_b + i) : 0.f;
+    }
+    if (MODE == MODE_DWCONV) {
+        for (int i = tid; i < (DWK + 1) * NMAX; i += NTHR) {
+            const int t = i / NMAX, c = i - t * NMAX;
+            dws[i] = c < K ? (t < DWK ? __ldg(p.dw_w + t * K + c) : __ldg(p.dw_b + c)) : 0.f;
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    bool failed = false;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    if (warp == 12) {
+        // =========================================================================== issue warp
+        const bool elected = elect_one();
+        const uint32_t idesc = make_idesc_f16(TM2, N);
+        const uint32_t lbo_b = (uint32_t)N * 16u;
+        auto load_w = [&](int g) {               // chunk g of this CTA's stream -> stage g % NAS
+            const int st = g % NAS, c = g % nchunks;
+            mbar_arrive_expect_tx(bar_wfull + 8 * st, w_chunk_bytes);
+            bulk_g2s(smem_u32(smem + OFF_W) + (uint32_t)st * W_STAGE,
+                     reinterpret_cast<const uint8_t*>(p.w_chunks) + (size_t)c * w_chunk_bytes, w_chunk_bytes,
+                     bar_wfull + 8 * st);
+        };
+        if (elected) {
+            if (total_chunks > 0) load_w(0);
+            if (total_chunks > 1) load_w(1);
+        }
+        __syncwarp();
+        for (int g = 0; g < total_chunks; ++g) {
+            const int st = g % NAS, use = g / NAS;
+            const int i = g / nchunks, c = g - i * nchunks;
+            const int acc = i & 1;
+            // prefetch the weights two chunks ahead; their stage was last used by chunk g-1
+            if (g + 2 < total_chunks) {
+                if (g >= 1 && !mbar_wait(bar_cfree + 8 * ((g + 2) % NAS), ((g - 1) / NAS) & 1)) failed = true;
+                if (elected) load_w(g + 2);
+            }
+            if (!mbar_wait(bar_wfull + 8 * st, use & 1)) failed = true;
+            if (!mbar_wait(bar_aready + 8 * st, use & 1)) failed = true;
+            if (c == 0 && i >= 2 && !mbar_wait(bar_accfree + 8 * acc, ((i >> 1) - 1) & 1)) failed = true;
+            tc_fence_after_sync();
+            const uint32_t a_base = smem_u32(smem + OFF_A) + (uint32_t)st * A_STAGE;
+            const uint32_t w_base = smem_u32(smem + OFF_W) + (uint32_t)st * W_STAGE;
+            const uint32_t d = tmem + (uint32_t)(acc * NMAX);
+#pragma unroll
+            for (int ks = 0; ks < KC / 16; ++ks) {
+                const uint64_t dah = make_smem_desc(a_base + (uint32_t)(2 * ks) * A_PANEL, A_PANEL, 128u);
+                const uint64_t dal = make_smem_desc(a_base + A_PLANE + (uint32_t)(2 * ks) * A_PANEL, A_PANEL, 128u);
+                const uint64_t dbh = make_smem_desc(w_base + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128u);
+                const uint64_t dbl = make_smem_desc(w_base + w_plane + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128u);
+                if (elected) {
+                    mma_f16_ss(d, dah, dbh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                    mma_f16_ss(d, dah, dbl, idesc, 1u);
+                    mma_f16_ss(d, dal, dbh, idesc, 1u);
+                }
+            }
+            if (elected) {
+                mma_commit(bar_cfree + 8 * st);
+                if (c == nchunks - 1) mma_commit(bar_accfull + 8 * acc);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 8) {
+        // =========================================================================== producers
+        const int ptid = tid - 256;
+        const int q = ptid & 7, rg = ptid >> 3;              // channel quad of the chunk, 8-row group
+        // rows of stream chunk g (tile i = g / nchunks, chunk c) -> x ring stage g % NXS (cp.async, zero fill)
+        auto issue_x = [&](int g) {
+            const int i = g / nchunks, c = g - i * nchunks;
+            const int tile = blockIdx.x + i * gridDim.x;
+            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM2;
+            const uint32_t dst0 = smem_u32(smem + OFF_X) + (uint32_t)(g % NXS) * X_STAGE;
+            for (int u = ptid; u < XROWS * 8; u += NPROD) {
+                const int row = u >> 3, piece = u & 7;
+                const float* src = p.X;
+                uint32_t nbytes = 0;
+                if (MODE == MODE_GATHER) {
+                    const int sidx = srcs[(i & 1) * TM2 + row];
+                    if (sidx >= 0) { src = p.X + ((size_t)b * p.n_src + sidx) * K + c * KC + piece * 4; nbytes = 16; }
+                } else {
+                    const int t = t0 - HALO + row;
+                    if (t >= 0 && t < p.T) { src = p.X + ((size_t)b * p.T + t) * K + c * KC + piece * 4; nbytes = 16; }
+                }
+                cp_async16(dst0 + (uint32_t)row * (KC * 4) + (uint32_t)piece * 16u, src, nbytes);
+            }
+        };
+        // length regulator: source phoneme of every frame of tile i (GATHER mode)
+        auto compute_srcs = [&](int i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            if (tile >= n_tiles) return;
+            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM2;
+            const bool in_smem = p.n_src <= 1024;
+            if (in_smem) {
+                for (int k = ptid; k < p.n_src; k += NPROD) scum[k] = __ldg(p.cum + (size_t)b * p.n_src + k);
+                named_bar_sync(1, NPROD);
+            }
+            const int t = t0 + ptid;
+            int sidx = -1;
+            if (t < p.T && t < p.valid_len[b]) {
+                const int* cg = p.cum + (size_t)b * p.n_src;
+                int lo = 0, hi = p.n_src;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int cv = in_smem ? scum[mid] : __ldg(cg + mid);
+                    if (cv > t) hi = mid; else lo = mid + 1;
+                }
+                sidx = lo < p.n_src ? lo : -1;
+            }
+            srcs[(i & 1) * TM2 + ptid] = sidx;
+            named_bar_sync(1, NPROD);
+        };
+        if (MODE == MODE_GATHER) { compute_srcs(0); compute_srcs(1); }
+        for (int g = 0; g < 3; ++g) {                         // three chunks in flight
+            if (g < total_chunks) issue_x(g);
+            cp_async_commit();
+        }
+        for (int g = 0; g < total_chunks; ++g) {
+            const int i = g / nchunks, c = g - i * nchunks;
+            const int sx = g % NXS, sa = g % NAS;
+            cp_async_wait<2>();                               // this thread's share of chunk g has landed
+            named_bar_sync(2, NPROD);                         // ... everybody's; chunk g-1's stage is free
+            if (MODE == MODE_GATHER && c == 0 && i >= 1) compute_srcs(i + 1);   // sources one tile ahead
+            if (g + 3 < total_chunks) issue_x(g + 3);
+            cp_async_commit();
+
+            const float* Xc = reinterpret_cast<const float*>(smem + OFF_X + (uint32_t)sx * X_STAGE);
+            uint2 ahi[8], alo[8];
+            {
+                float4 win[8 + 2 * HALO];
+#pragma unroll
+                for (int k = 0; k < 8 + 2 * HALO; ++k) win[k] = reinterpret_cast<const float4*>(Xc + (rg * 8 + k) * KC)[q];
+                if (MODE == MODE_DWCONV) {
+                    float4 wdw[DWK], bdw;
+#pragma unroll
+                    for (int t = 0; t < DWK; ++t) wdw[t] = reinterpret_cast<const float4*>(dws + t * NMAX + c * KC)[q];
+                    bdw = reinterpret_cast<const float4*>(dws + DWK * NMAX + c * KC)[q];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        float4 o = bdw;
+#pragma unroll
+                        for (int t = 0; t < DWK; ++t) {
+                            o.x = fmaf(wdw[t].x, win[r + t].x, o.x);
+                            o.y = fmaf(wdw[t].y, win[r + t].y, o.y);
+                            o.z = fmaf(wdw[t].z, win[r + t].z, o.z);
+                            o.w = fmaf(wdw[t].w, win[r + t].w, o.w);
+                        }
+                        split4(o, ahi[r], alo[r]);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) split4(win[r], ahi[r], alo[r]);
+                }
+            }
+            // A stage free?  (its previous chunk, g - NAS, has been consumed by the tensor core)
+            if (g >= NAS && !mbar_wait(bar_cfree + 8 * sa, ((g / NAS) - 1) & 1)) failed = true;
+            uint8_t* a_hi = smem + OFF_A + (uint32_t)sa * A_STAGE;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t off = (uint32_t)(q >> 1) * A_PANEL + (uint32_t)(rg * 8 + r) * 16u + (uint32_t)(q & 1) * 8u;
+                *reinterpret_cast<uint2*>(a_hi + off) = ahi[r];
+                *reinterpret_cast<uint2*>(a_hi + A_PLANE + off) = alo[r];
+            }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_aready + 8 * sa);
+        }
+        cp_async_wait<0>();
+    } else {
+        // =========================================================================== epilogue
+        const int qd = warp & 3, half = warp >> 2;
+        const int rbase = qd * 32 + half * 16;
+        const int t4 = lane & 3, tr = lane >> 2;
+        const float inv_n = 1.f / (float)N;
+        const int nhalves = (N + 127) >> 7;                   // 128-column halves of the accumulator
+        const uint32_t lane_addr = (uint32_t)rbase << 16;
+
+        for (int i = 0; i < my_tiles; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM2;
+            const int rows_valid = min(TM2, p.T - t0);
+            const int acc = i & 1;
+            const int row0 = rbase + tr, row1 = row0 + 8;
+            const size_t g0 = (size_t)b * p.T + t0 + row0, g1 = g0 + 8;
+            const bool ok0 = row0 < rows_valid, ok1 = row1 < rows_valid;
+            const uint32_t tacc = tmem + lane_addr + (uint32_t)(acc * NMAX);
+            if (p.res2) {   // pull this warp's 16 skip rows (16 KB) towards L2 while the GEMM runs
+                const int pr = rbase + (lane >> 1);
+                if (pr < rows_valid) {
+                    const float* sp = p.res2 + ((size_t)b * p.T + t0 + pr) * N + (lane & 1) * 128;
+                    prefetch_l2(sp); prefetch_l2(sp + 32); prefetch_l2(sp + 64); prefetch_l2(sp + 96);
+                }
+            }
+            if (!mbar_wait(bar_accfull + 8 * acc, (i >> 1) & 1)) failed = true;
+            tc_fence_after_sync();
+            const int zero_from = p.zero_from ? p.zero_from[b] : 0x7fffffff;
+            const bool z0 = (t0 + row0) >= zero_from, z1 = (t0 + row1) >= zero_from;
+
+            // ---- pass 1: bias (+ tanh), first statistics; activated values go back into the accumulator
+            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+            const bool need_stats = p.ln_g != nullptr;
+            for (int h = 0; h < nhalves; ++h) {
+                uint32_t r[64];
+                tmem_ld_16x256b_x16(tacc + (uint32_t)(h * 128), r);
+                tmem_ld_wait();
+                const int njv = min(16, (N - h * 128) >> 3);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float2 bb = *reinterpret_cast<const float2*>(par + h * 128 + 8 * j + 2 * t4);
+                    float a, bq, cq, dq;
+                    if (p.act_tanh) {
+                        a = tanh_scaled2(fmaf(__uint_as_float(r[4 * j]), kTanhScale2, bb.x));
+                        bq = tanh_scaled2(fmaf(__uint_as_float(r[4 * j + 1]), kTanhScale2, bb.y));
+                        cq = tanh_scaled2(fmaf(__uint_as_float(r[4 * j + 2]), kTanhScale2, bb.x));
+                        dq = tanh_scaled2(fmaf(__uint_as_float(r[4 * j + 3]), kTanhScale2, bb.y));
+                    } else {
+                        a = __uint_as_float(r[4 * j]) + bb.x; bq = __uint_as_float(r[4 * j + 1]) + bb.y;
+                        cq = __uint_as_float(r[4 * j + 2]) + bb.x; dq = __uint_as_float(r[4 * j + 3]) + bb.y;
+                    }
+                    if (j >= njv) { a = bq = cq = dq = 0.f; }
+                    s0 += a + bq; q0 = fmaf(a, a, q0); q0 = fmaf(bq, bq, q0);
+                    s1 += cq + dq; q1 = fmaf(cq, cq, q1); q1 = fmaf(dq, dq, q1);
+                    r[4 * j] = __float_as_uint(a); r[4 * j + 1] = __float_as_uint(bq);
+                    r[4 * j + 2] = __float_as_uint(cq); r[4 * j + 3] = __float_as_uint(dq);
+                }
+                if (need_stats) {
+                    tmem_st_16x256b_x16(tacc + (uint32_t)(h * 128), r);
+                } else {
+                    // no LayerNorm (mel head): the values are final
+                    float* y0 = p.Y + g0 * N + h * 128 + 2 * t4;
+                    float* y1 = p.Y + g1 * N + h * 128 + 2 * t4;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j < njv) {
+                            if (ok0) *reinterpret_cast<float2*>(y0 + 8 * j) = z0 ? make_float2(0.f, 0.f)
+                                : make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]));
+                            if (ok1) *reinterpret_cast<float2*>(y1 + 8 * j) = z1 ? make_float2(0.f, 0.f)
+                                : make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                        }
+                    }
+                }
+            }
+            if (need_stats) {
+                tmem_st_wait();
+                float ra, na, rb, nb;
+                quad_stats(s0, q0, inv_n, ra, na);
+                quad_stats(s1, q1, inv_n, rb, nb);
+                // ---- pass 2: normalise; plain layers store, block-end layers add the skip row, take the
+                //      second statistics and write back once more
+                s0 = q0 = s1 = q1 = 0.f;
+                for (int h = 0; h < nhalves; ++h) {
+                    uint32_t r[64];
+                    tmem_ld_16x256b_x16(tacc + (uint32_t)(h * 128), r);
+                    float2 sk[8];
+                    if (p.res2) {
+                        const float* sp = p.res2 + g0 * N + h * 128 + 2 * t4;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) sk[j] = ok0 ? __ldg(reinterpret_cast<const float2*>(sp + 8 * j)) : make_float2(0.f, 0.f);
+                    }
+                    tmem_ld_wait();
+                    // in place on r[] (one 64-register array live at a time)
+#define RF(k) __uint_as_float(r[k])
+#define WF(k, x) r[k] = __float_as_uint(x)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 gg = *reinterpret_cast<const float2*>(par + NMAX + h * 128 + 8 * j + 2 * t4);
+                        const float2 bb = *reinterpret_cast<const float2*>(par + 2 * NMAX + h * 128 + 8 * j + 2 * t4);
+                        WF(4 * j, fmaf(fmaf(RF(4 * j), ra, na), gg.x, bb.x));
+                        WF(4 * j + 1, fmaf(fmaf(RF(4 * j + 1), ra, na), gg.y, bb.y));
+                        WF(4 * j + 2, fmaf(fmaf(RF(4 * j + 2), rb, nb), gg.x, bb.x));
+                        WF(4 * j + 3, fmaf(fmaf(RF(4 * j + 3), rb, nb), gg.y, bb.y));
+                    }
+                    if (p.res2) {
+                        // skip rows in four staged batches of 8 float2 (row0 low/high, row1 low/high)
+#pragma unroll
+                        for (int part = 0; part < 4; ++part) {
+                            const int rsel = part >> 1, jo = (part & 1) * 8;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float a = RF(4 * (jo + j) + 2 * rsel) + sk[j].x, bq = RF(4 * (jo + j) + 2 * rsel + 1) + sk[j].y;
+                                if (rsel == 0) { s0 += a + bq; q0 = fmaf(a, a, q0); q0 = fmaf(bq, bq, q0); }
+                                else { s1 += a + bq; q1 = fmaf(a, a, q1); q1 = fmaf(bq, bq, q1); }
+                                WF(4 * (jo + j) + 2 * rsel, a); WF(4 * (jo + j) + 2 * rsel + 1, bq);
+                            }
+                            if (part < 3) {
+                                const int nr = (part + 1) >> 1, njo = ((part + 1) & 1) * 8;
+                                const float* sp = p.res2 + (nr ? g1 : g0) * N + h * 128 + 2 * t4 + 8 * njo;
+                                const bool okn = nr ? ok1 : ok0;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) sk[j] = okn ? __ldg(reinterpret_cast<const float2*>(sp + 8 * j)) : make_float2(0.f, 0.f);
+                            }
+                        }
+                        tmem_st_16x256b_x16(tacc + (uint32_t)(h * 128), r);
+                    } else {
+                        float* y0 = p.Y + g0 * N + h * 128 + 2 * t4;
+                        float* y1 = p.Y + g1 * N + h * 128 + 2 * t4;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (ok0) *reinterpret_cast<float2*>(y0 + 8 * j) = z0 ? make_float2(0.f, 0.f) : make_float2(RF(4 * j), RF(4 * j + 1));
+                            if (ok1) *reinterpret_cast<float2*>(y1 + 8 * j) = z1 ? make_float2(0.f, 0.f) : make_float2(RF(4 * j + 2), RF(4 * j + 3));
+                        }
+                    }
+#undef RF
+#undef WF
+                }
+                if (p.res2) {
+                    tmem_st_wait();
+                    quad_stats(s0, q0, inv_n, ra, na);
+                    quad_stats(s1, q1, inv_n, rb, nb);
+                    // ---- pass 3: second LayerNorm, store
+                    for (int h = 0; h < nhalves; ++h) {
+                        uint32_t r[64];
+                        tmem_ld_16x256b_x16(tacc + (uint32_t)(h * 128), r);
+                        tmem_ld_wait();
+                        float* y0 = p.Y + g0 * N + h * 128 + 2 * t4;
+                        float* y1 = p.Y + g1 * N + h * 128 + 2 * t4;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float2 gg = *reinterpret_cast<const float2*>(par + 3 * NMAX + h * 128 + 8 * j + 2 * t4);
+                            const float2 bb = *reinterpret_cast<const float2*>(par + 4 * NMAX + h * 128 + 8 * j + 2 * t4);
+                            const float a = fmaf(fmaf(__uint_as_float(r[4 * j]), ra, na), gg.x, bb.x);
+                            const float bq = fmaf(fmaf(__uint_as_float(r[4 * j + 1]), ra, na), gg.y, bb.y);
+                            const float cq = fmaf(fmaf(__uint_as_float(r[4 * j + 2]), rb, nb), gg.x, bb.x);
+                            const float dq = fmaf(fmaf(__uint_as_float(r[4 * j + 3]), rb, nb), gg.y, bb.y);
+                            if (ok0) *reinterpret_cast<float2*>(y0 + 8 * j) = z0 ? make_float2(0.f, 0.f) : make_float2(a, bq);
+                            if (ok1) *reinterpret_cast<float2*>(y1 + 8 * j) = z1 ? make_float2(0.f, 0.f) : make_float2(cq, dq);
+                        }
+                    }
+                }
+            }
+            // the accumulator (and its scratch use) is done: the GEMM of tile i+2 may overwrite it
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_accfree + 8 * acc);
+        }
+    }
+
+    if (failed) atomicExch(p.err, 1);
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int MODE>
+int launch_mode256(const Dec256Params& p, int grid, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        ES_CUDA(cudaFuncSetAttribute(umma_dec256_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    ES_CUDA(launch_pdl(umma_dec256_kernel<MODE>, grid, NTHR, SMEM_BYTES, s, p));
+    ES_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace
+
+bool umma_dec256_supported(int K, int dw_k, int N, int mode) {
+    if (N != 256 && N != 80) return false;
+    if (K % KC || K < KC || K > 512) return false;
+    if (mode == MODE_DWCONV && (K != 256 || dw_k != DWK)) return false;
+    return true;
+}
+
+// mode: 0 depthwise layer, 1 gather + projection, 2 plain (mel head / stand-alone projection)
+int launch_umma_dec256(int mode, int B, int T, int K, int N, int n_src, const float* X, const int* cum,
+                       const int* valid_len, const float* dw_w, const float* dw_b, const void* w_chunks,
+                       const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
+                       const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
+                       float* Y, cudaStream_t s) {
+    ES_CHECK(w_chunks && X && Y && bias, "null tensor");
+    ES_CHECK(umma_dec256_supported(K, DWK, N, mode), "shape outside the wide decoder kernel's envelope");
+    ES_CHECK(!(ln_g || res2) || N == 256, "LayerNorm epilogue needs N == 256");
+    int* err_flag = umma_err_flag();
+    ES_CHECK(err_flag, "cannot allocate the device error flag");
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        ES_CUDA(cudaGetDevice(&dev));
+        ES_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    Dec256Params p;
+    p.B = B; p.T = T; p.K = K; p.N = N; p.n_src = n_src; p.X = X; p.cum = cum; p.valid_len = valid_len;
+    p.dw_w = dw_w; p.dw_b = dw_b; p.w_chunks = w_chunks; p.bias = bias; p.act_tanh = act_tanh;
+    p.ln_g = ln_g; p.ln_b = ln_b; p.res2 = res2; p.ln2_g = ln2_g; p.ln2_b = ln2_b;
+    p.zero_from = zero_from; p.Y = Y; p.err = err_flag;
+    const int n_tiles = B * ((T + TM2 - 1) / TM2);
+    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    switch (mode) {
+        case MODE_DWCONV: return launch_mode256<MODE_DWCONV>(p, grid, s);
+        case MODE_GATHER: return launch_mode256<MODE_GATHER>(p, grid, s);
+        default: return launch_mode256<MODE_PLAIN>(p, grid, s);
+    }
+}
+
+}  // namespace es

@@ -187,10 +187,13 @@ class _Backend:
                     folded[f"{which}.{cv}_w_h16"] = packing.canon_split_taps(folded[f"{which}.{cv}_w"], c.dim)
         if self.part == "decoder":
             # B operands of the tcgen05 kernels: W as [N][K], split into fp16 hi/lo, canonical order
+            # dx2 == 128: whole-matrix image (weights stay resident in shared memory, es_umma_dec.cu);
+            # dx2 == 256: K-chunked image streamed per tile (es_umma_dec256.cu)
+            split = packing.canon_split_fp16 if self.cfg.dx2 <= 128 else packing.canon_split_chunks
             for l in range(self.cfg.n_dec_layers):
-                folded[f"dec{l}.pw_w_h16"] = packing.canon_split_fp16(folded[f"dec{l}.pw_w"][0].T)
-            folded["dproj_w_h16"] = packing.canon_split_fp16(folded["dproj_w"][0].T)
-            folded["mel_w_h16"] = packing.canon_split_fp16(folded["mel_w"][0].T[:self.cfg.n_mel])
+                folded[f"dec{l}.pw_w_h16"] = split(folded[f"dec{l}.pw_w"][0].T)
+            folded["dproj_w_h16"] = split(folded["dproj_w"][0].T)
+            folded["mel_w_h16"] = split(folded["mel_w"][0].T[:self.cfg.n_mel])
         flat_np, off = packing.pack(folded)
         self.flat = torch.from_numpy(flat_np).to(device)
         base = self.flat.data_ptr()

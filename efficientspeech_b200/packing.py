@@ -152,6 +152,20 @@ def canon_split_fp16(w_nk: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(planes).reshape(-1).view(np.float32)
 
 
+def canon_split_chunks(w_nk: np.ndarray, kc: int = 32) -> np.ndarray:
+    """[N][K] fp32 weight -> K-chunked split-fp16 image ``[K/kc][2 (hi, lo)][kc/8][N][8]`` for the
+    wide-decoder kernel (es_umma_dec256.cu): every chunk is one contiguous bulk copy and is, by
+    itself, a UMMA canonical K-major no-swizzle B operand of kc columns."""
+    w32 = np.ascontiguousarray(w_nk, dtype=np.float32)
+    n, k = w32.shape
+    assert k % kc == 0 and kc % 8 == 0
+    hi = w32.astype(np.float16)
+    lo = (w32 - hi.astype(np.float32)).astype(np.float16)
+    planes = np.stack([hi, lo]).reshape(2, n, k // kc, kc // 8, 8)          # [pl][n][chunk][panel][8]
+    img = planes.transpose(2, 0, 3, 1, 4)                                   # [chunk][pl][panel][n][8]
+    return np.ascontiguousarray(img).reshape(-1).view(np.float32)
+
+
 def canon_split_taps(w_tkn: np.ndarray, n: int) -> np.ndarray:
     """Folded conv weight [taps][K][N_padded] -> per-tap canonical split-fp16 images
     ``[taps][2 (hi, lo)][K/8][N][8]`` for the tcgen05 row GEMM (es_umma_enc.cu)."""

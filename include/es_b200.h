@@ -103,8 +103,10 @@ typedef struct es_dec_layer_w {     /* networks.py:279-283 */
     const float* pw_b;
     const float* ln_g;
     const float* ln_b;
-    /* split-fp16 image of pw_w for the tcgen05 kernel in the UMMA canonical K-major no-swizzle
-     * order: [2 (hi, lo)][K/8][N][8] halves (NULL -> the SIMT kernel is used) */
+    /* split-fp16 image of pw_w for the tcgen05 kernels in the UMMA canonical K-major no-swizzle
+     * order.  dx2 == 128: [2 (hi, lo)][K/8][N][8] halves (resident weights, es_umma_dec.cu);
+     * dx2 == 256: K-chunked [K/32][2 (hi, lo)][4][N][8] (streamed, es_umma_dec256.cu).  The same
+     * convention holds for dproj_w_h16 / mel_w_h16.  NULL -> the SIMT kernel is used. */
     const void*  pw_w_h16;
 } es_dec_layer_w_t;
 

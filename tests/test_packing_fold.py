@@ -56,3 +56,15 @@ def test_pack_layout_and_split_fp16():
     back = img.transpose(0, 2, 1, 3).reshape(2, n, k).astype(np.float64)
     assert np.abs(back[0] + back[1] - w).max() < 2e-7
     assert np.array_equal(back[0].astype(np.float16), w.astype(np.float16))
+
+
+def test_chunked_split_image_is_per_chunk_canonical():
+    """es_umma_dec256.cu streams the weight in 32-column K chunks; every chunk must by itself be
+    the canonical K-major image of that column slice (so chunk c == canon_split_fp16(w[:, c*32:(c+1)*32]))."""
+    rng = np.random.default_rng(5)
+    for n, k in ((256, 256), (80, 256), (256, 512)):
+        w = rng.standard_normal((n, k)).astype(np.float32)
+        img = packing.canon_split_chunks(w).view(np.float16).reshape(k // 32, -1)
+        for c in range(k // 32):
+            ref = packing.canon_split_fp16(w[:, c * 32:(c + 1) * 32]).view(np.float16)
+            assert np.array_equal(img[c], ref)
