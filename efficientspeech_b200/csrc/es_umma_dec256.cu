@@ -6,9 +6,13 @@
 //
 //   x ring   (4 stages)  [132 rows][32 ch] fp32, filled by the producers with 16-byte cp.async
 //                        (zero-fill outside the utterance / for padded frames; in GATHER mode the
-//                        rows come from the length-regulator source indices), 3 chunks in flight
+//                        rows come from the length-regulator source indices), 3 chunks in flight.
+//                        Every producer thread owns one 16-byte column piece and rows r, r+16, ...:
+//                        the per-chunk address work is one pointer plus compile-time offsets.
 //   A ring   (3 stages)  the producers' depthwise conv (k=5, sliding window in registers) of the
-//                        chunk, split fp16 hi/lo, UMMA canonical K-major no-swizzle panels
+//                        chunk, split fp16 hi/lo, UMMA canonical K-major no-swizzle panels.  The
+//                        panel stride (descriptor LBO) is padded by 16 bytes so that the four
+//                        panels a warp writes at once fall into different banks.
 //   W ring   (3 stages)  the matching [N][32] slice of the split weights (pre-chunked at pack
 //                        time), one bulk async copy (TMA 1-D) per chunk, from L2
 //
@@ -18,7 +22,8 @@
 //
 // Epilogue (8 warps, 16 rows each, mma-fragment layout, 4 threads per row): a 256-channel row is
 // 2 x 64 values per thread -- too many to hold -- so the row statistics are taken in passes over
-// the accumulator, which is used as scratch: tanh(acc + bias) is written back with tcgen05.st,
+// the accumulator, 64 columns (32 registers) at a time with the next TMEM load in flight, and
+// the accumulator doubles as scratch: tanh(acc + bias) is written back with tcgen05.st,
 // normalised (+ skip, second statistics, written back again on block-end layers) and finally
 // stored with 8-byte accesses (8 rows x 32 contiguous bytes per warp instruction).
 //
@@ -44,26 +49,27 @@ constexpr int NXS = 4;                    // x ring depth
 constexpr int NAS = 3;                    // A / W ring depth
 constexpr int NMAX = 256;
 constexpr uint32_t X_STAGE = (TM2 + DWK - 1) * KC * 4;      // 16896
-constexpr uint32_t A_PANEL = TM2 * 16;                      // 2048: 8 channels of all 128 rows
-constexpr uint32_t A_PLANE = (KC / 8) * A_PANEL;            // 8192
-constexpr uint32_t A_STAGE = 2 * A_PLANE;                   // 16384 (hi, lo)
+constexpr uint32_t A_PANEL = TM2 * 16 + 16;                 // 2064: 8 channels of all 128 rows (+16: bank spread)
+constexpr uint32_t A_PLANE = (KC / 8) * A_PANEL;            // 8256
+constexpr uint32_t A_STAGE = 2 * A_PLANE;                   // 16512 (hi, lo)
 constexpr uint32_t W_STAGE = 2 * (KC / 8) * NMAX * 16;      // 32768 (hi, lo)
 
 constexpr uint32_t OFF_X = 0;
 constexpr uint32_t OFF_A = OFF_X + NXS * X_STAGE;           // 67584
-constexpr uint32_t OFF_W = OFF_A + NAS * A_STAGE;           // 116736
-constexpr uint32_t OFF_PAR = OFF_W + NAS * W_STAGE;         // 215040: bias, ln g/b, ln2 g/b (5 x 256 floats)
-constexpr uint32_t OFF_DW = OFF_PAR + 5 * NMAX * 4;         // 220160: depthwise taps + bias (6 x 256 floats)
-constexpr uint32_t OFF_SRC = OFF_DW + 6 * NMAX * 4;         // 226304: gather sources, 2 x 128 ints
-constexpr uint32_t OFF_CUM = OFF_SRC + 2 * TM2 * 4;         // 227328: duration prefix sums of the utterance (<= 1024)
-constexpr uint32_t OFF_BAR = OFF_CUM + 1024 * 4;            // 231424
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;              // 231552
+constexpr uint32_t OFF_W = OFF_A + NAS * A_STAGE;           // 117120
+constexpr uint32_t OFF_PAR = OFF_W + NAS * W_STAGE;         // bias, ln g/b, ln2 g/b (5 x 256 floats)
+constexpr uint32_t OFF_DW = OFF_PAR + 5 * NMAX * 4;         // depthwise taps + bias (6 x 256 floats)
+constexpr uint32_t OFF_SRC = OFF_DW + 6 * NMAX * 4;         // gather sources, 2 x 128 ints
+constexpr uint32_t OFF_CUM = OFF_SRC + 2 * TM2 * 4;         // duration prefix sums of the utterance (<= 1024)
+constexpr uint32_t OFF_BAR = OFF_CUM + 1024 * 4;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;
+static_assert(OFF_W % 128 == 0 && OFF_A % 128 == 0, "operand alignment");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 enum { MODE_DWCONV = 0, MODE_GATHER = 1, MODE_PLAIN = 2 };
 
 struct Dec256Params {
-    int B, T, K, N;              // K input channels (multiple of 32, <= 512), N output channels (256 | 80)
+    int B, T, K;                 // K input channels (multiple of 32, <= 512)
     int n_src;
     const float* X;              // DWCONV/PLAIN: [B,T,K]; GATHER: fused4 [B,n_src,K]
     const int* cum;
@@ -88,11 +94,45 @@ __device__ __forceinline__ float tanh_scaled2(float arg) {     // see es_umma_de
     return fmaf(-2.f, r, 1.f);
 }
 
-template <int MODE>
+// final store of one 64-column step of the fragment (2 rows x 16 columns per thread); NJ = valid
+// 8-column groups.  ZERO: rows at or beyond the utterance's mel length store zeros.
+template <int NJ, bool ZERO>
+__device__ __forceinline__ void store_frag(float* y0, float* y1, bool ok0, bool ok1, bool z0, bool z1,
+                                           const uint32_t (&r)[32]) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        float2 a = make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]));
+        float2 c = make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        if (ZERO) {
+            if (z0) a = make_float2(0.f, 0.f);
+            if (z1) c = make_float2(0.f, 0.f);
+        }
+        if (ok0) *reinterpret_cast<float2*>(y0 + 8 * j) = a;
+        if (ok1) *reinterpret_cast<float2*>(y1 + 8 * j) = c;
+    }
+}
+
+// y = LN(v) on one 64-column step: v*r + nm, then the affine pair at parc + 8j
+__device__ __forceinline__ void norm_frag(uint32_t (&r)[32], const float* g, const float* be,
+                                          float ra, float na, float rb, float nb) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float2 gg = *reinterpret_cast<const float2*>(g + 8 * j);
+        const float2 bb = *reinterpret_cast<const float2*>(be + 8 * j);
+        r[4 * j] = __float_as_uint(fmaf(fmaf(__uint_as_float(r[4 * j]), ra, na), gg.x, bb.x));
+        r[4 * j + 1] = __float_as_uint(fmaf(fmaf(__uint_as_float(r[4 * j + 1]), ra, na), gg.y, bb.y));
+        r[4 * j + 2] = __float_as_uint(fmaf(fmaf(__uint_as_float(r[4 * j + 2]), rb, nb), gg.x, bb.x));
+        r[4 * j + 3] = __float_as_uint(fmaf(fmaf(__uint_as_float(r[4 * j + 3]), rb, nb), gg.y, bb.y));
+    }
+}
+
+template <int MODE, int N>
 __global__ void __launch_bounds__(NTHR, 1)
 umma_dec256_kernel(const Dec256Params p) {
     constexpr int HALO = (MODE == MODE_DWCONV) ? DWK / 2 : 0;
     constexpr int XROWS = TM2 + 2 * HALO;
+    constexpr int XITER = (XROWS + 15) / 16;                   // rows r, r+16, ... per producer thread
+    constexpr int NH = (N + 63) / 64;                          // 64-column epilogue steps
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float* par = reinterpret_cast<float*>(smem + OFF_PAR);
@@ -107,14 +147,14 @@ umma_dec256_kernel(const Dec256Params p) {
     const uint32_t bar_accfree = bar0 + 88;     // [2] accumulator drained by the 8 epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 112);
 
-    const int N = p.N, K = p.K;
+    const int K = (MODE == MODE_DWCONV) ? 256 : p.K;
     const int nchunks = K / KC;
     const int tiles_per_utt = (p.T + TM2 - 1) / TM2;
     const int n_tiles = p.B * tiles_per_utt;
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_chunks = my_tiles * nchunks;
-    const uint32_t w_plane = (uint32_t)(KC / 8) * N * 16u;     // bytes of one fp16 plane of one chunk
-    const uint32_t w_chunk_bytes = 2 * w_plane;
+    constexpr uint32_t w_plane = (uint32_t)(KC / 8) * N * 16u;   // bytes of one fp16 plane of one chunk
+    constexpr uint32_t w_chunk_bytes = 2 * w_plane;
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);      // two 256-column fp32 accumulators
@@ -140,7 +180,7 @@ umma_dec256_kernel(const Dec256Params p) {
     if (MODE == MODE_DWCONV) {
         for (int i = tid; i < (DWK + 1) * NMAX; i += NTHR) {
             const int t = i / NMAX, c = i - t * NMAX;
-            dws[i] = c < K ? (t < DWK ? __ldg(p.dw_w + t * K + c) : __ldg(p.dw_b + c)) : 0.f;
+            dws[i] = t < DWK ? __ldg(p.dw_w + t * K + c) : __ldg(p.dw_b + c);
         }
     }
     tc_fence_before_sync();
@@ -154,28 +194,27 @@ umma_dec256_kernel(const Dec256Params p) {
     if (warp == 12) {
         // =========================================================================== issue warp
         const bool elected = elect_one();
-        const uint32_t idesc = make_idesc_f16(TM2, N);
-        const uint32_t lbo_b = (uint32_t)N * 16u;
-        auto load_w = [&](int g) {               // chunk g of this CTA's stream -> stage g % NAS
-            const int st = g % NAS, c = g % nchunks;
+        constexpr uint32_t idesc = make_idesc_f16(TM2, N);
+        constexpr uint32_t lbo_b = (uint32_t)N * 16u;
+        auto load_w = [&](int st, int c) {       // chunk c of the weight -> stage st
             mbar_arrive_expect_tx(bar_wfull + 8 * st, w_chunk_bytes);
             bulk_g2s(smem_u32(smem + OFF_W) + (uint32_t)st * W_STAGE,
                      reinterpret_cast<const uint8_t*>(p.w_chunks) + (size_t)c * w_chunk_bytes, w_chunk_bytes,
                      bar_wfull + 8 * st);
         };
         if (elected) {
-            if (total_chunks > 0) load_w(0);
-            if (total_chunks > 1) load_w(1);
+            if (total_chunks > 0) load_w(0, 0);
+            if (total_chunks > 1) load_w(1, 1 % nchunks);
         }
         __syncwarp();
+        int i = 0, c = 0, st = 0, use = 0;       // tile, chunk, ring stage, ring pass of chunk g
+        int st2 = 2 % NAS, c2 = 2 % nchunks;     // stage / weight chunk of chunk g + 2
         for (int g = 0; g < total_chunks; ++g) {
-            const int st = g % NAS, use = g / NAS;
-            const int i = g / nchunks, c = g - i * nchunks;
             const int acc = i & 1;
             // prefetch the weights two chunks ahead; their stage was last used by chunk g-1
             if (g + 2 < total_chunks) {
-                if (g >= 1 && !mbar_wait(bar_cfree + 8 * ((g + 2) % NAS), ((g - 1) / NAS) & 1)) failed = true;
-                if (elected) load_w(g + 2);
+                if (g >= 1 && !mbar_wait(bar_cfree + 8 * st2, ((g - 1) / NAS) & 1)) failed = true;
+                if (elected) load_w(st2, c2);
             }
             if (!mbar_wait(bar_wfull + 8 * st, use & 1)) failed = true;
             if (!mbar_wait(bar_aready + 8 * st, use & 1)) failed = true;
@@ -201,35 +240,66 @@ umma_dec256_kernel(const Dec256Params p) {
                 if (c == nchunks - 1) mma_commit(bar_accfull + 8 * acc);
             }
             __syncwarp();
+            if (++c == nchunks) { c = 0; ++i; }
+            if (++st == NAS) { st = 0; ++use; }
+            if (++st2 == NAS) st2 = 0;
+            if (++c2 == nchunks) c2 = 0;
         }
     } else if (warp >= 8) {
         // =========================================================================== producers
         const int ptid = tid - 256;
-        const int q = ptid & 7, rg = ptid >> 3;              // channel quad of the chunk, 8-row group
-        // rows of stream chunk g (tile i = g / nchunks, chunk c) -> x ring stage g % NXS (cp.async, zero fill)
-        auto issue_x = [&](int g) {
-            const int i = g / nchunks, c = g - i * nchunks;
+        const int q = ptid & 7, rg = ptid >> 3;              // conv: channel quad of the chunk, 8-row group
+        const int xrow = ptid >> 3;                           // loads: rows xrow + 16*it, 16-byte piece q
+        const uint32_t x_smem = smem_u32(smem + OFF_X);
+
+        // ---- load stream (runs three chunks ahead of the conv stream) ---------------------------
+        int ld_i = 0, ld_c = 0, ld_s = 0;                     // tile, chunk, x stage of the next chunk to load
+        const float* ld_base = p.X;                           // row xrow of the tile, this thread's piece
+        uint32_t ld_mask = 0;                                 // bit it: row xrow + 16*it exists
+        auto tile_setup = [&](int i) {
             const int tile = blockIdx.x + i * gridDim.x;
             const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM2;
-            const uint32_t dst0 = smem_u32(smem + OFF_X) + (uint32_t)(g % NXS) * X_STAGE;
-            for (int u = ptid; u < XROWS * 8; u += NPROD) {
-                const int row = u >> 3, piece = u & 7;
-                const float* src = p.X;
-                uint32_t nbytes = 0;
-                if (MODE == MODE_GATHER) {
-                    const int sidx = srcs[(i & 1) * TM2 + row];
-                    if (sidx >= 0) { src = p.X + ((size_t)b * p.n_src + sidx) * K + c * KC + piece * 4; nbytes = 16; }
-                } else {
-                    const int t = t0 - HALO + row;
-                    if (t >= 0 && t < p.T) { src = p.X + ((size_t)b * p.T + t) * K + c * KC + piece * 4; nbytes = 16; }
+            if (MODE == MODE_GATHER) {
+                ld_base = p.X + (size_t)b * p.n_src * K + q * 4;
+            } else {
+                const int tf = t0 - HALO + xrow;
+                ld_base = p.X + ((long long)b * p.T + tf) * K + q * 4;
+                ld_mask = 0;
+#pragma unroll
+                for (int it = 0; it < XITER; ++it) {
+                    const int t = tf + 16 * it;
+                    if (t >= 0 && t < p.T && xrow + 16 * it < XROWS) ld_mask |= 1u << it;
                 }
-                cp_async16(dst0 + (uint32_t)row * (KC * 4) + (uint32_t)piece * 16u, src, nbytes);
+            }
+        };
+        auto load_next = [&]() {
+            const uint32_t dst = x_smem + (uint32_t)ld_s * X_STAGE + (uint32_t)ptid * 16u;
+#pragma unroll
+            for (int it = 0; it < XITER; ++it) {
+                if (XROWS % 16 == 0 || it < XITER - 1 || xrow + 16 * it < XROWS) {
+                    const float* src;
+                    bool ok;
+                    if (MODE == MODE_GATHER) {
+                        const int sidx = srcs[(ld_i & 1) * TM2 + xrow + 16 * it];
+                        ok = sidx >= 0;
+                        src = ld_base + (size_t)(ok ? sidx : 0) * K + ld_c * KC;
+                    } else {
+                        ok = (ld_mask >> it) & 1u;
+                        src = ok ? ld_base + (size_t)(16 * it) * K + ld_c * KC : p.X;
+                    }
+                    cp_async16(dst + (uint32_t)it * (16u * KC * 4u), src, ok ? 16u : 0u);
+                }
+            }
+            if (++ld_s == NXS) ld_s = 0;
+            if (++ld_c == nchunks) {
+                ld_c = 0;
+                if (++ld_i < my_tiles) tile_setup(ld_i);
             }
         };
         // length regulator: source phoneme of every frame of tile i (GATHER mode)
         auto compute_srcs = [&](int i) {
+            if (i >= my_tiles) return;
             const int tile = blockIdx.x + i * gridDim.x;
-            if (tile >= n_tiles) return;
             const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM2;
             const bool in_smem = p.n_src <= 1024;
             if (in_smem) {
@@ -252,17 +322,17 @@ umma_dec256_kernel(const Dec256Params p) {
             named_bar_sync(1, NPROD);
         };
         if (MODE == MODE_GATHER) { compute_srcs(0); compute_srcs(1); }
+        if (my_tiles > 0) tile_setup(0);
         for (int g = 0; g < 3; ++g) {                         // three chunks in flight
-            if (g < total_chunks) issue_x(g);
+            if (g < total_chunks) load_next();
             cp_async_commit();
         }
+        int i = 0, c = 0, sx = 0, sa = 0, use = 0;
         for (int g = 0; g < total_chunks; ++g) {
-            const int i = g / nchunks, c = g - i * nchunks;
-            const int sx = g % NXS, sa = g % NAS;
             cp_async_wait<2>();                               // this thread's share of chunk g has landed
             named_bar_sync(2, NPROD);                         // ... everybody's; chunk g-1's stage is free
             if (MODE == MODE_GATHER && c == 0 && i >= 1) compute_srcs(i + 1);   // sources one tile ahead
-            if (g + 3 < total_chunks) issue_x(g + 3);
+            if (g + 3 < total_chunks) load_next();
             cp_async_commit();
 
             const float* Xc = reinterpret_cast<const float*>(smem + OFF_X + (uint32_t)sx * X_STAGE);
@@ -294,18 +364,21 @@ umma_dec256_kernel(const Dec256Params p) {
                 }
             }
             // A stage free?  (its previous chunk, g - NAS, has been consumed by the tensor core)
-            if (g >= NAS && !mbar_wait(bar_cfree + 8 * sa, ((g / NAS) - 1) & 1)) failed = true;
-            uint8_t* a_hi = smem + OFF_A + (uint32_t)sa * A_STAGE;
+            if (g >= NAS && !mbar_wait(bar_cfree + 8 * sa, (use - 1) & 1)) failed = true;
+            uint8_t* a_hi = smem + OFF_A + (uint32_t)sa * A_STAGE
+                            + (uint32_t)(q >> 1) * A_PANEL + (uint32_t)(rg * 8) * 16u + (uint32_t)(q & 1) * 8u;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const uint32_t off = (uint32_t)(q >> 1) * A_PANEL + (uint32_t)(rg * 8 + r) * 16u + (uint32_t)(q & 1) * 8u;
-                *reinterpret_cast<uint2*>(a_hi + off) = ahi[r];
-                *reinterpret_cast<uint2*>(a_hi + A_PLANE + off) = alo[r];
+                *reinterpret_cast<uint2*>(a_hi + r * 16) = ahi[r];
+                *reinterpret_cast<uint2*>(a_hi + A_PLANE + r * 16) = alo[r];
             }
             fence_proxy_async_smem();
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_aready + 8 * sa);
+            if (++c == nchunks) { c = 0; ++i; }
+            if (++sx == NXS) sx = 0;
+            if (++sa == NAS) { sa = 0; ++use; }
         }
         cp_async_wait<0>();
     } else {
@@ -313,9 +386,11 @@ umma_dec256_kernel(const Dec256Params p) {
         const int qd = warp & 3, half = warp >> 2;
         const int rbase = qd * 32 + half * 16;
         const int t4 = lane & 3, tr = lane >> 2;
-        const float inv_n = 1.f / (float)N;
-        const int nhalves = (N + 127) >> 7;                   // 128-column halves of the accumulator
+        constexpr float inv_n = 1.f / (float)N;
         const uint32_t lane_addr = (uint32_t)rbase << 16;
+        const bool need_stats = p.ln_g != nullptr;
+        const bool act_tanh = p.act_tanh != 0;
+        const float* parc = par + 2 * t4;                       // this thread's column pair
 
         for (int i = 0; i < my_tiles; ++i) {
             const int tile = blockIdx.x + i * gridDim.x;
@@ -323,8 +398,9 @@ umma_dec256_kernel(const Dec256Params p) {
             const int rows_valid = min(TM2, p.T - t0);
             const int acc = i & 1;
             const int row0 = rbase + tr, row1 = row0 + 8;
-            const size_t g0 = (size_t)b * p.T + t0 + row0, g1 = g0 + 8;
             const bool ok0 = row0 < rows_valid, ok1 = row1 < rows_valid;
+            float* y0 = p.Y + ((size_t)b * p.T + t0 + row0) * N + 2 * t4;
+            float* y1 = y0 + 8 * N;
             const uint32_t tacc = tmem + lane_addr + (uint32_t)(acc * NMAX);
             if (p.res2) {   // pull this warp's 16 skip rows (16 KB) towards L2 while the GEMM runs
                 const int pr = rbase + (lane >> 1);
@@ -333,140 +409,119 @@ umma_dec256_kernel(const Dec256Params p) {
                     prefetch_l2(sp); prefetch_l2(sp + 32); prefetch_l2(sp + 64); prefetch_l2(sp + 96);
                 }
             }
-            if (!mbar_wait(bar_accfull + 8 * acc, (i >> 1) & 1)) failed = true;
-            tc_fence_after_sync();
             const int zero_from = p.zero_from ? p.zero_from[b] : 0x7fffffff;
             const bool z0 = (t0 + row0) >= zero_from, z1 = (t0 + row1) >= zero_from;
+            const bool any_zero = __any_sync(0xffffffffu, z0 || z1);
+            if (!mbar_wait(bar_accfull + 8 * acc, (i >> 1) & 1)) failed = true;
+            tc_fence_after_sync();
 
-            // ---- pass 1: bias (+ tanh), first statistics; activated values go back into the accumulator
+            // ---- pass 1: bias (+ tanh), first statistics; activated values go back into the accumulator.
+            //      Two register buffers: the TMEM load of step h+1 is in flight while step h is processed.
             float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-            const bool need_stats = p.ln_g != nullptr;
-            for (int h = 0; h < nhalves; ++h) {
-                uint32_t r[64];
-                tmem_ld_16x256b_x16(tacc + (uint32_t)(h * 128), r);
-                tmem_ld_wait();
-                const int njv = min(16, (N - h * 128) >> 3);
+            {
+                uint32_t rA[32], rB[32];
+                tmem_ld_16x256b_x8(tacc, rA);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float2 bb = *reinterpret_cast<const float2*>(par + h * 128 + 8 * j + 2 * t4);
-                    float a, bq, cq, dq;
-                    if (p.act_tanh) {
-                        a = tanh_scaled2(fmaf(__uint_as_float(r[4 * j]), kTanhScale2, bb.x));
-                        bq = tanh_scaled2(fmaf(__uint_as_float(r[4 * j + 1]), kTanhScale2, bb.y));
-                        cq = tanh_scaled2(fmaf(__uint_as_float(r[4 * j + 2]), kTanhScale2, bb.x));
-                        dq = tanh_scaled2(fmaf(__uint_as_float(r[4 * j + 3]), kTanhScale2, bb.y));
-                    } else {
-                        a = __uint_as_float(r[4 * j]) + bb.x; bq = __uint_as_float(r[4 * j + 1]) + bb.y;
-                        cq = __uint_as_float(r[4 * j + 2]) + bb.x; dq = __uint_as_float(r[4 * j + 3]) + bb.y;
-                    }
-                    if (j >= njv) { a = bq = cq = dq = 0.f; }
-                    s0 += a + bq; q0 = fmaf(a, a, q0); q0 = fmaf(bq, bq, q0);
-                    s1 += cq + dq; q1 = fmaf(cq, cq, q1); q1 = fmaf(dq, dq, q1);
-                    r[4 * j] = __float_as_uint(a); r[4 * j + 1] = __float_as_uint(bq);
-                    r[4 * j + 2] = __float_as_uint(cq); r[4 * j + 3] = __float_as_uint(dq);
-                }
-                if (need_stats) {
-                    tmem_st_16x256b_x16(tacc + (uint32_t)(h * 128), r);
-                } else {
-                    // no LayerNorm (mel head): the values are final
-                    float* y0 = p.Y + g0 * N + h * 128 + 2 * t4;
-                    float* y1 = p.Y + g1 * N + h * 128 + 2 * t4;
+                for (int h = 0; h < NH; ++h) {
+                    uint32_t (&r)[32] = (h & 1) ? rB : rA;
+                    uint32_t (&rn)[32] = (h & 1) ? rA : rB;
+                    tmem_ld_wait();
+                    if (h + 1 < NH) tmem_ld_16x256b_x8(tacc + (uint32_t)((h + 1) * 64), rn);
+                    const int njv = (N - h * 64) >= 64 ? 8 : (N - h * 64) / 8;      // compile-time after unrolling
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < 8; ++j) {
                         if (j < njv) {
-                            if (ok0) *reinterpret_cast<float2*>(y0 + 8 * j) = z0 ? make_float2(0.f, 0.f)
-                                : make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]));
-                            if (ok1) *reinterpret_cast<float2*>(y1 + 8 * j) = z1 ? make_float2(0.f, 0.f)
-                                : make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                            const float2 bb = *reinterpret_cast<const float2*>(parc + h * 64 + 8 * j);
+                            float a, bq, cq, dq;
+                            if (act_tanh) {
+                                a = tanh_scaled2(fmaf(__uint_as_float(r[4 * j]), kTanhScale2, bb.x));
+                                bq = tanh_scaled2(fmaf(__uint_as_float(r[4 * j + 1]), kTanhScale2, bb.y));
+                                cq = tanh_scaled2(fmaf(__uint_as_float(r[4 * j + 2]), kTanhScale2, bb.x));
+                                dq = tanh_scaled2(fmaf(__uint_as_float(r[4 * j + 3]), kTanhScale2, bb.y));
+                            } else {
+                                a = __uint_as_float(r[4 * j]) + bb.x; bq = __uint_as_float(r[4 * j + 1]) + bb.y;
+                                cq = __uint_as_float(r[4 * j + 2]) + bb.x; dq = __uint_as_float(r[4 * j + 3]) + bb.y;
+                            }
+                            s0 += a + bq; q0 = fmaf(a, a, q0); q0 = fmaf(bq, bq, q0);
+                            s1 += cq + dq; q1 = fmaf(cq, cq, q1); q1 = fmaf(dq, dq, q1);
+                            r[4 * j] = __float_as_uint(a); r[4 * j + 1] = __float_as_uint(bq);
+                            r[4 * j + 2] = __float_as_uint(cq); r[4 * j + 3] = __float_as_uint(dq);
                         }
+                    }
+                    if (need_stats) {
+                        tmem_st_16x256b_x8(tacc + (uint32_t)(h * 64), r);
+                    } else if (N - h * 64 >= 64) {      // no LayerNorm (mel head): the values are final
+                        if (any_zero) store_frag<8, true>(y0 + h * 64, y1 + h * 64, ok0, ok1, z0, z1, r);
+                        else store_frag<8, false>(y0 + h * 64, y1 + h * 64, ok0, ok1, z0, z1, r);
+                    } else {
+                        constexpr int NJL = (N % 64) / 8 > 0 ? (N % 64) / 8 : 8;
+                        if (any_zero) store_frag<NJL, true>(y0 + h * 64, y1 + h * 64, ok0, ok1, z0, z1, r);
+                        else store_frag<NJL, false>(y0 + h * 64, y1 + h * 64, ok0, ok1, z0, z1, r);
                     }
                 }
             }
-            if (need_stats) {
+            if (N == NMAX && need_stats) {
                 tmem_st_wait();
                 float ra, na, rb, nb;
                 quad_stats(s0, q0, inv_n, ra, na);
                 quad_stats(s1, q1, inv_n, rb, nb);
-                // ---- pass 2: normalise; plain layers store, block-end layers add the skip row, take the
-                //      second statistics and write back once more
-                s0 = q0 = s1 = q1 = 0.f;
-                for (int h = 0; h < nhalves; ++h) {
-                    uint32_t r[64];
-                    tmem_ld_16x256b_x16(tacc + (uint32_t)(h * 128), r);
-                    float2 sk[8];
-                    if (p.res2) {
-                        const float* sp = p.res2 + g0 * N + h * 128 + 2 * t4;
+                if (!p.res2) {
+                    // ---- pass 2 (plain layer): normalise and store
+                    uint32_t rA[32], rB[32];
+                    tmem_ld_16x256b_x8(tacc, rA);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) sk[j] = ok0 ? __ldg(reinterpret_cast<const float2*>(sp + 8 * j)) : make_float2(0.f, 0.f);
+                    for (int h = 0; h < NH; ++h) {
+                        uint32_t (&r)[32] = (h & 1) ? rB : rA;
+                        uint32_t (&rn)[32] = (h & 1) ? rA : rB;
+                        tmem_ld_wait();
+                        if (h + 1 < NH) tmem_ld_16x256b_x8(tacc + (uint32_t)((h + 1) * 64), rn);
+                        norm_frag(r, parc + NMAX + h * 64, parc + 2 * NMAX + h * 64, ra, na, rb, nb);
+                        if (any_zero) store_frag<8, true>(y0 + h * 64, y1 + h * 64, ok0, ok1, z0, z1, r);
+                        else store_frag<8, false>(y0 + h * 64, y1 + h * 64, ok0, ok1, z0, z1, r);
                     }
-                    tmem_ld_wait();
-                    // in place on r[] (one 64-register array live at a time)
-#define RF(k) __uint_as_float(r[k])
-#define WF(k, x) r[k] = __float_as_uint(x)
+                } else {
+                    // ---- pass 2 (block end): normalise, add the skip row, second statistics, write back
+                    s0 = q0 = s1 = q1 = 0.f;
+                    const float* sp0 = p.res2 + ((size_t)b * p.T + t0 + row0) * N + 2 * t4;
+                    const float* sp1 = sp0 + 8 * N;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float2 gg = *reinterpret_cast<const float2*>(par + NMAX + h * 128 + 8 * j + 2 * t4);
-                        const float2 bb = *reinterpret_cast<const float2*>(par + 2 * NMAX + h * 128 + 8 * j + 2 * t4);
-                        WF(4 * j, fmaf(fmaf(RF(4 * j), ra, na), gg.x, bb.x));
-                        WF(4 * j + 1, fmaf(fmaf(RF(4 * j + 1), ra, na), gg.y, bb.y));
-                        WF(4 * j + 2, fmaf(fmaf(RF(4 * j + 2), rb, nb), gg.x, bb.x));
-                        WF(4 * j + 3, fmaf(fmaf(RF(4 * j + 3), rb, nb), gg.y, bb.y));
-                    }
-                    if (p.res2) {
-                        // skip rows in four staged batches of 8 float2 (row0 low/high, row1 low/high)
+                    for (int h = 0; h < NH; ++h) {
+                        uint32_t r[32];
+                        tmem_ld_16x256b_x8(tacc + (uint32_t)(h * 64), r);
+                        float2 k0[8], k1[8];
 #pragma unroll
-                        for (int part = 0; part < 4; ++part) {
-                            const int rsel = part >> 1, jo = (part & 1) * 8;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float a = RF(4 * (jo + j) + 2 * rsel) + sk[j].x, bq = RF(4 * (jo + j) + 2 * rsel + 1) + sk[j].y;
-                                if (rsel == 0) { s0 += a + bq; q0 = fmaf(a, a, q0); q0 = fmaf(bq, bq, q0); }
-                                else { s1 += a + bq; q1 = fmaf(a, a, q1); q1 = fmaf(bq, bq, q1); }
-                                WF(4 * (jo + j) + 2 * rsel, a); WF(4 * (jo + j) + 2 * rsel + 1, bq);
-                            }
-                            if (part < 3) {
-                                const int nr = (part + 1) >> 1, njo = ((part + 1) & 1) * 8;
-                                const float* sp = p.res2 + (nr ? g1 : g0) * N + h * 128 + 2 * t4 + 8 * njo;
-                                const bool okn = nr ? ok1 : ok0;
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) sk[j] = okn ? __ldg(reinterpret_cast<const float2*>(sp + 8 * j)) : make_float2(0.f, 0.f);
-                            }
+                        for (int j = 0; j < 8; ++j) {
+                            k0[j] = ok0 ? __ldg(reinterpret_cast<const float2*>(sp0 + h * 64 + 8 * j)) : make_float2(0.f, 0.f);
+                            k1[j] = ok1 ? __ldg(reinterpret_cast<const float2*>(sp1 + h * 64 + 8 * j)) : make_float2(0.f, 0.f);
                         }
-                        tmem_st_16x256b_x16(tacc + (uint32_t)(h * 128), r);
-                    } else {
-                        float* y0 = p.Y + g0 * N + h * 128 + 2 * t4;
-                        float* y1 = p.Y + g1 * N + h * 128 + 2 * t4;
+                        tmem_ld_wait();
+                        norm_frag(r, parc + NMAX + h * 64, parc + 2 * NMAX + h * 64, ra, na, rb, nb);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (ok0) *reinterpret_cast<float2*>(y0 + 8 * j) = z0 ? make_float2(0.f, 0.f) : make_float2(RF(4 * j), RF(4 * j + 1));
-                            if (ok1) *reinterpret_cast<float2*>(y1 + 8 * j) = z1 ? make_float2(0.f, 0.f) : make_float2(RF(4 * j + 2), RF(4 * j + 3));
+                        for (int j = 0; j < 8; ++j) {
+                            const float a = __uint_as_float(r[4 * j]) + k0[j].x, bq = __uint_as_float(r[4 * j + 1]) + k0[j].y;
+                            const float cq = __uint_as_float(r[4 * j + 2]) + k1[j].x, dq = __uint_as_float(r[4 * j + 3]) + k1[j].y;
+                            s0 += a + bq; q0 = fmaf(a, a, q0); q0 = fmaf(bq, bq, q0);
+                            s1 += cq + dq; q1 = fmaf(cq, cq, q1); q1 = fmaf(dq, dq, q1);
+                            r[4 * j] = __float_as_uint(a); r[4 * j + 1] = __float_as_uint(bq);
+                            r[4 * j + 2] = __float_as_uint(cq); r[4 * j + 3] = __float_as_uint(dq);
                         }
+                        tmem_st_16x256b_x8(tacc + (uint32_t)(h * 64), r);
                     }
-#undef RF
-#undef WF
-                }
-                if (p.res2) {
                     tmem_st_wait();
                     quad_stats(s0, q0, inv_n, ra, na);
                     quad_stats(s1, q1, inv_n, rb, nb);
                     // ---- pass 3: second LayerNorm, store
-                    for (int h = 0; h < nhalves; ++h) {
-                        uint32_t r[64];
-                        tmem_ld_16x256b_x16(tacc + (uint32_t)(h * 128), r);
-                        tmem_ld_wait();
-                        float* y0 = p.Y + g0 * N + h * 128 + 2 * t4;
-                        float* y1 = p.Y + g1 * N + h * 128 + 2 * t4;
+                    uint32_t rA[32], rB[32];
+                    tmem_ld_16x256b_x8(tacc, rA);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float2 gg = *reinterpret_cast<const float2*>(par + 3 * NMAX + h * 128 + 8 * j + 2 * t4);
-                            const float2 bb = *reinterpret_cast<const float2*>(par + 4 * NMAX + h * 128 + 8 * j + 2 * t4);
-                            const float a = fmaf(fmaf(__uint_as_float(r[4 * j]), ra, na), gg.x, bb.x);
-                            const float bq = fmaf(fmaf(__uint_as_float(r[4 * j + 1]), ra, na), gg.y, bb.y);
-                            const float cq = fmaf(fmaf(__uint_as_float(r[4 * j + 2]), rb, nb), gg.x, bb.x);
-                            const float dq = fmaf(fmaf(__uint_as_float(r[4 * j + 3]), rb, nb), gg.y, bb.y);
-                            if (ok0) *reinterpret_cast<float2*>(y0 + 8 * j) = z0 ? make_float2(0.f, 0.f) : make_float2(a, bq);
-                            if (ok1) *reinterpret_cast<float2*>(y1 + 8 * j) = z1 ? make_float2(0.f, 0.f) : make_float2(cq, dq);
-                        }
+                    for (int h = 0; h < NH; ++h) {
+                        uint32_t (&r)[32] = (h & 1) ? rB : rA;
+                        uint32_t (&rn)[32] = (h & 1) ? rA : rB;
+                        tmem_ld_wait();
+                        if (h + 1 < NH) tmem_ld_16x256b_x8(tacc + (uint32_t)((h + 1) * 64), rn);
+                        norm_frag(r, parc + 3 * NMAX + h * 64, parc + 4 * NMAX + h * 64, ra, na, rb, nb);
+                        if (any_zero) store_frag<8, true>(y0 + h * 64, y1 + h * 64, ok0, ok1, z0, z1, r);
+                        else store_frag<8, false>(y0 + h * 64, y1 + h * 64, ok0, ok1, z0, z1, r);
                     }
                 }
             }
@@ -483,14 +538,14 @@ umma_dec256_kernel(const Dec256Params p) {
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int MODE>
+template <int MODE, int N>
 int launch_mode256(const Dec256Params& p, int grid, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        ES_CUDA(cudaFuncSetAttribute(umma_dec256_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        ES_CUDA(cudaFuncSetAttribute(umma_dec256_kernel<MODE, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    ES_CUDA(launch_pdl(umma_dec256_kernel<MODE>, grid, NTHR, SMEM_BYTES, s, p));
+    ES_CUDA(launch_pdl(umma_dec256_kernel<MODE, N>, grid, NTHR, SMEM_BYTES, s, p));
     ES_LAUNCH_OK();
     return 0;
 }
@@ -500,7 +555,8 @@ int launch_mode256(const Dec256Params& p, int grid, cudaStream_t s) {
 bool umma_dec256_supported(int K, int dw_k, int N, int mode) {
     if (N != 256 && N != 80) return false;
     if (K % KC || K < KC || K > 512) return false;
-    if (mode == MODE_DWCONV && (K != 256 || dw_k != DWK)) return false;
+    if (mode == MODE_DWCONV && (K != 256 || dw_k != DWK || N != 256)) return false;
+    if (mode == MODE_GATHER && N != 256) return false;
     return true;
 }
 
@@ -513,6 +569,7 @@ int launch_umma_dec256(int mode, int B, int T, int K, int N, int n_src, const fl
     ES_CHECK(w_chunks && X && Y && bias, "null tensor");
     ES_CHECK(umma_dec256_supported(K, DWK, N, mode), "shape outside the wide decoder kernel's envelope");
     ES_CHECK(!(ln_g || res2) || N == 256, "LayerNorm epilogue needs N == 256");
+    ES_CHECK(!res2 || ln_g, "the skip path needs the first LayerNorm");
     int* err_flag = umma_err_flag();
     ES_CHECK(err_flag, "cannot allocate the device error flag");
     static int n_sm = 0;
@@ -522,16 +579,18 @@ int launch_umma_dec256(int mode, int B, int T, int K, int N, int n_src, const fl
         ES_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
     Dec256Params p;
-    p.B = B; p.T = T; p.K = K; p.N = N; p.n_src = n_src; p.X = X; p.cum = cum; p.valid_len = valid_len;
+    p.B = B; p.T = T; p.K = K; p.n_src = n_src; p.X = X; p.cum = cum; p.valid_len = valid_len;
     p.dw_w = dw_w; p.dw_b = dw_b; p.w_chunks = w_chunks; p.bias = bias; p.act_tanh = act_tanh;
     p.ln_g = ln_g; p.ln_b = ln_b; p.res2 = res2; p.ln2_g = ln2_g; p.ln2_b = ln2_b;
     p.zero_from = zero_from; p.Y = Y; p.err = err_flag;
     const int n_tiles = B * ((T + TM2 - 1) / TM2);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
     switch (mode) {
-        case MODE_DWCONV: return launch_mode256<MODE_DWCONV>(p, grid, s);
-        case MODE_GATHER: return launch_mode256<MODE_GATHER>(p, grid, s);
-        default: return launch_mode256<MODE_PLAIN>(p, grid, s);
+        case MODE_DWCONV: return launch_mode256<MODE_DWCONV, 256>(p, grid, s);
+        case MODE_GATHER: return launch_mode256<MODE_GATHER, 256>(p, grid, s);
+        default:
+            if (N == 256) return launch_mode256<MODE_PLAIN, 256>(p, grid, s);
+            return launch_mode256<MODE_PLAIN, 80>(p, grid, s);
     }
 }
 
