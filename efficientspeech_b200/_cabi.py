@@ -8,7 +8,7 @@ from typing import Optional
 
 from . import build as _build
 
-ES_ABI_VERSION = 6
+ES_ABI_VERSION = 7
 ES_MAX_ENC_BLOCKS = 2
 ES_MAX_DEC_LAYERS = 24
 ES_MAX_DEC_BLOCKS = 8
@@ -65,6 +65,7 @@ PROTOTYPES = {
     "es_length_regulate": (_i, [_vp, _vp, _i, _i, _i] + [_vp] * 6),
     "es_decoder_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _sz]),
     "es_decoder_forward_gathered": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz]),
+    "es_dense_layout": (_i, [_i, _i, _i, _i]),
     "es_check_async_errors": (_i, [_vp]),
     "es_debug_set_trace": (_i, [_vp]),
     "es_launch_count": (C.c_uint64, []),

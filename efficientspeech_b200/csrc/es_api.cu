@@ -124,7 +124,8 @@ RowGemmParams base_params(int B, int n_in, int n_out, int K, int Nout, const flo
 // Dense layer: tcgen05 row GEMM when the layer is inside its envelope, fp32 SIMT otherwise.
 int gemm(const es_model* m, const RowGemmParams& p, const void* w_h16, cudaStream_t s) {
     if (m->use_tensor_core && w_h16) {
-        const int rc = launch_umma_rowgemm(p, w_h16, s);
+        const int lay = dense_layout(p.K, p.Nout, p.taps, p.stride);     // decides the packed image's format too
+        const int rc = lay == 1 ? launch_umma_rowgemm(p, w_h16, s) : lay >= 2 ? launch_umma_wide(p, w_h16, s) : -1;
         if (rc >= 0) return rc;
     }
     return launch_rowgemm(p, s);
@@ -197,6 +198,22 @@ int predictors(const es_model* m, int B, int N, const float* fused, float* const
         const void* w1[3] = {w[0]->conv1_w_h16, w[1]->conv1_w_h16, w[2]->conv1_w_h16};
         const void* w2[3] = {w[0]->conv2_w_h16, w[1]->conv2_w_h16, w[2]->conv2_w_h16};
         int rc;
+        if (dense_layout(st1[0].K, st1[0].Nout, st1[0].taps, st1[0].stride) >= 2) {
+            // wide predictors (base): streamed-weight kernel, one launch per predictor and stage
+            for (int i = 0; i < 3; ++i) {
+                ProfRange r(ES_K_PREDICTOR, s);
+                rc = launch_umma_wide(st1[i], w1[i], s);
+                if (rc > 0) return 1;
+                if (rc < 0 && launch_rowgemm(st1[i], s)) return 1;
+            }
+            for (int i = 0; i < 3; ++i) {
+                ProfRange r(ES_K_PREDICTOR, s);
+                rc = launch_umma_wide(st2[i], w2[i], s);
+                if (rc > 0) return 1;
+                if (rc < 0 && launch_rowgemm(st2[i], s)) return 1;
+            }
+            return 0;
+        }
         { ProfRange r(ES_K_PREDICTOR, s); rc = launch_umma_rowgemm_batch(st1, w1, 3, s); }
         if (rc > 0) return 1;
         if (rc == 0) {
@@ -233,6 +250,7 @@ int es_abi_version(void) { return ES_ABI_VERSION; }
 const char* es_last_error(void) { return es::g_error.c_str(); }
 uint64_t es_launch_count(void) { return es::g_launches.load(); }
 int es_debug_set_trace(void* dev_buf_i64) { es::umma_dec_set_trace(static_cast<long long*>(dev_buf_i64)); return 0; }
+int es_dense_layout(int K, int n_out, int taps, int stride) { return es::dense_layout(K, n_out, taps, stride); }
 int es_check_async_errors(void* stream) { return es::umma_dec_check_errors(static_cast<cudaStream_t>(stream)); }
 
 int es_profile_begin(int max_records) {

@@ -44,9 +44,9 @@ extern std::atomic<uint64_t> g_launches;
 
 // ---- launch with programmatic stream serialization (PDL); the kernel must call griddepcontrol.wait --
 template <typename Param>
-inline cudaError_t launch_pdl(void (*kernel)(Param), int grid, int block, size_t smem, cudaStream_t s, const Param& p) {
+inline cudaError_t launch_pdl(void (*kernel)(Param), dim3 grid, int block, size_t smem, cudaStream_t s, const Param& p) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = grid;
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;

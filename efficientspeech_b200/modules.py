@@ -172,19 +172,28 @@ class _Backend:
         sd = self._state()
         folded = packing.fold_encoder(sd, self.cfg) if self.part == "encoder" else packing.fold_decoder(sd, self.cfg)
         if self.part == "encoder":
-            # B operands of the tcgen05 row GEMM (layers inside its envelope: K <= 128, multiples of 16)
+            # B operands of the tcgen05 row GEMMs; the library says which image format each layer uses
+            # (resident taps image for es_umma_enc.cu, streamed units for es_umma_wide.cu)
             c = self.cfg
+
+            def image(name: str, n: int, stride: int = 1) -> np.ndarray:
+                w = folded[name]                                  # [taps][K][N_padded]
+                lay = lib.es_dense_layout(int(w.shape[1]), int(n), int(w.shape[0]), int(stride))
+                if lay >= 2:
+                    return packing.canon_split_units(w, n, 128 if lay == 2 else 256)
+                return packing.canon_split_taps(w, n)
+
             for i in range(2):
                 ci, hi, hci = c.enc_dims[i], c.enc_heads[i], c.enc_dims[i] * c.expansion
                 if i == 1:
-                    folded["enc1.merge_w_h16"] = packing.canon_split_taps(folded["enc1.merge_w"], ci)
-                folded[f"enc{i}.qkv_w_h16"] = packing.canon_split_taps(folded[f"enc{i}.qkv_w"], 3 * hi * ci)
-                folded[f"enc{i}.proj_w_h16"] = packing.canon_split_taps(folded[f"enc{i}.proj_w"], ci)
-                folded[f"enc{i}.ffn1_w_h16"] = packing.canon_split_taps(folded[f"enc{i}.ffn1_w"], hci)
-                folded[f"enc{i}.ffn2_w_h16"] = packing.canon_split_taps(folded[f"enc{i}.ffn2_w"], ci)
+                    folded["enc1.merge_w_h16"] = image("enc1.merge_w", ci, stride=2)
+                folded[f"enc{i}.qkv_w_h16"] = image(f"enc{i}.qkv_w", 3 * hi * ci)
+                folded[f"enc{i}.proj_w_h16"] = image(f"enc{i}.proj_w", ci)
+                folded[f"enc{i}.ffn1_w_h16"] = image(f"enc{i}.ffn1_w", hci)
+                folded[f"enc{i}.ffn2_w_h16"] = image(f"enc{i}.ffn2_w", ci)
             for which in ("pitch", "energy", "duration"):
                 for cv in ("conv1", "conv2"):
-                    folded[f"{which}.{cv}_w_h16"] = packing.canon_split_taps(folded[f"{which}.{cv}_w"], c.dim)
+                    folded[f"{which}.{cv}_w_h16"] = image(f"{which}.{cv}_w", c.dim)
         if self.part == "decoder":
             # B operands of the tcgen05 kernels: W as [N][K], split into fp16 hi/lo, canonical order
             # dx2 == 128: whole-matrix image (weights stay resident in shared memory, es_umma_dec.cu);

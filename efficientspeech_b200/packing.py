@@ -173,6 +173,21 @@ def canon_split_taps(w_tkn: np.ndarray, n: int) -> np.ndarray:
     return np.concatenate([canon_split_fp16(np.ascontiguousarray(w_tkn[t].T[:n])) for t in range(taps)])
 
 
+def canon_split_units(w_tkn: np.ndarray, n: int, nt: int, kc: int = 32) -> np.ndarray:
+    """Folded conv weight [taps][K][N_padded] -> streamed units for es_umma_wide.cu, in the order the
+    kernel consumes them: ``[n/nt][K/kc][taps][2 (hi, lo)][kc/8][nt][8]`` halves -- each unit is the
+    canonical K-major image of one tap's [nt][kc] slice (== canon_split_fp16 of that slice)."""
+    taps, k, _ = w_tkn.shape
+    assert n % nt == 0 and k % kc == 0
+    out = []
+    for y in range(n // nt):
+        for c in range(k // kc):
+            for t in range(taps):
+                sl = np.ascontiguousarray(w_tkn[t, c * kc:(c + 1) * kc, y * nt:(y + 1) * nt].T)   # [nt][kc]
+                out.append(canon_split_fp16(sl))
+    return np.concatenate(out)
+
+
 def pack(folded: Dict[str, np.ndarray]) -> Tuple[np.ndarray, Dict[str, int]]:
     """Concatenate the folded arrays (fp32, 256-byte aligned) -> (flat buffer, element offsets)."""
     offsets: Dict[str, int] = {}

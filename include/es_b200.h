@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ES_ABI_VERSION 6
+#define ES_ABI_VERSION 7
 #define ES_MAX_ENC_BLOCKS 2
 #define ES_MAX_DEC_LAYERS 24
 #define ES_MAX_DEC_BLOCKS 8
@@ -199,6 +199,16 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
                                 const float* fused4, const int32_t* dur_cum, const int32_t* mel_len,
                                 int zero_padded_frames, float* mel,
                                 void* workspace, size_t workspace_bytes);
+
+/* Format of the split-fp16 tensor-core image (`*_w_h16`) of a dense phoneme-side layer with K input
+ * channels, n_out output channels, `taps` conv taps and the given stride (the encoder blocks' qkv /
+ * proj / ffn1 / ffn2 / merge weights, the predictors' conv1 / conv2):
+ *   0  none: the layer runs on the fp32 SIMT kernel, the pointer is ignored
+ *   1  resident image  [taps][2 (hi,lo)][K/8][n_out][8] halves           (packing.canon_split_taps)
+ *   2  streamed units  [n_out/128][K/32][taps][2][4][128][8] halves      (packing.canon_split_units)
+ *   3  streamed units  [n_out/256][K/32][taps][2][4][256][8] halves
+ * The host packs what this returns; the library dispatches on the same rule. */
+int es_dense_layout(int K, int n_out, int taps, int stride);
 
 /* The tcgen05 kernels bound every mbarrier wait; a timeout sets a device flag instead of hanging
  * the GPU.  This call synchronises `stream` and returns non-zero if the flag was raised. */

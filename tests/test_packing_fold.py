@@ -68,3 +68,17 @@ def test_chunked_split_image_is_per_chunk_canonical():
         for c in range(k // 32):
             ref = packing.canon_split_fp16(w[:, c * 32:(c + 1) * 32]).view(np.float16)
             assert np.array_equal(img[c], ref)
+
+
+def test_streamed_units_image_order():
+    """es_umma_wide.cu consumes [n/nt][K/32][taps] units, each the canonical image of one tap's
+    [nt][32] slice."""
+    rng = np.random.default_rng(6)
+    taps, k, n, npad, nt = 3, 128, 256, 256, 128
+    w = rng.standard_normal((taps, k, npad)).astype(np.float32)
+    img = packing.canon_split_units(w, n, nt).view(np.float16).reshape(n // nt, k // 32, taps, -1)
+    for y in range(n // nt):
+        for c in range(k // 32):
+            for t in range(taps):
+                ref = packing.canon_split_fp16(np.ascontiguousarray(w[t, c * 32:(c + 1) * 32, y * nt:(y + 1) * nt].T))
+                assert np.array_equal(img[y, c, t], ref.view(np.float16))
