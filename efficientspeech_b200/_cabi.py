@@ -8,7 +8,7 @@ from typing import Optional
 
 from . import build as _build
 
-ES_ABI_VERSION = 7
+ES_ABI_VERSION = 8
 ES_MAX_ENC_BLOCKS = 2
 ES_MAX_DEC_LAYERS = 24
 ES_MAX_DEC_BLOCKS = 8
@@ -44,6 +44,7 @@ class es_weights_t(C.Structure):
     _fields_ = [
         ("enc", es_enc_block_w_t * ES_MAX_ENC_BLOCKS),
         ("fuse_a0", _fp), ("fuse_g", _fp), ("fuse_gb", _fp), ("fuse_c", _fp),
+        ("fuse_u_h16", _fp), ("fuse_a0_h16", _fp),
         ("pitch", es_predictor_w_t), ("energy", es_predictor_w_t), ("duration", es_predictor_w_t),
         ("dproj_w", _fp), ("dproj_b", _fp), ("dproj_ln_g", _fp), ("dproj_ln_b", _fp),
         ("dec", es_dec_layer_w_t * ES_MAX_DEC_LAYERS),

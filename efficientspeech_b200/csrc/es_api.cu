@@ -369,7 +369,28 @@ int es_encoder_forward(es_model_t* m, void* stream, int B, int N,
     }
     if (encoder_block(m, 1, B, n1, e.xm1, mask1, e, e.feat1, s)) return 1;
     // fuse (networks.py:189-219)
-    { ProfRange r(ES_K_FUSE, s);
+    bool fused_done = false;
+    if (m->use_tensor_core && m->w.fuse_u_h16 && m->w.fuse_a0_h16 && d % 128 == 0) {
+        // tensor-core form: U = feat1 [G_0|..|G_{k-1}] + [g_0|..|g_{k-1}] for every half-rate position (e.qkv is
+        // free by now), then fused = mask(c + A0 feat0 + the stride-2 scatter of U) in the second GEMM's epilogue
+        const int k = m->k[0];
+        float* U = e.qkv;
+        RowGemmParams p = base_params(B, n1, n1, 2 * d, k * d, e.feat1, 2 * d, nullptr, U, k * d);
+        p.bias = m->w.fuse_gb;
+        int rc;
+        { ProfRange r(ES_K_FUSE, s); rc = launch_umma_wide(p, m->w.fuse_u_h16, s, 128); }
+        if (rc > 0) return 1;
+        if (rc == 0) {
+            p = base_params(B, N, N, d, d, e.feat0, d, nullptr, e.fused, d);
+            p.bias = m->w.fuse_c; p.row_mask = phoneme_mask;
+            p.fuse_u = U; p.fuse_k = k; p.fuse_n1 = n1; p.fuse_ld = k * d;
+            ProfRange r(ES_K_FUSE, s);
+            rc = launch_umma_wide(p, m->w.fuse_a0_h16, s, 128);
+            if (rc != 0) { ES_CHECK(rc < 0, "fuse GEMM failed"); ES_CHECK(false, "fuse epilogue outside the streamed kernel's envelope"); }
+            fused_done = true;
+        }
+    }
+    if (!fused_done) { ProfRange r(ES_K_FUSE, s);
       if (launch_fuse(e.feat0, e.feat1, m->w.fuse_a0, m->w.fuse_g, m->w.fuse_gb, m->w.fuse_c, phoneme_mask,
                       e.fused, B, N, n1, d, m->k[0], s)) return 1; }
     // predictors (networks.py:349,357,366)

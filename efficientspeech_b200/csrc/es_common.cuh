@@ -131,6 +131,10 @@ struct RowGemmParams {
     int ldr2;
     const float* ln2_g;
     const float* ln2_b;
+    // Fuse epilogue (es_umma_wide.cu only): out[t] += sum over tau = t mod 2, tau < fuse_k, 0 <= (t-tau)/2 < fuse_n1
+    // of fuse_u[(b*fuse_n1 + (t-tau)/2) * fuse_ld + tau*Nout + col]         (ConvTranspose1d stride 2, networks.py:199-206)
+    const float* fuse_u;
+    int fuse_k, fuse_n1, fuse_ld;
     const uint8_t* row_mask;   // [B][n_out], 1 -> zero the row
     const int* zero_from;      // [B], rows t >= zero_from[b] are zeroed
     float* Y;                  // [B*n_out][ldy] or null

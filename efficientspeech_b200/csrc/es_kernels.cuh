@@ -43,7 +43,7 @@ int launch_umma_rowgemm(const RowGemmParams& p, const void* w_h16, cudaStream_t 
 int launch_umma_rowgemm_batch(const RowGemmParams* ps, const void* const* w_h16, int count, cudaStream_t s);
 // K-streamed row GEMM for the layers outside that envelope (es_umma_wide.cu); -1: not applicable
 int dense_layout(int K, int Nout, int taps, int stride);   // 0 none, 1 resident taps image, 2/3 streamed units (NT 128/256)
-int launch_umma_wide(const RowGemmParams& p, const void* w_units, cudaStream_t s);
+int launch_umma_wide(const RowGemmParams& p, const void* w_units, cudaStream_t s, int nt_force = 0);
 // tcgen05 attention (es_umma_attn.cu); -1: outside its envelope (n > 128 or C not in {32, 64})
 int launch_umma_attention(const float* qkv, float* out, int B, int n, int C, int H, float scale, cudaStream_t s);
 

@@ -357,6 +357,20 @@ umma_wide_kernel(const WideParams wp) {
                         v[4 * j] += k0[j].x; v[4 * j + 1] += k0[j].y; v[4 * j + 2] += k1[j].x; v[4 * j + 3] += k1[j].y;
                     }
                 }
+                if (p.fuse_u) {
+                    for (int tau = tt0 & 1; tau < p.fuse_k; tau += 2) {      // tt1 = tt0 + 8 has the same parity
+                        const int j0 = (tt0 - tau) >> 1, j1 = (tt1 - tau) >> 1;
+                        const bool v0 = ok0 && tt0 >= tau && j0 < p.fuse_n1, v1 = ok1 && tt1 >= tau && j1 < p.fuse_n1;
+                        const float* u0 = p.fuse_u + ((size_t)b * p.fuse_n1 + j0) * p.fuse_ld + tau * p.Nout + col0 + cb;
+                        const float* u1 = p.fuse_u + ((size_t)b * p.fuse_n1 + j1) * p.fuse_ld + tau * p.Nout + col0 + cb;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 a = v0 ? __ldg(reinterpret_cast<const float2*>(u0 + 8 * j)) : make_float2(0.f, 0.f);
+                            const float2 c2 = v1 ? __ldg(reinterpret_cast<const float2*>(u1 + 8 * j)) : make_float2(0.f, 0.f);
+                            v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += c2.x; v[4 * j + 3] += c2.y;
+                        }
+                    }
+                }
                 if (has_ln) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -449,6 +463,12 @@ int launch_wide(const WideParams& wp, dim3 grid, cudaStream_t s) {
 // Which split-fp16 weight image a dense phoneme-side layer uses (the host packs accordingly):
 // 0 none (fp32 SIMT only), 1 resident taps image (es_umma_enc.cu), 2 / 3 streamed units with
 // 128 / 256 output columns per tile (this file).
+// output columns per CTA of the streamed kernel for this geometry (0: not applicable)
+static int wide_tile(int K, int Nout, int taps, int stride) {
+    if (stride != 1 || (taps != 1 && taps != 3) || K % KC || K < KC) return 0;
+    return Nout % 256 == 0 ? 256 : Nout % 128 == 0 ? 128 : 0;
+}
+
 int dense_layout(int K, int Nout, int taps, int stride) {
     const bool geom1 = (stride == 1 && (taps == 1 || taps == 3)) || (stride == 2 && taps == 1);
     if (geom1 && K % 16 == 0 && K >= 16 && K <= 128 && Nout % 8 == 0 && Nout >= 16 && Nout <= 384 &&
@@ -456,25 +476,28 @@ int dense_layout(int K, int Nout, int taps, int stride) {
         const int nj = Nout > 128 ? 16 : Nout / 8;
         if (nj == 4 || nj == 8 || nj == 12 || nj == 16) return 1;
     }
-    if (stride == 1 && (taps == 1 || taps == 3) && K % KC == 0 && K >= KC) {
-        if (Nout % 256 == 0) return 3;
-        if (Nout % 128 == 0) return 2;
-    }
-    return 0;
+    const int nt = wide_tile(K, Nout, taps, stride);
+    return nt == 256 ? 3 : nt == 128 ? 2 : 0;
 }
 
 // Returns -1 when the layer's epilogue is outside this kernel's envelope (caller uses the SIMT path).
-int launch_umma_wide(const RowGemmParams& p_in, const void* w_units, cudaStream_t s) {
-    const int lay = dense_layout(p_in.K, p_in.Nout, p_in.taps, p_in.stride);
-    if (lay < 2 || !w_units) return -1;
-    const int NT = lay == 3 ? 256 : 128;
+// `nt_force` (128): the image was packed with that tile width regardless of dense_layout (Fuse).
+int launch_umma_wide(const RowGemmParams& p_in, const void* w_units, cudaStream_t s, int nt_force) {
+    int NT = wide_tile(p_in.K, p_in.Nout, p_in.taps, p_in.stride);
+    if (nt_force) {
+        if (NT == 0 || p_in.Nout % nt_force) return -1;
+        NT = nt_force;
+    } else if (dense_layout(p_in.K, p_in.Nout, p_in.taps, p_in.stride) < 2) {
+        return -1;
+    }
+    if (NT == 0 || !w_units) return -1;
     RowGemmParams p = p_in;
     if (p.mode != ROW_PLAIN || p.res2 || p.act1 == ACT_TANH) return -1;
     if (p.act2 != ACT_NONE && p.act2 != ACT_RELU) return -1;
     if ((p.ln_g || p.dot_out) && p.Nout != NT) return -1;      // whole row in one column tile
     if (p.lda % 4 || (p.Y && p.ldy % 2) || (p.res1 && p.ldr1 % 2)) return -1;
     if (p.n_in != p.n_out || p.pad != p.taps / 2) return -1;   // 'same' convs only
-    if (p.taps == 1 && !p.zero_from) {                          // row-local: utterance boundaries do not matter
+    if (p.taps == 1 && !p.zero_from && !p.fuse_u) {            // row-local: utterance boundaries do not matter
         p.n_in = p.n_out = p.B * p.n_out;
         p.B = 1;
     }

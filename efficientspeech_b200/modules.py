@@ -194,6 +194,12 @@ class _Backend:
             for which in ("pitch", "energy", "duration"):
                 for cv in ("conv1", "conv2"):
                     folded[f"{which}.{cv}_w_h16"] = image(f"{which}.{cv}_w", c.dim)
+            if c.dim % 128 == 0:
+                # Fuse as two tensor-core GEMMs (es_api.cu: fuse): all k transposed-conv taps at once
+                k = folded["fuse_g"].shape[0]
+                gcat = np.concatenate([folded["fuse_g"][t] for t in range(k)], axis=1)[None]       # [1][2d][k*d]
+                folded["fuse_u_h16"] = packing.canon_split_units(gcat, k * c.dim, 128)
+                folded["fuse_a0_h16"] = packing.canon_split_units(folded["fuse_a0"][None], c.dim, 128)
         if self.part == "decoder":
             # B operands of the tcgen05 kernels: W as [N][K], split into fp16 hi/lo, canonical order
             # dx2 == 128: whole-matrix image (weights stay resident in shared memory, es_umma_dec.cu);
@@ -218,6 +224,9 @@ class _Backend:
                         setattr(W.enc[i], f, at(f"enc{i}.{f}"))
             for f in ("fuse_a0", "fuse_g", "fuse_gb", "fuse_c"):
                 setattr(W, f, at(f))
+            for f in ("fuse_u_h16", "fuse_a0_h16"):
+                if f in off:
+                    setattr(W, f, at(f))
             for which in ("pitch", "energy", "duration"):
                 pw = getattr(W, which)
                 for f, _ in _cabi.es_predictor_w_t._fields_:

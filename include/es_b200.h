@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ES_ABI_VERSION 7
+#define ES_ABI_VERSION 8
 #define ES_MAX_ENC_BLOCKS 2
 #define ES_MAX_DEC_LAYERS 24
 #define ES_MAX_DEC_BLOCKS 8
@@ -117,6 +117,12 @@ typedef struct es_weights {
     const float* fuse_g;     /* [k][2d][d]    = Wf[:, d:] . Wct_tau^T . Wm1 */
     const float* fuse_gb;    /* [k][d]        = Wf[:, d:] . Wct_tau^T . bm1 */
     const float* fuse_c;     /* [d]           = Wf[:, :d] bm0 + Wf[:, d:] bct + bf */
+    /* tensor-core form of the same maps for d % 128 == 0 (base), both as streamed units with 128
+     * output columns (es_dense_layout format 2): U = feat1 . [G_0 | .. | G_{k-1}] + [g_0 | .. | g_{k-1}]
+     * for every half-rate position, then fused[t] = c + A0 feat0[t] + sum_{tau = t mod 2, ..} U_tau[(t - tau) / 2].
+     * NULL -> the fp32 SIMT fuse kernel runs. */
+    const void*  fuse_u_h16;   /* units image of [2d] -> [k*d] */
+    const void*  fuse_a0_h16;  /* units image of [d] -> [d] */
     es_predictor_w_t pitch;
     es_predictor_w_t energy;
     es_predictor_w_t duration;
