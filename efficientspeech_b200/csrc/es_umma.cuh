@@ -232,15 +232,68 @@ __device__ __forceinline__ uint32_t canon_off(int row, int kchunk, int rows) {
     return (uint32_t)kchunk * (uint32_t)(rows * 16) + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2) ------------------------------------------------------
+// Two fp32 lanes in one 64-bit register pair, one issue slot per instruction: the epilogues and the
+// operand producers of the tensor-core kernels are issue-bound, not FLOP-bound, so halving the FMA-pipe
+// instruction count is what matters.  Each lane is an ordinary IEEE fma.rn / add.rn (bit-identical to
+// the scalar form).  pk2/up2 are register-allocation no-ops when the halves already sit in an aligned pair.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 pk2u(uint32_t lo, uint32_t hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 up2(f32x2 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // ---- shared epilogue / prologue math ------------------------------------------------------------------
 constexpr float kLnEpsU = 1e-5f;
+// 2 consecutive channels -> split fp16 pair: hi = fp16(v), lo = fp16(v - hi)
+__device__ __forceinline__ void split2(f32x2 v, uint32_t& hi, uint32_t& lo) {
+    const float2 a = up2(v);
+    const __half2 h = __floats2half2_rn(a.x, a.y);
+    const float2 b = __half22float2(h);
+    const float2 d = up2(sub2(v, pk2(b.x, b.y)));
+    const __half2 l = __floats2half2_rn(d.x, d.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 // 4 consecutive channels -> split fp16: hi = fp16(v), lo = fp16(v - hi)
 __device__ __forceinline__ void split4(float4 v, uint2& hi, uint2& lo) {
-    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-    const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
-    const __half2 l0 = __floats2half2_rn(v.x - b0.x, v.y - b0.y), l1 = __floats2half2_rn(v.z - b1.x, v.w - b1.y);
-    hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-    lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    split2(pk2(v.x, v.y), hi.x, lo.x);
+    split2(pk2(v.z, v.w), hi.y, lo.y);
+}
+__device__ __forceinline__ void split4(ulonglong2 v, uint2& hi, uint2& lo) {
+    split2(v.x, hi.x, lo.x);
+    split2(v.y, hi.y, lo.y);
 }
 
 // LayerNorm in the 16x256b fragment layout: v[4j+2*row+b] = column 8j+2*t4+b of this thread's row
@@ -300,6 +353,50 @@ __device__ __forceinline__ void fragment_layernorm_row(float (&v)[64], const flo
         const float2 bb = *reinterpret_cast<const float2*>(be + 8 * j + 2 * t4);
         v[4 * j + 2 * ROW] = fmaf(fmaf(v[4 * j + 2 * ROW], r, nm), gg.x, bb.x);
         v[4 * j + 2 * ROW + 1] = fmaf(fmaf(v[4 * j + 2 * ROW + 1], r, nm), gg.y, bb.y);
+    }
+}
+
+// ---- packed-pair versions of the fragment LayerNorm: v[2j + row] holds columns 8j+2*t4, +1 of this thread's
+// row `row` (the 16x256b fragment layout, adjacent columns paired) ---------------------------------------
+__device__ __forceinline__ void fragment_layernorm2_p(f32x2 (&v)[32], const float* __restrict__ g,
+                                                      const float* __restrict__ be, int t4, float inv_n) {
+    f32x2 s0 = 0ull, q0 = 0ull, s1 = 0ull, q1 = 0ull;          // (+0.f, +0.f)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        s0 = add2(s0, v[2 * j]); q0 = fma2(v[2 * j], v[2 * j], q0);
+        s1 = add2(s1, v[2 * j + 1]); q1 = fma2(v[2 * j + 1], v[2 * j + 1], q1);
+    }
+    const float2 a0 = up2(s0), b0 = up2(q0), a1 = up2(s1), b1 = up2(q1);
+    float r0, n0, r1, n1;
+    quad_stats(a0.x + a0.y, b0.x + b0.y, inv_n, r0, n0);
+    quad_stats(a1.x + a1.y, b1.x + b1.y, inv_n, r1, n1);
+    const f32x2 R0 = pk2(r0, r0), N0 = pk2(n0, n0), R1 = pk2(r1, r1), N1 = pk2(n1, n1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const f32x2 gg = *reinterpret_cast<const f32x2*>(g + 8 * j + 2 * t4);
+        const f32x2 bb = *reinterpret_cast<const f32x2*>(be + 8 * j + 2 * t4);
+        v[2 * j] = fma2(fma2(v[2 * j], R0, N0), gg, bb);
+        v[2 * j + 1] = fma2(fma2(v[2 * j + 1], R1, N1), gg, bb);
+    }
+}
+template <int ROW>
+__device__ __forceinline__ void fragment_layernorm_row_p(f32x2 (&v)[32], const float* __restrict__ g,
+                                                         const float* __restrict__ be, int t4, float inv_n) {
+    f32x2 s = 0ull, q = 0ull, s2 = 0ull, q2 = 0ull;            // two chains per statistic (one row only: less ILP)
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        s = add2(s, v[2 * j + ROW]); q = fma2(v[2 * j + ROW], v[2 * j + ROW], q);
+        s2 = add2(s2, v[2 * j + 2 + ROW]); q2 = fma2(v[2 * j + 2 + ROW], v[2 * j + 2 + ROW], q2);
+    }
+    const float2 a = up2(add2(s, s2)), b = up2(add2(q, q2));
+    float r, nm;
+    quad_stats(a.x + a.y, b.x + b.y, inv_n, r, nm);
+    const f32x2 R = pk2(r, r), NM = pk2(nm, nm);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const f32x2 gg = *reinterpret_cast<const f32x2*>(g + 8 * j + 2 * t4);
+        const f32x2 bb = *reinterpret_cast<const f32x2*>(be + 8 * j + 2 * t4);
+        v[2 * j + ROW] = fma2(fma2(v[2 * j + ROW], R, NM), gg, bb);
     }
 }
 

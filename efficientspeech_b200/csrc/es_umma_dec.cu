@@ -92,11 +92,15 @@ struct UmmaDecParams {
 // The argument arrives pre-scaled (acc * c + bias * c, c = 2 log2 e).  Saturates correctly at
 // +-inf (ex2 -> inf -> rcp -> 0 -> 1; ex2 -> 0 -> rcp(1) -> -1); absolute error ~1.2e-7.
 constexpr float kTanhScale = 2.8853900817779268f;
-__device__ __forceinline__ float tanh_from_scaled(float arg) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
-    return fmaf(-2.f, r, 1.f);
+__device__ __forceinline__ float ex2_approx(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+    return e;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // byte offset of channels 4*lane..4*lane+3 of tile row `row` inside an A plane
@@ -234,7 +238,7 @@ umma_dec_kernel(const UmmaDecParams p) {
     } else if (warp >= 8) {
         // =========================================================================== producers
         const int pw = warp - 8, ptid = tid - 256;
-        const float4* dwp = reinterpret_cast<const float4*>(smem + OFF_DW);   // [5 taps + bias][32 lanes] float4
+        const ulonglong2* dwp = reinterpret_cast<const ulonglong2*>(smem + OFF_DW);   // [5 taps + bias][32 lanes] 4 channels as 2 fp32 pairs
 
         int i = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
@@ -293,12 +297,12 @@ umma_dec_kernel(const UmmaDecParams p) {
             uint2 ahi[16], alo[16];                          // this lane's share: 16 rows x 4 channels, split fp16
             if (MODE == MODE_GATHER) {
                 // all 16 source rows of this warp are requested at once (one L2 round trip, not two)
-                float4 rowv[16];
+                ulonglong2 rowv[16];
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
                     const int sidx = srcs[pw * 16 + r];
-                    rowv[r] = sidx >= 0 ? __ldg(reinterpret_cast<const float4*>(p.X + ((size_t)b * p.n_src + sidx) * CK) + lane)
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                    rowv[r] = sidx >= 0 ? __ldg(reinterpret_cast<const ulonglong2*>(p.X + ((size_t)b * p.n_src + sidx) * CK) + lane)
+                                        : make_ulonglong2(0ull, 0ull);
                 }
 #pragma unroll
                 for (int r = 0; r < 16; ++r) split4(rowv[r], ahi[r], alo[r]);
@@ -307,27 +311,26 @@ umma_dec_kernel(const UmmaDecParams p) {
                 for (int pass = 0; pass < 2; ++pass) {
                     const int r0 = pw * 16 + pass * 8;
                     // per-lane depthwise taps for channels 4*lane..4*lane+3 (3 KB in shared memory; kept out of
-                    // the persistent register set so the staged A rows fit without spilling)
-                    float4 wdw[DWK], bdw;
+                    // the persistent register set so the staged A rows fit without spilling); channel pairs
+                    // are packed fp32x2 operands: 10 FFMA2 per row instead of 20 FFMA
+                    ulonglong2 wdw[DWK], bdw;
                     if (MODE == MODE_DWCONV) {
 #pragma unroll
                         for (int t = 0; t < DWK; ++t) wdw[t] = dwp[t * 32 + lane];
                         bdw = dwp[DWK * 32 + lane];
                     }
-                    float4 win[8 + 2 * HALO];
+                    ulonglong2 win[8 + 2 * HALO];
 #pragma unroll
-                    for (int k = 0; k < 8 + 2 * HALO; ++k) win[k] = reinterpret_cast<const float4*>(Xs + (r0 + k) * CK)[lane];
+                    for (int k = 0; k < 8 + 2 * HALO; ++k) win[k] = reinterpret_cast<const ulonglong2*>(Xs + (r0 + k) * CK)[lane];
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        float4 o;
+                        ulonglong2 o;
                         if (MODE == MODE_DWCONV) {
                             o = bdw;
 #pragma unroll
                             for (int t = 0; t < DWK; ++t) {
-                                o.x = fmaf(wdw[t].x, win[r + t].x, o.x);
-                                o.y = fmaf(wdw[t].y, win[r + t].y, o.y);
-                                o.z = fmaf(wdw[t].z, win[r + t].z, o.z);
-                                o.w = fmaf(wdw[t].w, win[r + t].w, o.w);
+                                o.x = fma2(wdw[t].x, win[r + t].x, o.x);
+                                o.y = fma2(wdw[t].y, win[r + t].y, o.y);
                             }
                         } else {
                             o = win[r];
@@ -397,57 +400,69 @@ umma_dec_kernel(const UmmaDecParams p) {
             // block-end layers: the 32 skip values of this thread's first row are requested NOW (L2-prefetched
             // above) and land while the tanh / LayerNorm math below runs; the second row's follow while the
             // first row is normalised (keeps the live set at 64 + 32 registers)
-            float2 sk[16];
+            f32x2 sk[16];
             const float* s0 = p.res2 + g0 * N + 2 * t4;
             const float* s1 = p.res2 + g1 * N + 2 * t4;
             if (p.res2) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    sk[j] = ok0 ? __ldg(reinterpret_cast<const float2*>(s0 + 8 * j)) : make_float2(0.f, 0.f);
+                    sk[j] = ok0 ? __ldg(reinterpret_cast<const f32x2*>(s0 + 8 * j)) : 0ull;
             }
-            float v[64];
+            // v[2j + row]: columns 8j + 2*t4, +1 of this thread's row `row`, as one packed fp32 pair
+            f32x2 v[32];
             if (p.act_tanh) {
+                // tanh(x) = 1 - 2 / (1 + 2^(x * 2 log2 e)): FFMA2, 2 x MUFU.EX2, FADD2, 2 x MUFU.RCP, FFMA2 per pair
+                const f32x2 cs = pk2(kTanhScale, kTanhScale), one2 = pk2(1.f, 1.f), mtwo2 = pk2(-2.f, -2.f);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float2 bb = *reinterpret_cast<const float2*>(par + 8 * j + 2 * t4);
-                    v[4 * j] = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j]), kTanhScale, bb.x));
-                    v[4 * j + 1] = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j + 1]), kTanhScale, bb.y));
-                    v[4 * j + 2] = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j + 2]), kTanhScale, bb.x));
-                    v[4 * j + 3] = tanh_from_scaled(fmaf(__uint_as_float(r[4 * j + 3]), kTanhScale, bb.y));
+                    const f32x2 bb = *reinterpret_cast<const f32x2*>(par + 8 * j + 2 * t4);
+#pragma unroll
+                    for (int row = 0; row < 2; ++row) {
+                        const float2 a = up2(fma2(pk2u(r[4 * j + 2 * row], r[4 * j + 2 * row + 1]), cs, bb));
+                        const float2 d = up2(add2(pk2(ex2_approx(a.x), ex2_approx(a.y)), one2));
+                        v[2 * j + row] = fma2(mtwo2, pk2(rcp_approx(d.x), rcp_approx(d.y)), one2);
+                    }
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float2 bb = *reinterpret_cast<const float2*>(par + 8 * j + 2 * t4);
-                    v[4 * j] = __uint_as_float(r[4 * j]) + bb.x;
-                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
-                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.x;
-                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.y;
+                    const f32x2 bb = *reinterpret_cast<const f32x2*>(par + 8 * j + 2 * t4);
+                    v[2 * j] = add2(pk2u(r[4 * j], r[4 * j + 1]), bb);
+                    v[2 * j + 1] = add2(pk2u(r[4 * j + 2], r[4 * j + 3]), bb);
                 }
             }
-            if (p.ln_g) fragment_layernorm2(v, par + 128, par + 256, t4, inv_n);   // LayerNorm only with N == 128
+            if (p.ln_g) fragment_layernorm2_p(v, par + 128, par + 256, t4, inv_n);   // LayerNorm only with N == 128
             if (tr_on) ES_TRACE(2 + g, u, 3);
             if (p.res2) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { v[4 * j] += sk[j].x; v[4 * j + 1] += sk[j].y; }
+                for (int j = 0; j < 16; ++j) v[2 * j] = add2(v[2 * j], sk[j]);
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    sk[j] = ok1 ? __ldg(reinterpret_cast<const float2*>(s1 + 8 * j)) : make_float2(0.f, 0.f);
-                fragment_layernorm_row<0>(v, par + 384, par + 512, t4, inv_n);
+                    sk[j] = ok1 ? __ldg(reinterpret_cast<const f32x2*>(s1 + 8 * j)) : 0ull;
+                fragment_layernorm_row_p<0>(v, par + 384, par + 512, t4, inv_n);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { v[4 * j + 2] += sk[j].x; v[4 * j + 3] += sk[j].y; }
-                fragment_layernorm_row<1>(v, par + 384, par + 512, t4, inv_n);
+                for (int j = 0; j < 16; ++j) v[2 * j + 1] = add2(v[2 * j + 1], sk[j]);
+                fragment_layernorm_row_p<1>(v, par + 384, par + 512, t4, inv_n);
             }
             if (tr_on) ES_TRACE(2 + g, u, 4);
-            const int zero_from = p.zero_from ? p.zero_from[b] : 0x7fffffff;
-            const bool z0 = (t0 + row0) >= zero_from, z1 = (t0 + row1) >= zero_from;
+            if (p.zero_from) {          // mel head: frames past mel_len are zeroed (networks.py:424-427); rare rows
+                const int zero_from = p.zero_from[b];
+                if (t0 + row0 >= zero_from) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[2 * j] = 0ull;
+                }
+                if (t0 + row1 >= zero_from) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[2 * j + 1] = 0ull;
+                }
+            }
             float* y0 = p.Y + g0 * N + 2 * t4;
             float* y1 = p.Y + g1 * N + 2 * t4;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 if (j < nj) {
-                    if (ok0) *reinterpret_cast<float2*>(y0 + 8 * j) = z0 ? make_float2(0.f, 0.f) : make_float2(v[4 * j], v[4 * j + 1]);
-                    if (ok1) *reinterpret_cast<float2*>(y1 + 8 * j) = z1 ? make_float2(0.f, 0.f) : make_float2(v[4 * j + 2], v[4 * j + 3]);
+                    if (ok0) *reinterpret_cast<f32x2*>(y0 + 8 * j) = v[2 * j];
+                    if (ok1) *reinterpret_cast<f32x2*>(y1 + 8 * j) = v[2 * j + 1];
                 }
             }
             if (tr_on) ES_TRACE(2 + g, u, 5);
