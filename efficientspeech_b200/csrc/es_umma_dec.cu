@@ -115,7 +115,9 @@ __device__ __forceinline__ uint32_t a_off(int row, int lane) {
         if (p.trace && blockIdx.x == 0 && (iter) < 32) p.trace[((role) * 32 + (iter)) * 8 + (ev)] = clock64(); \
     } while (0)
 
-template <int MODE>
+// RES2: block-end layer (skip add + second LayerNorm) -- a compile-time switch, so that the plain layers do not
+// reserve the 32 skip registers and ptxas can hoist the parameter loads of the epilogue instead
+template <int MODE, bool RES2>
 __global__ void __launch_bounds__(NTHR, 1)
 umma_dec_kernel(const UmmaDecParams p) {
     constexpr int HALO = (MODE == MODE_DWCONV) ? DWK / 2 : 0;
@@ -379,7 +381,7 @@ umma_dec_kernel(const UmmaDecParams p) {
 
             const bool tr_on = (q == 0 && lane == 0);
             if (tr_on) ES_TRACE(2 + g, u, 0);
-            if (p.res2) {   // pull this warp's 16 skip rows (8 KB) towards L2 while the GEMM runs
+            if (RES2) {   // pull this warp's 16 skip rows (8 KB) towards L2 while the GEMM runs
                 const int pr = rbase + (lane >> 1);
                 if (pr < rows_valid) {
                     const float* sp = p.res2 + ((size_t)b * p.T + t0 + pr) * N + (lane & 1) * 64;
@@ -400,13 +402,17 @@ umma_dec_kernel(const UmmaDecParams p) {
             // block-end layers: the 32 skip values of this thread's first row are requested NOW (L2-prefetched
             // above) and land while the tanh / LayerNorm math below runs; the second row's follow while the
             // first row is normalised (keeps the live set at 64 + 32 registers)
-            f32x2 sk[16];
-            const float* s0 = p.res2 + g0 * N + 2 * t4;
-            const float* s1 = p.res2 + g1 * N + 2 * t4;
-            if (p.res2) {
+            // (16-byte loads of 4 consecutive columns -- 8 rows x 64 B per warp-wide load -- un-swapped into
+            // the fragment layout by one quad shuffle per pair when they are consumed, see the stores below)
+            ulonglong2 sk[8];
+            const bool odd = t4 & 1;
+            const int qcol = odd ? 8 + 2 * (t4 - 1) : 2 * t4;   // first of this thread's 4 consecutive columns
+            const float* s0 = p.res2 + g0 * N + qcol;
+            const float* s1 = s0 + 8 * N;
+            if (RES2) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    sk[j] = ok0 ? __ldg(reinterpret_cast<const f32x2*>(s0 + 8 * j)) : 0ull;
+                for (int k = 0; k < 8; ++k)
+                    sk[k] = ok0 ? __ldg(reinterpret_cast<const ulonglong2*>(s0 + 16 * k)) : make_ulonglong2(0ull, 0ull);
             }
             // v[2j + row]: columns 8j + 2*t4, +1 of this thread's row `row`, as one packed fp32 pair
             f32x2 v[32];
@@ -433,15 +439,23 @@ umma_dec_kernel(const UmmaDecParams p) {
             }
             if (p.ln_g) fragment_layernorm2_p(v, par + 128, par + 256, t4, inv_n);   // LayerNorm only with N == 128
             if (tr_on) ES_TRACE(2 + g, u, 3);
-            if (p.res2) {
+            if (RES2) {
+                // thread pairs (t4, t4^1) hold [group 2k: own pair, partner's pair] (even t4) or
+                // [group 2k+1: partner's pair, own pair] (odd t4): swap the foreign halves
+                auto add_skip = [&](int row) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[2 * j] = add2(v[2 * j], sk[j]);
+                    for (int k = 0; k < 8; ++k) {
+                        const f32x2 recv = __shfl_xor_sync(0xffffffffu, odd ? sk[k].x : sk[k].y, 1);
+                        v[4 * k + row] = add2(v[4 * k + row], odd ? recv : sk[k].x);
+                        v[4 * k + 2 + row] = add2(v[4 * k + 2 + row], odd ? sk[k].y : recv);
+                    }
+                };
+                add_skip(0);
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    sk[j] = ok1 ? __ldg(reinterpret_cast<const f32x2*>(s1 + 8 * j)) : 0ull;
+                for (int k = 0; k < 8; ++k)
+                    sk[k] = ok1 ? __ldg(reinterpret_cast<const ulonglong2*>(s1 + 16 * k)) : make_ulonglong2(0ull, 0ull);
                 fragment_layernorm_row_p<0>(v, par + 384, par + 512, t4, inv_n);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[2 * j + 1] = add2(v[2 * j + 1], sk[j]);
+                add_skip(1);
                 fragment_layernorm_row_p<1>(v, par + 384, par + 512, t4, inv_n);
             }
             if (tr_on) ES_TRACE(2 + g, u, 4);
@@ -456,13 +470,26 @@ umma_dec_kernel(const UmmaDecParams p) {
                     for (int j = 0; j < 16; ++j) v[2 * j + 1] = 0ull;
                 }
             }
-            float* y0 = p.Y + g0 * N + 2 * t4;
-            float* y1 = p.Y + g1 * N + 2 * t4;
+            // Stores.  In the fragment layout a warp-wide 8-byte store touches 8 rows x 32 B: 8 L1 wavefronts
+            // for 256 B, and the L1 data pipe (shared with the operand fetches of the tensor core) is the
+            // busiest unit of this kernel.  Neighbouring threads of a quad therefore swap one column pair per
+            // two 8-column groups, so that every thread owns 4 consecutive columns and a warp-wide 16-byte
+            // store covers 8 rows x 64 B: half the wavefronts per byte.
+            float* y0 = p.Y + g0 * N + qcol;
+            float* y1 = y0 + 8 * N;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if (j < nj) {
-                    if (ok0) *reinterpret_cast<f32x2*>(y0 + 8 * j) = v[2 * j];
-                    if (ok1) *reinterpret_cast<f32x2*>(y1 + 8 * j) = v[2 * j + 1];
+            for (int k = 0; k < 8; ++k) {
+                if (2 * k < nj) {                                // nj is even (N % 16 == 0)
+#pragma unroll
+                    for (int row = 0; row < 2; ++row) {
+                        const f32x2 keep = odd ? v[4 * k + 2 + row] : v[4 * k + row];
+                        const f32x2 send = odd ? v[4 * k + row] : v[4 * k + 2 + row];
+                        const f32x2 recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                        ulonglong2 o;
+                        o.x = odd ? recv : keep;
+                        o.y = odd ? keep : recv;
+                        if (row == 0 ? ok0 : ok1) *reinterpret_cast<ulonglong2*>((row == 0 ? y0 : y1) + 16 * k) = o;
+                    }
                 }
             }
             if (tr_on) ES_TRACE(2 + g, u, 5);
@@ -479,14 +506,14 @@ int* g_err_flag = nullptr;
 long long* g_trace = nullptr;
 int g_trace_pick = 0, g_trace_count = 0;   // which launch after es_debug_set_trace is stamped (env ES_TRACE_LAUNCH)
 
-template <int MODE>
+template <int MODE, bool RES2>
 int launch_mode(const UmmaDecParams& p, int grid, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        ES_CUDA(cudaFuncSetAttribute(umma_dec_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        ES_CUDA(cudaFuncSetAttribute(umma_dec_kernel<MODE, RES2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    ES_CUDA(launch_pdl(umma_dec_kernel<MODE>, grid, NTHR, SMEM_BYTES, s, p));
+    ES_CUDA(launch_pdl(umma_dec_kernel<MODE, RES2>, grid, NTHR, SMEM_BYTES, s, p));
     ES_LAUNCH_OK();
     return 0;
 }
@@ -524,9 +551,9 @@ int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, co
     const int n_tiles = B * ((T + TM - 1) / TM);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
     switch (mode) {
-        case MODE_DWCONV: return launch_mode<MODE_DWCONV>(p, grid, s);
-        case MODE_GATHER: return launch_mode<MODE_GATHER>(p, grid, s);
-        default: return launch_mode<MODE_PLAIN>(p, grid, s);
+        case MODE_DWCONV: return res2 ? launch_mode<MODE_DWCONV, true>(p, grid, s) : launch_mode<MODE_DWCONV, false>(p, grid, s);
+        case MODE_GATHER: ES_CHECK(!res2, "gather mode has no skip input"); return launch_mode<MODE_GATHER, false>(p, grid, s);
+        default: ES_CHECK(!res2, "plain mode has no skip input"); return launch_mode<MODE_PLAIN, false>(p, grid, s);
     }
 }
 
