@@ -373,16 +373,26 @@ def run_b200_arm(a):
     layer_bytes = B * T * cfg.dx2 * 4 * (2 * L + nb) / L
     layer_flops = B * T * (2 * cfg.dx2 * cfg.dx2 + 2 * cfg.decoder_kernel_size * cfg.dx2)
     dl = per_kind.get("dec_layer", [])
+    kname = "decoder layer (dwconv k5 + 1x1 GEMM + bias + tanh + LN [+ skip + LN])"
+    if per_kind.get("dec_stack"):
+        # all L depthwise layers + the mel head in ONE persistent launch: the algorithmic bytes are the sum over
+        # its layers (x read + y written per layer, + skip read on block-end layers, + [B*T, 80] mel written)
+        dl = per_kind["dec_stack"]
+        layer_bytes = B * T * 4 * (cfg.dx2 * (2 * L + nb) + cfg.dx2 + cfg.n_mel)
+        layer_flops = L * layer_flops + B * T * 2 * cfg.dx2 * cfg.n_mel
+        kname = f"decoder stack: {L} x (dwconv k5 + 1x1 GEMM + bias + tanh + LN [+ skip + LN]) + mel head, one persistent launch"
     roof = None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.isfile(tpath) and a.variant == "tiny" and B == 256 and T == 768 and not a.simt:
         with open(tpath) as f:
-            traffic = float(json.load(f)["dram_bytes_per_launch"])      # one ncu --set full capture (same shape)
+            tj = json.load(f)
+        if tj.get("kind", "dec_layer") == ("dec_stack" if per_kind.get("dec_stack") else "dec_layer"):
+            traffic = float(tj["dram_bytes_per_launch"])      # one ncu --set full capture (same shape)
     if dl:
         avg_ms = float(np.mean(dl))
         achieved = layer_bytes / (avg_ms * 1e-3) / 1e9
-        roof = {"kernel": "decoder layer (dwconv k5 + 1x1 GEMM + bias + tanh + LN [+ skip + LN])",
+        roof = {"kernel": kname,
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": avg_ms, "launches_timed": len(dl),

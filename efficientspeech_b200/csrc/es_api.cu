@@ -46,6 +46,7 @@ struct es_model {
     es_config_t cfg;
     es_weights_t w;
     int use_tensor_core;
+    int use_dec_stack;      // multi-layer decoder launch (off by default: measured slower; es_model_set_decoder_stack)
     // derived geometry
     int d, C[2], H[2], k[2], hC[2], dx4, dx2, n_layers;
 };
@@ -102,11 +103,13 @@ EncBufs plan_encoder(const es_model* m, Arena& a, int B, int N) {
 
 struct DecBufs {
     float* buf[3];
+    int* ready;          // per-(layer, tile) completion counters of the multi-layer decoder launch
 };
 
 DecBufs plan_decoder(const es_model* m, Arena& a, int B, int T) {
     DecBufs d;
     for (int i = 0; i < 3; ++i) d.buf[i] = a.take<float>((size_t)B * T * m->dx2);
+    d.ready = a.take<int>(umma_dec_stack_ready_ints(B, T, m->n_layers + 1));
     return d;
 }
 
@@ -250,6 +253,7 @@ int es_abi_version(void) { return ES_ABI_VERSION; }
 const char* es_last_error(void) { return es::g_error.c_str(); }
 uint64_t es_launch_count(void) { return es::g_launches.load(); }
 int es_debug_set_trace(void* dev_buf_i64) { es::umma_dec_set_trace(static_cast<long long*>(dev_buf_i64)); return 0; }
+int es_debug_set_decoder_stack_grid(int ctas) { es::umma_dec_stack_set_grid(ctas); return 0; }
 int es_dense_layout(int K, int n_out, int taps, int stride) { return es::dense_layout(K, n_out, taps, stride); }
 int es_check_async_errors(void* stream) { return es::umma_dec_check_errors(static_cast<cudaStream_t>(stream)); }
 
@@ -306,6 +310,7 @@ int es_model_create(const es_config_t* cfg, const es_weights_t* w, es_model_t** 
     m->cfg = *cfg;
     m->w = *w;
     m->use_tensor_core = 1;
+    m->use_dec_stack = 0;
     m->d = cfg->dim;
     m->C[0] = cfg->dim; m->C[1] = 2 * cfg->dim;
     m->H[0] = cfg->head; m->H[1] = 2 * cfg->head;
@@ -323,6 +328,12 @@ void es_model_destroy(es_model_t* m) { delete m; }
 int es_model_set_tensor_core(es_model_t* m, int enable) {
     ES_CHECK(m, "null model");
     m->use_tensor_core = enable ? 1 : 0;
+    return 0;
+}
+
+int es_model_set_decoder_stack(es_model_t* m, int enable) {
+    ES_CHECK(m, "null model");
+    m->use_dec_stack = enable ? 1 : 0;
     return 0;
 }
 
@@ -486,6 +497,42 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
                    float* mel, cudaStream_t s) {
     const int C = m->dx2;
     int layer = 0;
+    // 128-channel decoders: every depthwise layer and the mel head in ONE persistent launch (es_umma_dec.cu)
+    if (m->use_tensor_core && m->use_dec_stack && m->w.mel_w_h16 && m->cfg.n_mel == 80 &&
+        umma_dec_supported(C, m->cfg.decoder_kernel_size, C) && m->n_layers + 1 <= 8) {
+        UmmaDecStage st[8];
+        memset(st, 0, sizeof(st));
+        int n = 0, sk = s_idx;
+        bool ok = true;
+        for (int blk = 0; blk < m->cfg.n_blocks && ok; ++blk) {
+            int in_idx = sk;
+            for (int l = 0; l < m->cfg.block_depth; ++l, ++n) {
+                int out_idx = 0;
+                while (out_idx == sk || out_idx == in_idx) ++out_idx;
+                const es_dec_layer_w_t& w = m->w.dec[n];
+                if (!w.pw_w_h16) { ok = false; break; }
+                const bool last = (l == m->cfg.block_depth - 1);
+                UmmaDecStage& a = st[n];
+                a.X = db.buf[in_idx]; a.Y = db.buf[out_idx]; a.res2 = last ? db.buf[sk] : nullptr;
+                a.dw_w = w.dw_w; a.dw_b = w.dw_b; a.w_h16 = w.pw_w_h16; a.bias = w.pw_b;
+                a.ln_g = w.ln_g; a.ln_b = w.ln_b;
+                a.ln2_g = last ? m->w.blk_ln_g[blk] : nullptr; a.ln2_b = last ? m->w.blk_ln_b[blk] : nullptr;
+                a.N = C; a.act_tanh = 1;
+                in_idx = out_idx;
+            }
+            sk = in_idx;
+        }
+        if (ok) {
+            UmmaDecStage& a = st[n];                 // mel = Linear(skip); padded frames zeroed
+            a.X = db.buf[sk]; a.Y = mel; a.w_h16 = m->w.mel_w_h16; a.bias = m->w.mel_b; a.zero_from = zero_from;
+            a.N = m->cfg.n_mel; a.act_tanh = 0;
+            ++n;
+            int rc;
+            { ProfRange r(ES_K_DEC_STACK, s); rc = launch_umma_dec_stack(B, T, n, st, db.ready, s); }
+            if (rc > 0) return 1;
+            if (rc == 0) return 0;
+        }
+    }
     for (int blk = 0; blk < m->cfg.n_blocks; ++blk) {
         int in_idx = s_idx;
         for (int l = 0; l < m->cfg.block_depth; ++l, ++layer) {

@@ -28,6 +28,18 @@ int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, co
                     const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
                     float* Y, cudaStream_t s);
 int umma_dec_check_errors(cudaStream_t s);
+// one layer of the multi-layer decoder launch (es_umma_dec.cu: umma_dec_stack_kernel)
+struct UmmaDecStage {
+    const float* X; float* Y; const float* res2;
+    const float* dw_w; const float* dw_b;        // dw_w == nullptr: no depthwise stage (mel head)
+    const void* w_h16; const float* bias;
+    const float* ln_g; const float* ln_b; const float* ln2_g; const float* ln2_b;
+    const int* zero_from;
+    int N; int act_tanh;
+};
+int launch_umma_dec_stack(int B, int T, int n_stages, const UmmaDecStage* stages, int* ready, cudaStream_t s);
+size_t umma_dec_stack_ready_ints(int B, int T, int n_stages);
+void umma_dec_stack_set_grid(int ctas);   // tests: run the multi-layer kernel with few CTAs (0: one per SM)
 // wide decoders (dx2 = 256): K-streamed tcgen05 kernel (es_umma_dec256.cu)
 bool umma_dec256_supported(int K, int dw_k, int N, int mode);
 int launch_umma_dec256(int mode, int B, int T, int K, int N, int n_src, const float* X, const int* cum,

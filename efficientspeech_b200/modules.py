@@ -150,6 +150,7 @@ class _Backend:
         self.handle = C.c_void_p(None)
         self.workspace: Optional[torch.Tensor] = None
         self.tensor_core = True
+        self.decoder_stack = False
 
     def __del__(self):
         try:
@@ -165,7 +166,7 @@ class _Backend:
 
     def ensure(self, device: torch.device) -> C.c_void_p:
         params = list(self.owner.parameters())
-        key = (str(device), self.tensor_core) + tuple((p.data_ptr(), p._version) for p in params)
+        key = (str(device), self.tensor_core, self.decoder_stack) + tuple((p.data_ptr(), p._version) for p in params)
         if key == self.key:
             return self.handle
         lib = _cabi.load()
@@ -251,6 +252,7 @@ class _Backend:
         h = C.c_void_p(None)
         _cabi.check(lib.es_model_create(C.byref(cc), C.byref(W), C.byref(h)))
         _cabi.check(lib.es_model_set_tensor_core(h, 1 if self.tensor_core else 0))
+        _cabi.check(lib.es_model_set_decoder_stack(h, 1 if self.decoder_stack else 0))
         self.handle = h
         self.key = key
         return h
@@ -304,6 +306,12 @@ class MelDecoder(nn.Module):
     def set_tensor_core(self, enable: bool) -> None:
         """True (default): tcgen05 split-fp16 decoder layers; False: fp32 SIMT kernels."""
         self._backend.tensor_core = bool(enable)
+
+    def set_decoder_stack(self, enable: bool) -> None:
+        """True: all depthwise layers + mel head as one persistent multi-layer launch when the batch is
+        large enough; False (default): one launch per layer.  Bit-identical results; measured slower on
+        B200 (0.41 ms vs 0.29 ms for tiny, B=256, T=768 -- DESIGN.md section 5.4), kept as an experiment."""
+        self._backend.decoder_stack = bool(enable)
 
     def forward(self, features):
         _require_cuda(features, "features")

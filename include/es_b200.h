@@ -152,6 +152,11 @@ int  es_model_create(const es_config_t* cfg, const es_weights_t* w, es_model_t**
 void es_model_destroy(es_model_t* m);
 /* 0: SIMT fp32 kernels everywhere; 1 (default): tcgen05 split-fp16 decoder layers where supported */
 int  es_model_set_tensor_core(es_model_t* m, int enable);
+/* 1: 128-channel decoders run all depthwise layers + the mel head (MelDecoder.forward,
+ * networks.py:293-302) as ONE persistent multi-layer launch when the batch gives every SM >= 4 tiles;
+ * 0 (default): one launch per layer.  Results are bit-identical either way; the single launch measured
+ * slower on B200 and is kept as an opt-in experiment. */
+int  es_model_set_decoder_stack(es_model_t* m, int enable);
 
 /* Scratch requirement (bytes) of the calls below for a batch of B utterances, N phonemes,
  * T frames (T may be 0 for encoder-only use). */
@@ -223,6 +228,9 @@ int es_check_async_errors(void* stream);
 /* Debug aid: when non-NULL, CTA 0 of every subsequent tcgen05 decoder launch writes clock64() stamps
  * [4 roles][32 tiles][8 events] (int64, device memory) -- tools/trace_decoder.py.  NULL turns it off. */
 int es_debug_set_trace(void* dev_buf_i64);
+/* Tests only: run the multi-layer decoder launch with `ctas` CTAs instead of one per SM (0 restores the
+ * default), so that small problems exercise its cross-CTA layer hand-off. */
+int es_debug_set_decoder_stack_grid(int ctas);
 
 /* Number of kernels the library has launched since process start (bench.py's gpu_launches). */
 uint64_t es_launch_count(void);
@@ -242,6 +250,7 @@ uint64_t es_launch_count(void);
 #define ES_K_DEC_LAYER  8
 #define ES_K_MEL        9
 #define ES_K_POOLMASK   10
+#define ES_K_DEC_STACK  11   /* all depthwise decoder layers + mel head in one persistent launch */
 int es_profile_begin(int max_records);
 int es_profile_end(void);
 int es_profile_collect(int32_t* kinds_host, float* ms_host, int capacity, int* n_out);

@@ -242,3 +242,39 @@ def test_cuda_graph_replay_matches_eager():
     got = npy(g({k: v for k, v in x2.items() if torch.is_tensor(v)})["mel"])
     assert np.array_equal(got, want)
     model.check_async_errors()
+
+
+@pytest.mark.parametrize("B,T,ctas", [(3, 700, 7), (5, 333, 4), (2, 1031, 5), (1, 64 * 12, 3)])
+def test_decoder_stack_matches_per_layer_launches(B, T, ctas):
+    """Multi-layer persistent decoder launch (cross-CTA layer hand-off through global flags) against one
+    launch per layer: bit-identical, and both within the mel bar of the oracle.  The CTA count is forced
+    down so that a small problem gives every CTA >= 4 tiles and neighbouring tiles live on different CTAs."""
+    cfg = VARIANTS["tiny"]
+    sd = init_state_dict(cfg, seed=9)
+    model = cuda_model("tiny", sd)
+    rng = np.random.default_rng(B * 1000 + T)
+    feats = rng.standard_normal((B, T, cfg.dx4)).astype(np.float32)
+    x = torch.from_numpy(feats).to(DEV)
+    lib = _cabi.load()
+    l0 = lib.es_launch_count()
+    try:
+        _cabi.check(lib.es_debug_set_decoder_stack_grid(ctas))
+        model.decoder.set_decoder_stack(True)
+        with torch.no_grad():
+            got_stack = npy(model.decoder(x))
+        n_stack = lib.es_launch_count() - l0
+        model.decoder.set_decoder_stack(False)
+        l0 = lib.es_launch_count()
+        with torch.no_grad():
+            got_layers = npy(model.decoder(x))
+        n_layers = lib.es_launch_count() - l0
+    finally:
+        _cabi.check(lib.es_debug_set_decoder_stack_grid(0))
+        model.decoder.set_decoder_stack(False)
+    torch.cuda.synchronize()
+    es.Phoneme2Mel.check_async_errors()
+    assert n_stack == 2 and n_layers == cfg.n_dec_layers + 2, (n_stack, n_layers)   # proj + stack vs proj + L + mel
+    assert np.array_equal(got_stack, got_layers)
+    S = es_oracle._cast_state(sd, np.float32)
+    want = es_oracle.mel_decoder(feats, S, es_oracle.infer_config(S))
+    assert np.abs(got_stack - want).max() <= TOL_MEL
