@@ -374,20 +374,20 @@ def run_b200_arm(a):
     layer_flops = B * T * (2 * cfg.dx2 * cfg.dx2 + 2 * cfg.decoder_kernel_size * cfg.dx2)
     dl = per_kind.get("dec_layer", [])
     kname = "decoder layer (dwconv k5 + 1x1 GEMM + bias + tanh + LN [+ skip + LN])"
-    if per_kind.get("dec_stack"):
-        # all L depthwise layers + the mel head in ONE persistent launch: the algorithmic bytes are the sum over
-        # its layers (x read + y written per layer, + skip read on block-end layers, + [B*T, 80] mel written)
-        dl = per_kind["dec_stack"]
-        layer_bytes = B * T * 4 * (cfg.dx2 * (2 * L + nb) + cfg.dx2 + cfg.n_mel)
-        layer_flops = L * layer_flops + B * T * 2 * cfg.dx2 * cfg.n_mel
-        kname = f"decoder stack: {L} x (dwconv k5 + 1x1 GEMM + bias + tanh + LN [+ skip + LN]) + mel head, one persistent launch"
+    gather_mode = int(model.decoder._backend.gather_mode)
+    gather_fused = gather_mode == 2 and cfg.dx2 == 128 and not a.simt
+    if gather_fused:
+        # the first block reads its input rows (first layer) and its skip rows (last layer) from the per-phoneme
+        # projection table [B*N+1, dx2] instead of [B,T,dx2] tensors: those two reads are the table, once each
+        layer_bytes = (B * T * cfg.dx2 * 4 * (2 * L + nb - 2) + 2 * (B * N + 1) * cfg.dx2 * 4) / L
+        kname += "; first block gathers input / skip rows from the per-phoneme projection table"
     roof = None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.isfile(tpath) and a.variant == "tiny" and B == 256 and T == 768 and not a.simt:
         with open(tpath) as f:
             tj = json.load(f)
-        if tj.get("kind", "dec_layer") == ("dec_stack" if per_kind.get("dec_stack") else "dec_layer"):
+        if int(tj.get("gather_mode", 0)) == gather_mode:
             traffic = float(tj["dram_bytes_per_launch"])      # one ncu --set full capture (same shape)
     if dl:
         avg_ms = float(np.mean(dl))
@@ -410,7 +410,7 @@ def run_b200_arm(a):
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": int(launches), "roofline": roof,
             "mel_rtf": value * HOP / SR, "kernel_ms_per_step": kernel_ms,
-            "decoder_path": "simt-fp32" if a.simt else "tcgen05-split-fp16",
+            "decoder_path": "simt-fp32" if a.simt else "tcgen05-split-fp16", "gather_mode": gather_mode,
             "launch_mode": "eager" if a.no_graph else "cuda-graph replay (one graph per step)",
             "ms_kernels_per_step_profiled": float(sum(np.sum(v) for v in per_kind.values())) / a.steps}
     if world == 1 and not a.no_cpu_baseline:

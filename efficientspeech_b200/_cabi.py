@@ -8,12 +8,13 @@ from typing import Optional
 
 from . import build as _build
 
-ES_ABI_VERSION = 8
+ES_ABI_VERSION = 9
+ES_GATHER_PER_FRAME, ES_GATHER_MATERIALIZE, ES_GATHER_FUSED = 0, 1, 2
 ES_MAX_ENC_BLOCKS = 2
 ES_MAX_DEC_LAYERS = 24
 ES_MAX_DEC_BLOCKS = 8
 KERNEL_KINDS = ["embed", "enc_gemm", "attention", "fuse", "predictor", "variance", "lenreg",
-                "dec_proj", "dec_layer", "mel", "poolmask", "dec_stack"]
+                "dec_proj", "dec_layer", "mel", "poolmask"]
 
 _fp = C.c_void_p      # device pointers travel as integers
 
@@ -61,16 +62,16 @@ PROTOTYPES = {
     "es_model_create": (_i, [C.POINTER(es_config_t), C.POINTER(es_weights_t), C.POINTER(_vp)]),
     "es_model_destroy": (None, [_vp]),
     "es_model_set_tensor_core": (_i, [_vp, _i]),
-    "es_model_set_decoder_stack": (_i, [_vp, _i]),
+    "es_model_set_decoder_gather": (_i, [_vp, _i]),
     "es_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "es_encoder_forward": (_i, [_vp, _vp, _i, _i] + [_vp] * 12 + [_vp, _sz]),
     "es_length_regulate": (_i, [_vp, _vp, _i, _i, _i] + [_vp] * 6),
+    "es_frame_rows": (_i, [_vp, _vp, _i, _i, _i] + [_vp] * 3),
     "es_decoder_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _sz]),
     "es_decoder_forward_gathered": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz]),
     "es_dense_layout": (_i, [_i, _i, _i, _i]),
     "es_check_async_errors": (_i, [_vp]),
     "es_debug_set_trace": (_i, [_vp]),
-    "es_debug_set_decoder_stack_grid": (_i, [_i]),
     "es_launch_count": (C.c_uint64, []),
     "es_profile_begin": (_i, [_i]),
     "es_profile_end": (_i, []),

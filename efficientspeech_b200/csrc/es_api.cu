@@ -46,7 +46,7 @@ struct es_model {
     es_config_t cfg;
     es_weights_t w;
     int use_tensor_core;
-    int use_dec_stack;      // multi-layer decoder launch (off by default: measured slower; es_model_set_decoder_stack)
+    int gather_mode;        // es_model_set_decoder_gather: ES_GATHER_* (how the length regulator meets the decoder)
     // derived geometry
     int d, C[2], H[2], k[2], hC[2], dx4, dx2, n_layers;
 };
@@ -103,14 +103,26 @@ EncBufs plan_encoder(const es_model* m, Arena& a, int B, int N) {
 
 struct DecBufs {
     float* buf[3];
-    int* ready;          // per-(layer, tile) completion counters of the multi-layer decoder launch
+    float* P;            // gathered entry (N > 0): per-phoneme projection table [B*N + 1][dx2], last row = padded frames
+    int* src;            //                         frame -> table row map [B*T]
+    int pad_id;          //                         = B*N, the table row of the zero-padded frames
 };
 
-DecBufs plan_decoder(const es_model* m, Arena& a, int B, int T) {
+DecBufs plan_decoder(const es_model* m, Arena& a, int B, int N, int T) {
     DecBufs d;
     for (int i = 0; i < 3; ++i) d.buf[i] = a.take<float>((size_t)B * T * m->dx2);
-    d.ready = a.take<int>(umma_dec_stack_ready_ints(B, T, m->n_layers + 1));
+    d.P = nullptr; d.src = nullptr; d.pad_id = B * N;
+    if (N > 0) {
+        d.P = a.take<float>(((size_t)B * N + 1) * m->dx2);
+        d.src = a.take<int>((size_t)B * T);
+    }
     return d;
+}
+
+size_t decoder_workspace_bytes(const es_model* m, int B, int N, int T) {
+    Arena a(nullptr);
+    plan_decoder(m, a, B, N, T);
+    return align_up(a.off, 256) + 256;
 }
 
 RowGemmParams base_params(int B, int n_in, int n_out, int K, int Nout, const float* A, int lda,
@@ -244,6 +256,8 @@ int predictors(const es_model* m, int B, int N, const float* fused, float* const
 
 int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, const int* zero_from,
                    float* mel, cudaStream_t s);
+int project_rows(const es_model* m, int rows, const float* in, float* out, cudaStream_t s);
+bool decoder_all_umma128(const es_model* m);
 
 }  // namespace
 
@@ -253,7 +267,6 @@ int es_abi_version(void) { return ES_ABI_VERSION; }
 const char* es_last_error(void) { return es::g_error.c_str(); }
 uint64_t es_launch_count(void) { return es::g_launches.load(); }
 int es_debug_set_trace(void* dev_buf_i64) { es::umma_dec_set_trace(static_cast<long long*>(dev_buf_i64)); return 0; }
-int es_debug_set_decoder_stack_grid(int ctas) { es::umma_dec_stack_set_grid(ctas); return 0; }
 int es_dense_layout(int K, int n_out, int taps, int stride) { return es::dense_layout(K, n_out, taps, stride); }
 int es_check_async_errors(void* stream) { return es::umma_dec_check_errors(static_cast<cudaStream_t>(stream)); }
 
@@ -310,7 +323,7 @@ int es_model_create(const es_config_t* cfg, const es_weights_t* w, es_model_t** 
     m->cfg = *cfg;
     m->w = *w;
     m->use_tensor_core = 1;
-    m->use_dec_stack = 0;
+    m->gather_mode = ES_GATHER_FUSED;
     m->d = cfg->dim;
     m->C[0] = cfg->dim; m->C[1] = 2 * cfg->dim;
     m->H[0] = cfg->head; m->H[1] = 2 * cfg->head;
@@ -331,9 +344,10 @@ int es_model_set_tensor_core(es_model_t* m, int enable) {
     return 0;
 }
 
-int es_model_set_decoder_stack(es_model_t* m, int enable) {
+int es_model_set_decoder_gather(es_model_t* m, int mode) {
     ES_CHECK(m, "null model");
-    m->use_dec_stack = enable ? 1 : 0;
+    ES_CHECK(mode == ES_GATHER_PER_FRAME || mode == ES_GATHER_MATERIALIZE || mode == ES_GATHER_FUSED, "unknown gather mode");
+    m->gather_mode = mode;
     return 0;
 }
 
@@ -341,7 +355,7 @@ size_t es_workspace_bytes(const es_model_t* m, int B, int N, int T) {
     if (!m || B <= 0) return 0;
     Arena a(nullptr);
     if (N > 0) plan_encoder(m, a, B, N);
-    if (T > 0) plan_decoder(m, a, B, T);
+    if (T > 0) plan_decoder(m, a, B, N, T);
     return align_up(a.off, 256) + 256;
 }
 
@@ -381,24 +395,30 @@ int es_encoder_forward(es_model_t* m, void* stream, int B, int N,
     if (encoder_block(m, 1, B, n1, e.xm1, mask1, e, e.feat1, s)) return 1;
     // fuse (networks.py:189-219)
     bool fused_done = false;
-    if (m->use_tensor_core && m->w.fuse_u_h16 && m->w.fuse_a0_h16 && d % 128 == 0) {
+    if (m->use_tensor_core && m->w.fuse_u_h16 && m->w.fuse_a0_h16) {
         // tensor-core form: U = feat1 [G_0|..|G_{k-1}] + [g_0|..|g_{k-1}] for every half-rate position (e.qkv is
-        // free by now), then fused = mask(c + A0 feat0 + the stride-2 scatter of U) in the second GEMM's epilogue
+        // free by now), then fused = mask(c + A0 feat0 + the stride-2 scatter of U) in the second GEMM's epilogue.
+        // d % 128 == 0: streamed-weight kernel (es_umma_wide.cu); d <= 64: resident-weight row GEMM (es_umma_enc.cu).
+        // The packed images follow the same rule (modules.py).
         const int k = m->k[0];
+        const bool wide = d % 128 == 0;
+        const bool narrow = !wide && dense_layout(2 * d, k * d, 1, 1) == 1 && dense_layout(d, d, 1, 1) == 1;
         float* U = e.qkv;
-        RowGemmParams p = base_params(B, n1, n1, 2 * d, k * d, e.feat1, 2 * d, nullptr, U, k * d);
-        p.bias = m->w.fuse_gb;
-        int rc;
-        { ProfRange r(ES_K_FUSE, s); rc = launch_umma_wide(p, m->w.fuse_u_h16, s, 128); }
-        if (rc > 0) return 1;
-        if (rc == 0) {
-            p = base_params(B, N, N, d, d, e.feat0, d, nullptr, e.fused, d);
-            p.bias = m->w.fuse_c; p.row_mask = phoneme_mask;
-            p.fuse_u = U; p.fuse_k = k; p.fuse_n1 = n1; p.fuse_ld = k * d;
-            ProfRange r(ES_K_FUSE, s);
-            rc = launch_umma_wide(p, m->w.fuse_a0_h16, s, 128);
-            if (rc != 0) { ES_CHECK(rc < 0, "fuse GEMM failed"); ES_CHECK(false, "fuse epilogue outside the streamed kernel's envelope"); }
-            fused_done = true;
+        if (wide || narrow) {
+            RowGemmParams p = base_params(B, n1, n1, 2 * d, k * d, e.feat1, 2 * d, nullptr, U, k * d);
+            p.bias = m->w.fuse_gb;
+            int rc;
+            { ProfRange r(ES_K_FUSE, s); rc = wide ? launch_umma_wide(p, m->w.fuse_u_h16, s, 128) : launch_umma_rowgemm(p, m->w.fuse_u_h16, s); }
+            if (rc > 0) return 1;
+            if (rc == 0) {
+                p = base_params(B, N, N, d, d, e.feat0, d, nullptr, e.fused, d);
+                p.bias = m->w.fuse_c; p.row_mask = phoneme_mask;
+                p.fuse_u = U; p.fuse_k = k; p.fuse_n1 = n1; p.fuse_ld = k * d;
+                ProfRange r(ES_K_FUSE, s);
+                rc = wide ? launch_umma_wide(p, m->w.fuse_a0_h16, s, 128) : launch_umma_rowgemm(p, m->w.fuse_a0_h16, s);
+                if (rc != 0) { ES_CHECK(rc < 0, "fuse GEMM failed"); ES_CHECK(false, "fuse epilogue outside the tensor-core kernels' envelope"); }
+                fused_done = true;
+            }
         }
     }
     if (!fused_done) { ProfRange r(ES_K_FUSE, s);
@@ -424,15 +444,24 @@ int es_length_regulate(es_model_t* m, void* stream, int B, int N, int T,
                                   static_cast<cudaStream_t>(stream));
 }
 
+int es_frame_rows(es_model_t* m, void* stream, int B, int N, int T,
+                  const int32_t* dur_cum, const int32_t* mel_len, int32_t* rows) {
+    ES_CHECK(m, "null model");
+    ES_CHECK(dur_cum && mel_len && rows, "null tensor");
+    ProfRange r(ES_K_LENREG, static_cast<cudaStream_t>(stream));
+    return launch_frame_source(dur_cum, mel_len, rows, B, N, T, nullptr, nullptr, nullptr, 0, nullptr,
+                               static_cast<cudaStream_t>(stream));
+}
+
 int es_decoder_forward(es_model_t* m, void* stream, int B, int T, const float* features, float* mel,
                        void* workspace, size_t workspace_bytes) {
     ES_CHECK(m, "null model");
     ES_CHECK(B >= 1 && B <= 65535 && T >= 1, "need 1 <= B <= 65535 and T >= 1 frames");
     ES_CHECK(features && mel, "null tensor");
-    ES_CHECK(workspace && workspace_bytes >= es_workspace_bytes(m, B, 0, T), "workspace too small");
+    ES_CHECK(workspace && workspace_bytes >= decoder_workspace_bytes(m, B, 0, T), "workspace too small");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Arena a(reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256)));
-    DecBufs db = plan_decoder(m, a, B, T);
+    DecBufs db = plan_decoder(m, a, B, 0, T);
     // skip = LN(tanh(Linear(features)))                                           networks.py:292
     if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx4 == 128 &&
         umma_dec_supported(m->dx2, m->cfg.decoder_kernel_size, m->dx2)) {
@@ -461,11 +490,26 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
     ES_CHECK(m, "null model");
     ES_CHECK(B >= 1 && B <= 65535 && N >= 1 && T >= 1, "need 1 <= B <= 65535, N >= 1 and T >= 1 frames");
     ES_CHECK(fused4 && dur_cum && mel_len && mel, "null tensor");
-    ES_CHECK(workspace && workspace_bytes >= es_workspace_bytes(m, B, 0, T), "workspace too small");
+    const bool commute = m->gather_mode != ES_GATHER_PER_FRAME;
+    ES_CHECK(workspace && workspace_bytes >= decoder_workspace_bytes(m, B, commute ? N : 0, T), "workspace too small");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Arena a(reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256)));
-    DecBufs db = plan_decoder(m, a, B, T);
-    // length-regulator gather fused into the projection's operand load (networks.py:228-258, :292)
+    DecBufs db = plan_decoder(m, a, B, commute ? N : 0, T);
+    if (commute) {
+        // The projection is row-wise and the length regulator is a row gather: project once per PHONEME
+        // (B*N rows), expand through the frame -> row map (es_gather.cu).  networks.py:228-258, :292
+        const int R = B * N;
+        { ProfRange r(ES_K_DEC_PROJ, s); if (project_rows(m, R, fused4, db.P, s)) return 1; }
+        { ProfRange r(ES_K_LENREG, s);
+          if (launch_frame_source(dur_cum, mel_len, db.src, B, N, T, m->w.dproj_b, m->w.dproj_ln_g, m->w.dproj_ln_b,
+                                  m->dx2, db.P + (size_t)R * m->dx2, s)) return 1; }
+        if (m->gather_mode == ES_GATHER_FUSED && decoder_all_umma128(m))
+            // the first block reads its input and skip rows straight from the table: [B,T,dx2] is never materialised
+            return decoder_layers(m, B, T, db, -1, zero_padded_frames ? mel_len : nullptr, mel, s);
+        { ProfRange r(ES_K_LENREG, s); if (launch_gather_rows(db.P, db.src, db.buf[0], (long long)B * T, m->dx2, s)) return 1; }
+        return decoder_layers(m, B, T, db, 0, zero_padded_frames ? mel_len : nullptr, mel, s);
+    }
+    // legacy form: length-regulator gather fused into the projection's operand load, one GEMM row per FRAME
     if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx4 == 128 &&
         umma_dec_supported(m->dx2, m->cfg.decoder_kernel_size, m->dx2)) {
         { ProfRange r(ES_K_DEC_PROJ, s);
@@ -492,47 +536,35 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
 
 namespace {
 
-// Decoder blocks + mel head (networks.py:293-302, :424-427).  db.buf[s_idx] holds `skip`.
+// every depthwise layer runs on the 128-channel tcgen05 kernel (which has the gathered-row variant)
+bool decoder_all_umma128(const es_model* m) {
+    if (!m->use_tensor_core || !umma_dec_supported(m->dx2, m->cfg.decoder_kernel_size, m->dx2)) return false;
+    for (int l = 0; l < m->n_layers; ++l) if (!m->w.dec[l].pw_w_h16) return false;
+    return true;
+}
+
+// out[r] = LN(tanh(Linear(in[r]))) for `rows` independent rows (MelDecoder.proj, networks.py:292)
+int project_rows(const es_model* m, int rows, const float* in, float* out, cudaStream_t s) {
+    if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx4 == 128 &&
+        umma_dec_supported(m->dx2, m->cfg.decoder_kernel_size, m->dx2))
+        return launch_umma_dec(2, 1, rows, m->dx2, 0, in, nullptr, nullptr, nullptr, nullptr, m->w.dproj_w_h16,
+                               m->w.dproj_b, 1, m->w.dproj_ln_g, m->w.dproj_ln_b, nullptr, nullptr, nullptr,
+                               nullptr, out, s);
+    if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx2 == 256 && umma_dec256_supported(m->dx4, 5, 256, 2))
+        return launch_umma_dec256(2, 1, rows, m->dx4, m->dx2, 0, in, nullptr, nullptr, nullptr, nullptr, m->w.dproj_w_h16,
+                                  m->w.dproj_b, 1, m->w.dproj_ln_g, m->w.dproj_ln_b, nullptr, nullptr, nullptr,
+                                  nullptr, out, s);
+    RowGemmParams p = base_params(1, rows, rows, m->dx4, m->dx2, in, m->dx4, m->w.dproj_w, out, m->dx2);
+    p.bias = m->w.dproj_b; p.act1 = ACT_TANH; p.ln_g = m->w.dproj_ln_g; p.ln_b = m->w.dproj_ln_b;
+    return launch_rowgemm(p, s);
+}
+
+// Decoder blocks + mel head (networks.py:293-302, :424-427).  db.buf[s_idx] holds `skip`; s_idx < 0: `skip` is
+// virtual -- row db.src[b*T + t] of the table db.P -- and the first block gathers it (decoder_all_umma128 only).
 int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, const int* zero_from,
                    float* mel, cudaStream_t s) {
     const int C = m->dx2;
     int layer = 0;
-    // 128-channel decoders: every depthwise layer and the mel head in ONE persistent launch (es_umma_dec.cu)
-    if (m->use_tensor_core && m->use_dec_stack && m->w.mel_w_h16 && m->cfg.n_mel == 80 &&
-        umma_dec_supported(C, m->cfg.decoder_kernel_size, C) && m->n_layers + 1 <= 8) {
-        UmmaDecStage st[8];
-        memset(st, 0, sizeof(st));
-        int n = 0, sk = s_idx;
-        bool ok = true;
-        for (int blk = 0; blk < m->cfg.n_blocks && ok; ++blk) {
-            int in_idx = sk;
-            for (int l = 0; l < m->cfg.block_depth; ++l, ++n) {
-                int out_idx = 0;
-                while (out_idx == sk || out_idx == in_idx) ++out_idx;
-                const es_dec_layer_w_t& w = m->w.dec[n];
-                if (!w.pw_w_h16) { ok = false; break; }
-                const bool last = (l == m->cfg.block_depth - 1);
-                UmmaDecStage& a = st[n];
-                a.X = db.buf[in_idx]; a.Y = db.buf[out_idx]; a.res2 = last ? db.buf[sk] : nullptr;
-                a.dw_w = w.dw_w; a.dw_b = w.dw_b; a.w_h16 = w.pw_w_h16; a.bias = w.pw_b;
-                a.ln_g = w.ln_g; a.ln_b = w.ln_b;
-                a.ln2_g = last ? m->w.blk_ln_g[blk] : nullptr; a.ln2_b = last ? m->w.blk_ln_b[blk] : nullptr;
-                a.N = C; a.act_tanh = 1;
-                in_idx = out_idx;
-            }
-            sk = in_idx;
-        }
-        if (ok) {
-            UmmaDecStage& a = st[n];                 // mel = Linear(skip); padded frames zeroed
-            a.X = db.buf[sk]; a.Y = mel; a.w_h16 = m->w.mel_w_h16; a.bias = m->w.mel_b; a.zero_from = zero_from;
-            a.N = m->cfg.n_mel; a.act_tanh = 0;
-            ++n;
-            int rc;
-            { ProfRange r(ES_K_DEC_STACK, s); rc = launch_umma_dec_stack(B, T, n, st, db.ready, s); }
-            if (rc > 0) return 1;
-            if (rc == 0) return 0;
-        }
-    }
     for (int blk = 0; blk < m->cfg.n_blocks; ++blk) {
         int in_idx = s_idx;
         for (int l = 0; l < m->cfg.block_depth; ++l, ++layer) {
@@ -540,6 +572,18 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
             while (out_idx == s_idx || out_idx == in_idx) ++out_idx;
             const es_dec_layer_w_t& w = m->w.dec[layer];
             const bool last = (l == m->cfg.block_depth - 1);
+            if (in_idx < 0 || (last && s_idx < 0)) {
+                // first block of the gathered entry: input and / or skip rows come from the projection table
+                ES_CHECK(db.P && db.src && w.pw_w_h16 && umma_dec_supported(C, m->cfg.decoder_kernel_size, C),
+                         "virtual skip needs the 128-channel tcgen05 layer kernel");
+                ProfRange r(ES_K_DEC_LAYER, s);
+                if (launch_umma_dec_gathered(B, T, C, in_idx < 0 ? db.P : db.buf[in_idx], w.dw_w, w.dw_b, w.pw_w_h16, w.pw_b, 1,
+                                             w.ln_g, w.ln_b, last ? (s_idx < 0 ? db.P : db.buf[s_idx]) : nullptr,
+                                             last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
+                                             db.src, db.pad_id, in_idx < 0, last && s_idx < 0, db.buf[out_idx], s)) return 1;
+                in_idx = out_idx;
+                continue;
+            }
             if (m->use_tensor_core && w.pw_w_h16 && umma_dec_supported(C, m->cfg.decoder_kernel_size, C)) {
                 ProfRange r(ES_K_DEC_LAYER, s);
                 if (launch_umma_dec(0, B, T, C, 0, db.buf[in_idx], nullptr, nullptr, w.dw_w, w.dw_b, w.pw_w_h16,

@@ -20,6 +20,12 @@ int launch_variance_scan(const float* fused, const float* dur_feat, const float*
 int launch_length_regulate(const float* fused4, const int32_t* cum, const uint8_t* pmask, float* feats,
                            uint8_t* fmask, int32_t* src, int B, int N, int T, int C, cudaStream_t s);
 
+// length regulator as an index map + row gather (es_gather.cu)
+int launch_frame_source(const int32_t* cum, const int32_t* valid_len, int32_t* src, int B, int N, int T,
+                        const float* bias, const float* ln_g, const float* ln_b, int C, float* pad_row,
+                        cudaStream_t s);
+int launch_gather_rows(const float* P, const int32_t* src, float* Y, long long rows, int C, cudaStream_t s);
+
 // tcgen05 decoder kernel (es_umma_dec.cu)
 bool umma_dec_supported(int C, int dw_k, int N);
 int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, const int* cum,
@@ -27,19 +33,14 @@ int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, co
                     const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
                     const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
                     float* Y, cudaStream_t s);
+// depthwise layer whose input rows (gather_x) and / or skip rows (gather_res2) are rows of a table addressed
+// through the frame -> row map `src` [B*T] (launch_frame_source): X / res2 then point at the table, whose row
+// `pad_id` (the largest index) serves the zero-padded frames
+int launch_umma_dec_gathered(int B, int T, int N, const float* X, const float* dw_w, const float* dw_b,
+                             const void* w_h16, const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
+                             const float* res2, const float* ln2_g, const float* ln2_b, const int* src, int pad_id,
+                             int gather_x, int gather_res2, float* Y, cudaStream_t s);
 int umma_dec_check_errors(cudaStream_t s);
-// one layer of the multi-layer decoder launch (es_umma_dec.cu: umma_dec_stack_kernel)
-struct UmmaDecStage {
-    const float* X; float* Y; const float* res2;
-    const float* dw_w; const float* dw_b;        // dw_w == nullptr: no depthwise stage (mel head)
-    const void* w_h16; const float* bias;
-    const float* ln_g; const float* ln_b; const float* ln2_g; const float* ln2_b;
-    const int* zero_from;
-    int N; int act_tanh;
-};
-int launch_umma_dec_stack(int B, int T, int n_stages, const UmmaDecStage* stages, int* ready, cudaStream_t s);
-size_t umma_dec_stack_ready_ints(int B, int T, int n_stages);
-void umma_dec_stack_set_grid(int ctas);   // tests: run the multi-layer kernel with few CTAs (0: one per SM)
 // wide decoders (dx2 = 256): K-streamed tcgen05 kernel (es_umma_dec256.cu)
 bool umma_dec256_supported(int K, int dw_k, int N, int mode);
 int launch_umma_dec256(int mode, int B, int T, int K, int N, int n_src, const float* X, const int* cum,

@@ -64,7 +64,9 @@ constexpr uint32_t W_PLANE_MAX = 128 * CK * 2;                // 32768
 constexpr uint32_t OFF_PAR = OFF_W + 2 * W_PLANE_MAX;         // bias, ln g/b, ln2 g/b: 5 x 128 floats
 constexpr uint32_t OFF_DW = OFF_PAR + 5 * 128 * 4;            // depthwise taps + bias: 6 x 128 floats
 constexpr uint32_t OFF_SRC = OFF_DW + 6 * 128 * 4;            // gather sources: 64 ints
-constexpr uint32_t OFF_BAR = OFF_SRC + TM * 4;                // 12 mbarriers + tmem base
+constexpr int MAP_LD = 72;                                    // row-map stride per ring slot (68 tile rows)
+constexpr uint32_t OFF_MAP = OFF_SRC + TM * 4;                // gathered x tiles: tile row -> staged row, per ring slot
+constexpr uint32_t OFF_BAR = OFF_MAP + NSTAGE * MAP_LD * 4;   // 12 mbarriers + tmem base
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -84,6 +86,8 @@ struct UmmaDecParams {
     const float* ln_g; const float* ln_b;       // LayerNorm over N, or null
     const float* res2; const float* ln2_g; const float* ln2_b;   // out = LN2(out + res2), or null
     const int* zero_from;        // [B] rows t >= zero_from[b] zeroed, or null
+    const int* src;              // GX / GS kernels: frame -> table row map [B*T] (es_gather.cu); X / res2 is the table
+    int pad_id;                  // GX: table row of the zero-padded frames (the largest row index)
     float* Y;                    // [B,T,N]
     int* err;                    // device error flag (mbarrier timeout)
     long long* trace;            // debug: per-role clock64 stamps of CTA 0 ([4 roles][32 tiles][8 events]) or null
@@ -119,15 +123,13 @@ __device__ __forceinline__ uint32_t a_off(int row, int lane) {
 // Epilogue math of one warp's 16 x 128 accumulator slab, in registers (fragment layout of
 // tcgen05.ld.16x256b: r[4j + 2*row + b] = column 8j + 2*t4 + b of this thread's row `row`):
 // bias -> tanh -> LayerNorm [-> + skip -> LayerNorm] [-> zero padded frames] -> 16-byte stores.
-// `res0` / `y0` point at this thread's first row (row 1 is 8 rows further); zero_rows: rows >= it are zeroed.
-// LD_CG: the skip tensor was written earlier by THIS launch (multi-layer kernel) -> L2-coherent loads.
-template <bool RES2, bool LD_CG = false, typename Stamp>
+// `res0` / `res1` point at the skip rows of this thread's two rows, `yrow0` at its first output row (the second
+// is 8 rows further); zero_rows: rows >= it are zeroed.
+template <bool RES2, typename Stamp>
 __device__ __forceinline__ void epilogue_math(uint32_t (&r)[64], const float* par, int N, int nj, float inv_n,
-                                              bool act_tanh, bool has_ln, const float* res0, float* yrow0,
-                                              bool ok0, bool ok1, int zero_rows, int t4, Stamp stamp) {
-    auto ld_skip = [](const float* ptr) {
-        return LD_CG ? __ldcg(reinterpret_cast<const ulonglong2*>(ptr)) : __ldg(reinterpret_cast<const ulonglong2*>(ptr));
-    };
+                                              bool act_tanh, bool has_ln, const float* res0, const float* res1,
+                                              float* yrow0, bool ok0, bool ok1, int zero_rows, int t4, Stamp stamp) {
+    auto ld_skip = [](const float* ptr) { return __ldg(reinterpret_cast<const ulonglong2*>(ptr)); };
     // block-end layers: the 32 skip values of this thread's first row are requested NOW (L2-prefetched
     // above) and land while the tanh / LayerNorm math below runs; the second row's follow while the
     // first row is normalised (keeps the live set at 64 + 32 registers)
@@ -137,7 +139,7 @@ __device__ __forceinline__ void epilogue_math(uint32_t (&r)[64], const float* pa
     const bool odd = t4 & 1;
     const int qcol = odd ? 8 + 2 * (t4 - 1) : 2 * t4;   // first of this thread's 4 consecutive columns
     const float* s0 = res0 + qcol;
-    const float* s1 = s0 + 8 * N;
+    const float* s1 = res1 + qcol;
     if (RES2) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -222,9 +224,19 @@ __device__ __forceinline__ void epilogue_math(uint32_t (&r)[64], const float* pa
 
 // RES2: block-end layer (skip add + second LayerNorm) -- a compile-time switch, so that the plain layers do not
 // reserve the 32 skip registers and ptxas can hoist the parameter loads of the epilogue instead
-template <int MODE, bool RES2>
+// GX / GS (DWCONV only): the input rows (GX) and / or the skip rows (GS) are rows of an L2-resident table
+// addressed through the frame -> row map p.src -- the length regulator fused into the first decoder block.
+// GX: the rows of one utterance are nondecreasing in t and CONTIGUOUS in the table, so the distinct rows a
+// tile needs arrive as ONE bulk copy (~T/N times fewer bytes than the tile), plus the padded-frame row; the
+// issue warp writes a tile-row -> staged-row map next to it and the producers read their conv window through
+// that map (rows outside the utterance map to -1 = zeros, so no zero fill either).  Runs of zero-duration
+// phonemes that would overflow the slot fall back to one 512-byte copy per frame.  The row indices are
+// fetched one iteration ahead.  GS: the epilogue reads its skip rows through the map.
+template <int MODE, bool RES2, bool GX = false, bool GS = false>
 __global__ void __launch_bounds__(NTHR, 1)
 umma_dec_kernel(const UmmaDecParams p) {
+    static_assert(!(GX || GS) || MODE == MODE_DWCONV, "gathered rows: depthwise layers only");
+    static_assert(!GS || RES2, "gathered skip rows need the block-end epilogue");
     constexpr int HALO = (MODE == MODE_DWCONV) ? DWK / 2 : 0;
     constexpr int XROWS = TM + 2 * HALO;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -232,6 +244,7 @@ umma_dec_kernel(const UmmaDecParams p) {
     uint8_t* a_hi = smem + OFF_A;
     float* par = reinterpret_cast<float*>(smem + OFF_PAR);
     int* srcs = reinterpret_cast<int*>(smem + OFF_SRC);
+    int* xmap = reinterpret_cast<int*>(smem + OFF_MAP);
     const uint32_t bar_x = smem_u32(smem + OFF_BAR);          // [3] x tile landed
     const uint32_t bar_w = bar_x + 24;                        //     weights landed
     const uint32_t bar_mma = bar_x + 32;                      // [2] accumulator g full / A operand free
@@ -303,10 +316,66 @@ umma_dec_kernel(const UmmaDecParams p) {
         const uint64_t db_step = (uint64_t)((2u * lbo_b) >> 4);
         const bool elected = elect_one();                    // one lane issues on behalf of the CTA; the
                                                              // control flow stays warp-uniform
+        // gathered x: lane l owns frames lo + l, lo + l + 32, lo + l + 64 of a tile (<= 68 frames)
+        constexpr bool gx = GX;
+        int sx[3] = {-1, -1, -1};
+        auto load_src = [&](int tile) {
+            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
+            const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
+            const int* sp = p.src + (size_t)b * p.T;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int r = lo + lane + 32 * k;
+                sx[k] = r < hi ? __ldg(sp + r) : -1;
+            }
+        };
+        auto issue_rows = [&](int tile, int slot) {
+            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
+            const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
+            const int head = lo - (t0 - HALO), nfr = hi - lo;   // tile rows [head, head + nfr) are frames lo..hi-1
+            const int first = __shfl_sync(0xffffffffu, sx[0], 0);
+            int mx = -1;
+            bool anypad = false;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (sx[k] == p.pad_id) anypad = true;
+                else mx = max(mx, sx[k]);                    // -1 (no frame) never wins
+            }
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            const int has_pad = __any_sync(0xffffffffu, anypad) ? 1 : 0;
+            const int nr = mx >= 0 ? mx - first + 1 : 0;     // distinct table rows [first, mx]; padded frames are the tail
+            const bool compact = nr + has_pad <= XROWS;
+            int* mp = xmap + slot * MAP_LD;
+            for (int r = lane; r < XROWS; r += 32)
+                if (r < head || r >= head + nfr) mp[r] = -1;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int r = head + lane + 32 * k;
+                if (sx[k] >= 0) mp[r] = compact ? (sx[k] == p.pad_id ? nr : sx[k] - first) : r;
+            }
+            __syncwarp();                                    // the map is written before the barrier can complete
+            const uint32_t dst = smem_u32(smem + OFF_XS) + (uint32_t)slot * X_STAGE;
+            if (compact) {
+                if (elected) {
+                    mbar_arrive_expect_tx(bar_x + 8 * slot, (uint32_t)(nr + has_pad) * CK * 4u);
+                    if (nr) bulk_g2s(dst, p.X + (size_t)first * CK, (uint32_t)nr * CK * 4u, bar_x + 8 * slot);
+                    if (has_pad) bulk_g2s(dst + (uint32_t)nr * CK * 4u, p.X + (size_t)p.pad_id * CK, CK * 4u, bar_x + 8 * slot);
+                }
+            } else {
+                if (elected) mbar_arrive_expect_tx(bar_x + 8 * slot, (uint32_t)nfr * CK * 4u);
+                __syncwarp();                                // the byte count is registered before any copy can complete
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (sx[k] >= 0) bulk_g2s(dst + (uint32_t)(head + lane + 32 * k) * CK * 4u, p.X + (size_t)sx[k] * CK, CK * 4u, bar_x + 8 * slot);
+            }
+        };
         if (MODE != MODE_GATHER) {
             for (int k = 0; k < NSTAGE; ++k) {
                 const int tile = blockIdx.x + k * gridDim.x;
-                if (tile < n_tiles && elected) issue_x(tile, k);
+                if (tile < n_tiles) {
+                    if (gx) { load_src(tile); issue_rows(tile, k); }
+                    else if (elected) issue_x(tile, k);
+                }
             }
         }
         if (!mbar_wait(bar_w, 0)) failed = true;
@@ -314,6 +383,8 @@ umma_dec_kernel(const UmmaDecParams p) {
         int i = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
             const int g = i & 1, u = i >> 1, slot = i % NSTAGE;
+            const int next = tile + NSTAGE * (int)gridDim.x;
+            if (gx && next < n_tiles) load_src(next);                    // row indices land while this tile's GEMM is set up
             if (elected) ES_TRACE(0, i, 0);
             if (!mbar_wait(bar_aready, i & 1)) failed = true;            // A operand of tile i written
             if (elected) ES_TRACE(0, i, 1);
@@ -335,9 +406,10 @@ umma_dec_kernel(const UmmaDecParams p) {
             if (elected) { mma_commit(bar_mma + 8 * g); ES_TRACE(0, i, 3); }
             // ring slot of tile i was released by the producers before they signalled bar_aready:
             // the tile three steps ahead starts streaming into it
-            if (MODE != MODE_GATHER && tile + NSTAGE * (int)gridDim.x < n_tiles) {
+            if (MODE != MODE_GATHER && next < n_tiles) {
                 if (!mbar_wait(bar_xfree + 8 * slot, (i / NSTAGE) & 1)) failed = true;
-                if (elected) issue_x(tile + NSTAGE * gridDim.x, slot);
+                if (gx) issue_rows(next, slot);
+                else if (elected) issue_x(next, slot);
             }
             if (elected) ES_TRACE(0, i, 4);
             __syncwarp();
@@ -355,7 +427,10 @@ umma_dec_kernel(const UmmaDecParams p) {
             const bool tr_on = (pw == 0 && lane == 0);
             if (tr_on) ES_TRACE(1, i, 0);
 
-            if (MODE != MODE_GATHER) {
+            if (GX) {
+                if (!mbar_wait(bar_x + 8 * slot, (i / NSTAGE) & 1)) failed = true;   // staged rows + row map
+                if (tr_on) ES_TRACE(1, i, 1);
+            } else if (MODE != MODE_GATHER) {
                 // zero the halo / tail rows the bulk copy does not cover (utterance boundaries only)
                 const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
                 const int head = lo - (t0 - HALO), tail0 = hi - (t0 - HALO);
@@ -427,8 +502,17 @@ umma_dec_kernel(const UmmaDecParams p) {
                         bdw = dwp[DWK * 32 + lane];
                     }
                     ulonglong2 win[8 + 2 * HALO];
+                    if (GX) {
+                        const int* mp = xmap + slot * MAP_LD + r0;
 #pragma unroll
-                    for (int k = 0; k < 8 + 2 * HALO; ++k) win[k] = reinterpret_cast<const ulonglong2*>(Xs + (r0 + k) * CK)[lane];
+                        for (int k = 0; k < 8 + 2 * HALO; ++k) {
+                            const int mrow = mp[k];
+                            win[k] = mrow >= 0 ? reinterpret_cast<const ulonglong2*>(Xs + mrow * CK)[lane] : make_ulonglong2(0ull, 0ull);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8 + 2 * HALO; ++k) win[k] = reinterpret_cast<const ulonglong2*>(Xs + (r0 + k) * CK)[lane];
+                    }
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
                         ulonglong2 o;
@@ -481,17 +565,29 @@ umma_dec_kernel(const UmmaDecParams p) {
             const int rows_valid = min(TM, p.T - t0);
             const int u = i >> 1;
             const int row0 = rbase + tr, row1 = row0 + 8;
-            const size_t g0 = (size_t)b * p.T + t0 + row0, g1 = g0 + 8;
+            const size_t g0 = (size_t)b * p.T + t0 + row0;
             const bool ok0 = row0 < rows_valid, ok1 = row1 < rows_valid;
 
             const bool tr_on = (q == 0 && lane == 0);
             if (tr_on) ES_TRACE(2 + g, u, 0);
-            if (RES2) {   // pull this warp's 16 skip rows (8 KB) towards L2 while the GEMM runs
-                const int pr = rbase + (lane >> 1);
-                if (pr < rows_valid) {
-                    const float* sp = p.res2 + ((size_t)b * p.T + t0 + pr) * N + (lane & 1) * 64;
-                    prefetch_l2(sp);
-                    prefetch_l2(sp + 32);
+            const float* res0 = nullptr;
+            const float* res1 = nullptr;
+            if (RES2) {
+                const int pr = rbase + (lane >> 1);          // lanes 2k, 2k+1 <-> row rbase + k of this warp's 16
+                if (GS) {
+                    // skip rows come from the (L2-resident) table: fetch the row indices while the GEMM runs
+                    const int s_pr = pr < rows_valid ? __ldg(p.src + (size_t)b * p.T + t0 + pr) : 0;
+                    res0 = p.res2 + (size_t)__shfl_sync(0xffffffffu, s_pr, 2 * tr) * N;
+                    res1 = p.res2 + (size_t)__shfl_sync(0xffffffffu, s_pr, 2 * tr + 16) * N;
+                } else {
+                    // pull this warp's 16 skip rows (8 KB) towards L2 while the GEMM runs
+                    if (pr < rows_valid) {
+                        const float* sp = p.res2 + ((size_t)b * p.T + t0 + pr) * N + (lane & 1) * 64;
+                        prefetch_l2(sp);
+                        prefetch_l2(sp + 32);
+                    }
+                    res0 = p.res2 + g0 * N;
+                    res1 = res0 + 8 * N;
                 }
             }
             if (!mbar_wait(bar_mma + 8 * g, u & 1)) failed = true;
@@ -505,334 +601,9 @@ umma_dec_kernel(const UmmaDecParams p) {
             if (lane == 0) mbar_arrive(bar_tfree + 8 * g);     // accumulator drained: the GEMM of tile i+2 may start
             if (tr_on) ES_TRACE(2 + g, u, 2);
             epilogue_math<RES2>(r, par, N, nj, inv_n, p.act_tanh != 0, p.ln_g != nullptr,
-                                RES2 ? p.res2 + g0 * N : nullptr, p.Y + g0 * N, ok0, ok1,
+                                res0, res1, p.Y + g0 * N, ok0, ok1,
                                 p.zero_from ? p.zero_from[b] - (t0 + row0) : 0x7fffffff, t4,
                                 [&](int ev) { if (tr_on) ES_TRACE(2 + g, u, ev); });
-            if (tr_on) ES_TRACE(2 + g, u, 5);
-        }
-    }
-
-    if (failed) atomicExch(p.err, 1);
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
-}
-
-// ================================================================================================
-// Multi-layer persistent kernel: ALL depthwise layers of the decoder (and the mel head, as a layer with
-// an identity depthwise stage) in ONE launch.  A per-layer launch spends about a third of its time
-// outside the steady state -- launch + prologue, pipeline fill, and above all the drain while the
-// epilogue warps finish the last tiles -- and a 208 KB CTA cannot overlap that with its successor.
-// Here the tile -> CTA map is the same in every layer (tile % gridDim.x) and a CTA walks
-// layer 0 over its tiles, then layer 1, ...: the x ring, the MMA issue and the epilogues stream
-// straight across layer boundaries.  Layer s+1 of tile t needs rows of tiles t-1, t, t+1 of layer s
-// (2-frame halo); t is this CTA's own, the neighbours belong to CTAs blockIdx.x -+ 1 which run the
-// same schedule, so their results are ~a full layer old when they are needed.  Completion is
-// published per (layer, tile) in global memory -- every epilogue warp fences its stores and adds 1,
-// the issue warp acquires 4 arrivals on the (up to) three tiles before it starts the bulk copy -- so
-// the only serialisation left per layer is the swap of the resident weights (the MMAs of the old
-// layer must have completed; 64 KB from L2).
-// Requires every CTA resident at once (grid <= #SMs, 1 CTA/SM: guaranteed on an otherwise idle GPU;
-// all waits are bounded and raise the error flag instead of hanging) and >= 4 tiles per CTA.
-constexpr int MAX_STACK = 8;
-struct DecStage {
-    const float* X; float* Y; const float* res2;
-    const float* dw_w; const float* dw_b;                 // dw_w == nullptr: identity (mel head)
-    const void* w_h16; const float* bias;
-    const float* ln_g; const float* ln_b; const float* ln2_g; const float* ln2_b;
-    const int* zero_from;
-    int N; int act_tanh;
-};
-struct UmmaStackParams {
-    int B, T, n_stages;
-    int* ready;                  // [n_stages - 1][n_tiles] epilogue-warp arrivals, zeroed before the launch
-    int* err;
-    long long* trace;
-    DecStage st[MAX_STACK];
-};
-constexpr uint32_t S_OFF_PAR = OFF_W + 2 * W_PLANE_MAX;          // one parameter block per epilogue group: 2 x 5 x 128 floats
-constexpr uint32_t S_OFF_DW = S_OFF_PAR + 2 * 5 * 128 * 4;
-constexpr uint32_t S_OFF_BAR = S_OFF_DW + 6 * 128 * 4;
-constexpr uint32_t S_SMEM_BYTES = S_OFF_BAR + 128;
-static_assert(S_SMEM_BYTES <= 227 * 1024, "shared memory budget");
-
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-__global__ void __launch_bounds__(NTHR, 1)
-umma_dec_stack_kernel(const __grid_constant__ UmmaStackParams p) {
-    constexpr int HALO = DWK / 2, XROWS = TM + 2 * HALO;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint8_t* a_hi = smem + OFF_A;
-    const uint32_t bar_x = smem_u32(smem + S_OFF_BAR);
-    const uint32_t bar_w = bar_x + 24;
-    const uint32_t bar_mma = bar_x + 32;
-    const uint32_t bar_tfree = bar_x + 48;
-    const uint32_t bar_xfree = bar_x + 64;
-    const uint32_t bar_aready = bar_x + 88;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S_OFF_BAR + 96);
-
-    const int S = p.n_stages;
-    const int tiles_per_utt = (p.T + TM - 1) / TM;
-    const int n_tiles = p.B * tiles_per_utt;
-    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total_it = my_tiles * S;
-
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 128);
-    if (tid == 0) {
-        for (int k = 0; k < NSTAGE; ++k) mbar_init(bar_x + 8 * k, 1);
-        mbar_init(bar_w, 1);
-        mbar_init(bar_mma, 1);
-        mbar_init(bar_mma + 8, 1);
-        mbar_init(bar_tfree, 4);
-        mbar_init(bar_tfree + 8, 4);
-        for (int k = 0; k < NSTAGE; ++k) mbar_init(bar_xfree + 8 * k, 4);
-        mbar_init(bar_aready, 4);
-        fence_mbar_init();
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-    bool failed = false;
-    pdl_launch_dependents();
-    pdl_wait();
-
-    if (warp == 12) {
-        // =========================================================================== issue warp
-        const bool elected = elect_one();
-        // tiles t-1, t, t+1 of the previous layer finished (4 epilogue-warp arrivals each)?  one lane polls
-        auto wait_ready = [&](int s, int tile, int t0) -> bool {
-            const int* f = p.ready + (size_t)(s - 1) * n_tiles + tile;
-            const bool left = t0 > 0, right = t0 + TM < p.T;
-            for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
-                if (ld_acquire_gpu(f) >= 4 && (!left || ld_acquire_gpu(f - 1) >= 4) && (!right || ld_acquire_gpu(f + 1) >= 4)) {
-                    fence_proxy_async_all();         // the bulk copy (async proxy) reads what generic-proxy stores wrote
-                    return true;
-                }
-                __nanosleep(64);
-            }
-            return false;
-        };
-        auto issue_x = [&](int it, int slot) -> bool {
-            const int s = it / my_tiles, tile = blockIdx.x + (it - s * my_tiles) * gridDim.x;
-            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
-            const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
-            const uint32_t bytes = (uint32_t)(hi - lo) * CK * 4u;
-            bool ok = true;
-            if (s > 0) ok = wait_ready(s, tile, t0);
-            mbar_arrive_expect_tx(bar_x + 8 * slot, bytes);
-            bulk_g2s(smem_u32(smem + OFF_XS) + (uint32_t)slot * X_STAGE + (uint32_t)(lo - (t0 - HALO)) * CK * 4u,
-                     p.st[s].X + ((size_t)b * p.T + lo) * CK, bytes, bar_x + 8 * slot);
-            return ok;
-        };
-        for (int k = 0; k < NSTAGE; ++k)
-            if (k < total_it && elected && !issue_x(k, k)) failed = true;
-        uint32_t idesc = 0, lbo_b = 0;
-        uint64_t dah0 = 0, dal0 = 0, dbh0 = 0, dbl0 = 0, db_step = 0;
-        for (int it = 0; it < total_it; ++it) {
-            const int s = it / my_tiles;
-            const int g = it & 1, u = it >> 1, slot = it % NSTAGE;
-            if (it == s * my_tiles) {
-                // layer boundary: every MMA of the previous layer has completed (commits complete in order),
-                // then its resident weights are replaced
-                if (it > 0 && !mbar_wait(bar_mma + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1)) failed = true;
-                const int N = p.st[s].N;
-                const uint32_t w_plane = (uint32_t)N * CK * 2u;
-                if (elected) {
-                    mbar_arrive_expect_tx(bar_w, 2 * w_plane);
-                    bulk_g2s(smem_u32(smem + OFF_W), p.st[s].w_h16, w_plane, bar_w);
-                    bulk_g2s(smem_u32(smem + OFF_W) + w_plane, reinterpret_cast<const uint8_t*>(p.st[s].w_h16) + w_plane, w_plane, bar_w);
-                }
-                idesc = make_idesc_f16(TM, N);
-                lbo_b = (uint32_t)N * 16u;
-                dah0 = make_smem_desc(smem_u32(a_hi), A_LBO, A_SBO);
-                dal0 = make_smem_desc(smem_u32(a_hi) + A_PLANE, A_LBO, A_SBO);
-                dbh0 = make_smem_desc(smem_u32(smem + OFF_W), lbo_b, 128u);
-                dbl0 = make_smem_desc(smem_u32(smem + OFF_W) + w_plane, lbo_b, 128u);
-                db_step = (uint64_t)((2u * lbo_b) >> 4);
-                if (!mbar_wait(bar_w, s & 1)) failed = true;
-                __syncwarp();
-            }
-            if (elected) ES_TRACE(0, it, 0);
-            if (!mbar_wait(bar_aready, it & 1)) failed = true;
-            if (elected) ES_TRACE(0, it, 1);
-            if (u > 0 && !mbar_wait(bar_tfree + 8 * g, (u - 1) & 1)) failed = true;
-            tc_fence_after_sync();
-            if (elected) ES_TRACE(0, it, 2);
-            const uint32_t acc = tmem + ((uint32_t)(16 * g) << 16);
-#pragma unroll
-            for (int k = 0; k < CK / 16; ++k) {
-                const uint64_t da = (uint64_t)((uint32_t)(2 * k) * A_LBO >> 4);
-                const uint64_t db = (uint64_t)k * db_step;
-                if (elected) {
-                    mma_f16_ss(acc, dah0 + da, dbh0 + db, idesc, k > 0 ? 1u : 0u);
-                    mma_f16_ss(acc, dah0 + da, dbl0 + db, idesc, 1u);
-                    mma_f16_ss(acc, dal0 + da, dbh0 + db, idesc, 1u);
-                }
-            }
-            if (elected) { mma_commit(bar_mma + 8 * g); ES_TRACE(0, it, 3); }
-            if (it + NSTAGE < total_it) {
-                if (!mbar_wait(bar_xfree + 8 * slot, (it / NSTAGE) & 1)) failed = true;
-                if (elected && !issue_x(it + NSTAGE, slot)) failed = true;
-            }
-            if (elected) ES_TRACE(0, it, 4);
-            __syncwarp();
-        }
-    } else if (warp >= 8) {
-        // =========================================================================== producers
-        const int pw = warp - 8, ptid = tid - 256;
-        float* dws = reinterpret_cast<float*>(smem + S_OFF_DW);
-        const ulonglong2* dwp = reinterpret_cast<const ulonglong2*>(smem + S_OFF_DW);
-        bool identity = false;
-        for (int it = 0; it < total_it; ++it) {
-            const int s = it / my_tiles, tile = blockIdx.x + (it - s * my_tiles) * gridDim.x;
-            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
-            const int slot = it % NSTAGE;
-            float* Xs = reinterpret_cast<float*>(smem + OFF_XS + (uint32_t)slot * X_STAGE);
-            const bool tr_on = (pw == 0 && lane == 0);
-            if (it == s * my_tiles) {          // layer boundary: this layer's depthwise taps
-                named_bar_sync(1, NPROD);      // every producer warp is done with the previous taps
-                identity = p.st[s].dw_w == nullptr;
-                if (!identity)
-                    for (int k = ptid; k < (DWK + 1) * CK; k += NPROD)
-                        dws[k] = k < DWK * CK ? __ldg(p.st[s].dw_w + k) : __ldg(p.st[s].dw_b + k - DWK * CK);
-                named_bar_sync(1, NPROD);
-            }
-            if (tr_on) ES_TRACE(1, it, 0);
-            {
-                const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
-                const int head = lo - (t0 - HALO), tail0 = hi - (t0 - HALO);
-                const bool edge = head > 0 || tail0 < XROWS;
-                if (edge) {
-                    for (int k = ptid; k < (head + XROWS - tail0) * (CK / 4); k += NPROD) {
-                        int r = k / (CK / 4);
-                        const int c4 = k - r * (CK / 4);
-                        if (r >= head) r = tail0 + (r - head);
-                        reinterpret_cast<float4*>(Xs + r * CK)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-                if (!mbar_wait(bar_x + 8 * slot, (it / NSTAGE) & 1)) failed = true;
-                if (edge) named_bar_sync(1, NPROD);
-                if (tr_on) ES_TRACE(1, it, 1);
-            }
-            uint2 ahi[16], alo[16];
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int r0 = pw * 16 + pass * 8;
-                ulonglong2 win[8 + 2 * HALO];
-#pragma unroll
-                for (int k = 0; k < 8 + 2 * HALO; ++k) win[k] = reinterpret_cast<const ulonglong2*>(Xs + (r0 + k) * CK)[lane];
-                if (identity) {
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) split4(win[r + HALO], ahi[pass * 8 + r], alo[pass * 8 + r]);
-                } else {
-                    ulonglong2 wdw[DWK], bdw;
-#pragma unroll
-                    for (int t = 0; t < DWK; ++t) wdw[t] = dwp[t * 32 + lane];
-                    bdw = dwp[DWK * 32 + lane];
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        ulonglong2 o = bdw;
-#pragma unroll
-                        for (int t = 0; t < DWK; ++t) {
-                            o.x = fma2(wdw[t].x, win[r + t].x, o.x);
-                            o.y = fma2(wdw[t].y, win[r + t].y, o.y);
-                        }
-                        split4(o, ahi[pass * 8 + r], alo[pass * 8 + r]);
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_xfree + 8 * slot);
-            if (tr_on) ES_TRACE(1, it, 2);
-            if (it > 0 && !mbar_wait(bar_mma + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1)) failed = true;
-            if (tr_on) ES_TRACE(1, it, 3);
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const uint32_t off = a_off(pw * 16 + r, lane);
-                *reinterpret_cast<uint2*>(a_hi + off) = ahi[r];
-                *reinterpret_cast<uint2*>(a_hi + A_PLANE + off) = alo[r];
-            }
-            if (tr_on) ES_TRACE(1, it, 4);
-            fence_proxy_async_smem();
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_aready);
-            if (tr_on) ES_TRACE(1, it, 5);
-        }
-    } else {
-        // =========================================================================== epilogue
-        const int q = warp & 3, g = warp >> 2;
-        const int rbase = q * 16;
-        const int t4 = lane & 3, tr = lane >> 2;
-        float* par = reinterpret_cast<float*>(smem + S_OFF_PAR) + g * 5 * 128;      // this group's parameter block
-        const int gtid = tid - g * 128;
-        int cur_s = -1, N = 128, nj = 16;
-        float inv_n = 1.f / 128.f;
-        for (int it = g; it < total_it; it += 2) {
-            const int s = it / my_tiles, tile = blockIdx.x + (it - s * my_tiles) * gridDim.x;
-            const DecStage& st = p.st[s];
-            if (s != cur_s) {                  // this group's first tile of a layer: its epilogue parameters
-                named_bar_sync(2 + g, 128);
-                N = st.N;
-                for (int k = gtid; k < 128; k += 128) {
-                    par[k] = (k < N) ? __ldg(st.bias + k) * (st.act_tanh ? kTanhScale : 1.f) : 0.f;
-                    par[128 + k] = (st.ln_g && k < N) ? __ldg(st.ln_g + k) : 0.f;
-                    par[256 + k] = (st.ln_g && k < N) ? __ldg(st.ln_b + k) : 0.f;
-                    par[384 + k] = (st.ln2_g && k < N) ? __ldg(st.ln2_g + k) : 0.f;
-                    par[512 + k] = (st.ln2_g && k < N) ? __ldg(st.ln2_b + k) : 0.f;
-                }
-                named_bar_sync(2 + g, 128);
-                nj = N >> 3;
-                inv_n = 1.f / (float)N;
-                cur_s = s;
-            }
-            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
-            const int rows_valid = min(TM, p.T - t0);
-            const int u = it >> 1;
-            const int row0 = rbase + tr, row1 = row0 + 8;
-            const size_t g0 = (size_t)b * p.T + t0 + row0;
-            const bool ok0 = row0 < rows_valid, ok1 = row1 < rows_valid;
-            const bool tr_on = (q == 0 && lane == 0);
-            const bool res2 = st.res2 != nullptr;
-            if (tr_on) ES_TRACE(2 + g, u, 0);
-            if (res2) {
-                const int pr = rbase + (lane >> 1);
-                if (pr < rows_valid) {
-                    const float* sp = st.res2 + ((size_t)b * p.T + t0 + pr) * N + (lane & 1) * 64;
-                    prefetch_l2(sp);
-                    prefetch_l2(sp + 32);
-                }
-            }
-            if (!mbar_wait(bar_mma + 8 * g, u & 1)) failed = true;
-            tc_fence_after_sync();
-            if (tr_on) ES_TRACE(2 + g, u, 1);
-            uint32_t r[64];
-            tmem_ld_16x256b_x16(tmem + ((uint32_t)(32 * q + 16 * g) << 16), r);
-            tmem_ld_wait();
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tfree + 8 * g);
-            if (tr_on) ES_TRACE(2 + g, u, 2);
-            const int zero_rows = st.zero_from ? st.zero_from[b] - (t0 + row0) : 0x7fffffff;
-            auto stamp = [&](int ev) { if (tr_on) ES_TRACE(2 + g, u, ev); };
-            if (res2)
-                epilogue_math<true, true>(r, par, N, nj, inv_n, st.act_tanh != 0, st.ln_g != nullptr, st.res2 + g0 * N,
-                                          st.Y + g0 * N, ok0, ok1, zero_rows, t4, stamp);
-            else
-                epilogue_math<false, true>(r, par, N, nj, inv_n, st.act_tanh != 0, st.ln_g != nullptr, nullptr,
-                                           st.Y + g0 * N, ok0, ok1, zero_rows, t4, stamp);
-            if (s + 1 < S) {                   // publish: this warp's 16 rows of (layer s, tile) are in global memory
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) atomicAdd(p.ready + (size_t)s * n_tiles + tile, 1);
-            }
             if (tr_on) ES_TRACE(2 + g, u, 5);
         }
     }
@@ -847,14 +618,14 @@ int* g_err_flag = nullptr;
 long long* g_trace = nullptr;
 int g_trace_pick = 0, g_trace_count = 0;   // which launch after es_debug_set_trace is stamped (env ES_TRACE_LAUNCH)
 
-template <int MODE, bool RES2>
+template <int MODE, bool RES2, bool GX = false, bool GS = false>
 int launch_mode(const UmmaDecParams& p, int grid, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        ES_CUDA(cudaFuncSetAttribute(umma_dec_kernel<MODE, RES2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        ES_CUDA(cudaFuncSetAttribute(umma_dec_kernel<MODE, RES2, GX, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    ES_CUDA(launch_pdl(umma_dec_kernel<MODE, RES2>, grid, NTHR, SMEM_BYTES, s, p));
+    ES_CUDA(launch_pdl(umma_dec_kernel<MODE, RES2, GX, GS>, grid, NTHR, SMEM_BYTES, s, p));
     ES_LAUNCH_OK();
     return 0;
 }
@@ -888,7 +659,8 @@ int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, co
     p.B = B; p.T = T; p.N = N; p.n_src = n_src; p.X = X; p.cum = cum; p.valid_len = valid_len;
     p.dw_w = dw_w; p.dw_b = dw_b; p.w_h16 = w_h16; p.bias = bias; p.act_tanh = act_tanh;
     p.ln_g = ln_g; p.ln_b = ln_b; p.res2 = res2; p.ln2_g = ln2_g; p.ln2_b = ln2_b;
-    p.zero_from = zero_from; p.Y = Y; p.err = g_err_flag; p.trace = (g_trace && g_trace_count++ == g_trace_pick) ? g_trace : nullptr;
+    p.zero_from = zero_from; p.src = nullptr; p.pad_id = 0;
+    p.Y = Y; p.err = g_err_flag; p.trace = (g_trace && g_trace_count++ == g_trace_pick) ? g_trace : nullptr;
     const int n_tiles = B * ((T + TM - 1) / TM);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
     switch (mode) {
@@ -898,52 +670,34 @@ int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, co
     }
 }
 
-// All depthwise layers (+ mel head) of a 128-channel decoder in one launch; -1: not applicable (caller falls
-// back to one launch per layer).  `ready` is workspace for (n_stages - 1) * n_tiles ints.
-int umma_dec_stack_grid_override = 0;      // tests: run the multi-layer kernel on small problems with few CTAs
-int launch_umma_dec_stack(int B, int T, int n_stages, const UmmaDecStage* stages, int* ready, cudaStream_t s) {
-    if (n_stages < 2 || n_stages > MAX_STACK || !ready) return -1;
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        ES_CUDA(cudaGetDevice(&dev));
-        ES_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        const char* e = getenv("ES_DEC_STACK_GRID");
-        if (e && !umma_dec_stack_grid_override) umma_dec_stack_grid_override = atoi(e);
-    }
-    const int n_tiles = B * ((T + TM - 1) / TM);
-    const int grid = umma_dec_stack_grid_override > 0 ? (umma_dec_stack_grid_override < n_sm ? umma_dec_stack_grid_override : n_sm) : n_sm;
-    if (n_tiles < 4 * grid) return -1;      // >= 4 tiles per CTA (the x ring prefetches 3 tiles ahead across layers)
+// Depthwise layer with table-gathered input and / or skip rows (the length regulator fused into the first block).
+int launch_umma_dec_gathered(int B, int T, int N, const float* X, const float* dw_w, const float* dw_b,
+                             const void* w_h16, const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
+                             const float* res2, const float* ln2_g, const float* ln2_b, const int* src, int pad_id,
+                             int gather_x, int gather_res2, float* Y, cudaStream_t s) {
+    ES_CHECK(w_h16 && X && Y && bias && dw_w && dw_b && src, "null tensor");
+    ES_CHECK(N == 128, "gathered layers are full-width (N == 128)");
+    ES_CHECK(gather_x || gather_res2, "nothing to gather");
+    ES_CHECK(!gather_res2 || res2, "gathered skip without a table");
+    ES_CHECK(!(gather_x && res2) || gather_res2, "a layer that gathers its input also gathers its skip (first block)");
     if (!g_err_flag) {
         ES_CUDA(cudaMalloc(&g_err_flag, sizeof(int)));
         ES_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
     }
-    UmmaStackParams p;
-    memset(&p, 0, sizeof(p));
-    p.B = B; p.T = T; p.n_stages = n_stages; p.ready = ready; p.err = g_err_flag;
-    p.trace = (g_trace && g_trace_count++ == g_trace_pick) ? g_trace : nullptr;
-    for (int i = 0; i < n_stages; ++i) {
-        const UmmaDecStage& a = stages[i];
-        ES_CHECK(a.X && a.Y && a.w_h16 && a.bias, "null tensor");
-        ES_CHECK(a.N % 16 == 0 && a.N >= 32 && a.N <= 128, "N must be a multiple of 16 in [32,128]");
-        ES_CHECK(!(a.ln_g || a.res2) || a.N == 128, "LayerNorm epilogue needs N == 128");
-        DecStage& d = p.st[i];
-        d.X = a.X; d.Y = a.Y; d.res2 = a.res2; d.dw_w = a.dw_w; d.dw_b = a.dw_b; d.w_h16 = a.w_h16; d.bias = a.bias;
-        d.ln_g = a.ln_g; d.ln_b = a.ln_b; d.ln2_g = a.ln2_g; d.ln2_b = a.ln2_b; d.zero_from = a.zero_from;
-        d.N = a.N; d.act_tanh = a.act_tanh;
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        ES_CUDA(cudaFuncSetAttribute(umma_dec_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_BYTES));
-        attr_set = true;
-    }
-    ES_CUDA(cudaMemsetAsync(ready, 0, sizeof(int) * (size_t)(n_stages - 1) * n_tiles, s));
-    ES_CUDA(launch_pdl(umma_dec_stack_kernel, grid, NTHR, S_SMEM_BYTES, s, p));
-    ES_LAUNCH_OK();
-    return 0;
+    int dev = 0, n_sm = 0;
+    ES_CUDA(cudaGetDevice(&dev));
+    ES_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    UmmaDecParams p;
+    p.B = B; p.T = T; p.N = N; p.n_src = 0; p.X = X; p.cum = nullptr; p.valid_len = nullptr;
+    p.dw_w = dw_w; p.dw_b = dw_b; p.w_h16 = w_h16; p.bias = bias; p.act_tanh = act_tanh;
+    p.ln_g = ln_g; p.ln_b = ln_b; p.res2 = res2; p.ln2_g = ln2_g; p.ln2_b = ln2_b;
+    p.zero_from = nullptr; p.src = src; p.pad_id = pad_id;
+    p.Y = Y; p.err = g_err_flag; p.trace = (g_trace && g_trace_count++ == g_trace_pick) ? g_trace : nullptr;
+    const int n_tiles = B * ((T + TM - 1) / TM);
+    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    if (!res2) return launch_mode<MODE_DWCONV, false, true, false>(p, grid, s);
+    return gather_x ? launch_mode<MODE_DWCONV, true, true, true>(p, grid, s) : launch_mode<MODE_DWCONV, true, false, true>(p, grid, s);
 }
-void umma_dec_stack_set_grid(int ctas) { umma_dec_stack_grid_override = ctas; }
-size_t umma_dec_stack_ready_ints(int B, int T, int n_stages) { return (size_t)(n_stages > 1 ? n_stages - 1 : 0) * B * ((T + TM - 1) / TM); }
 
 // device flag raised by any tcgen05 kernel whose bounded mbarrier wait timed out (shared with es_umma_enc.cu)
 int* umma_err_flag() {

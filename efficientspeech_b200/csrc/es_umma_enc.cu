@@ -13,11 +13,11 @@
 //                         ([tap][hi,lo][K/8][N][8], prepared at pack time) are bulk-loaded once
 //                         per CTA and stay resident.
 //   epilogue warps 0..7   tcgen05.ld 16x256b per 128-column chunk; bias, boundary-aware tap bias,
-//                         ReLU / exact-erf GELU, scalar head (quad shuffle), residual, LayerNorm,
-//                         second activation, padding mask, 8-byte stores -- all in registers.
+//                         ReLU / exact-erf GELU, scalar head (quad shuffle), residual, Fuse scatter,
+//                         LayerNorm, second activation, padding mask, 8-byte stores -- all in registers.
 //
 // Used for: QKV / attention-output projections, the folded MixFFN conv and mlp2, the block-1
-// merge conv (stride 2, 1 tap) and both convs of the three variance predictors whenever
+// merge conv (stride 2, 1 tap), both GEMMs of the folded Fuse (d <= 64) and both convs of the three variance predictors whenever
 // K <= 128, N <= 384 and the weights fit in shared memory; everything else stays on the fp32
 // SIMT kernels of es_rowgemm.cu.
 #include <stdlib.h>
@@ -303,6 +303,21 @@ umma_rowgemm_kernel(const UrgParams up) {
                             }
                         }
                     }
+                    if (p.fuse_u) {
+                        // Fuse: stride-2 transposed-conv scatter of U (networks.py:199-206); tt1 = tt0 + 8 has tt0's parity
+                        for (int tau = tt0 & 1; tau < p.fuse_k; tau += 2) {
+                            const int j0 = (tt0 - tau) >> 1, j1 = (tt1 - tau) >> 1;
+                            const bool v0 = ok0 && tt0 >= tau && j0 < p.fuse_n1, v1 = ok1 && tt1 >= tau && j1 < p.fuse_n1;
+                            const float* u0 = p.fuse_u + ((size_t)b * p.fuse_n1 + (v0 ? j0 : 0)) * p.fuse_ld + tau * N + 2 * t4;
+                            const float* u1 = p.fuse_u + ((size_t)b * p.fuse_n1 + (v1 ? j1 : 0)) * p.fuse_ld + tau * N + 2 * t4;
+#pragma unroll
+                            for (int j = 0; j < NJ; ++j) {
+                                const float2 a = v0 ? __ldg(reinterpret_cast<const float2*>(u0 + 8 * j)) : make_float2(0.f, 0.f);
+                                const float2 cc = v1 ? __ldg(reinterpret_cast<const float2*>(u1 + 8 * j)) : make_float2(0.f, 0.f);
+                                v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += cc.x; v[4 * j + 3] += cc.y;
+                            }
+                        }
+                    }
                     if (p.ln_g) {
                         float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;
 #pragma unroll
@@ -364,7 +379,8 @@ int launch_umma_rowgemm_batch(const RowGemmParams* ps, const void* const* w_h16,
         if (!w_h16[i] || o.mode != ROW_PLAIN || o.res2) return -1;
         if (o.B != p.B || o.n_in != p.n_in || o.n_out != p.n_out || o.K != p.K || o.Nout != p.Nout || o.taps != p.taps ||
             o.stride != p.stride || o.pad != p.pad) return -1;
-        if (o.Nout > 128 && (o.ln_g || o.dot_out || o.res1 || o.act2 != ACT_NONE)) return -1;
+        if (o.Nout > 128 && (o.ln_g || o.dot_out || o.res1 || o.fuse_u || o.act2 != ACT_NONE)) return -1;
+        if (o.fuse_u && (o.fuse_ld % 2 || o.taps != 1 || o.stride != 1)) return -1;
         if (o.lda % 4 || (o.Y && o.ldy % 2) || (o.res1 && o.ldr1 % 2)) return -1;
         if (o.act2 != ACT_NONE && o.act2 != ACT_RELU) return -1;
         if (o.act1 == ACT_TANH) return -1;

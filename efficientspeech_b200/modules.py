@@ -12,6 +12,7 @@ current CUDA stream.  There is no CPU fallback: non-CUDA inputs raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -150,7 +151,8 @@ class _Backend:
         self.handle = C.c_void_p(None)
         self.workspace: Optional[torch.Tensor] = None
         self.tensor_core = True
-        self.decoder_stack = False
+        # ES_DEC_GATHER_MODE (0/1/2) overrides the default for A/B runs of the same command line
+        self.gather_mode = int(os.environ.get("ES_DEC_GATHER_MODE", _cabi.ES_GATHER_FUSED))
 
     def __del__(self):
         try:
@@ -166,7 +168,8 @@ class _Backend:
 
     def ensure(self, device: torch.device) -> C.c_void_p:
         params = list(self.owner.parameters())
-        key = (str(device), self.tensor_core, self.decoder_stack) + tuple((p.data_ptr(), p._version) for p in params)
+        key = (str(device), self.tensor_core, self.gather_mode) + \
+            tuple((p.data_ptr(), p._version) for p in params)
         if key == self.key:
             return self.handle
         lib = _cabi.load()
@@ -195,12 +198,15 @@ class _Backend:
             for which in ("pitch", "energy", "duration"):
                 for cv in ("conv1", "conv2"):
                     folded[f"{which}.{cv}_w_h16"] = image(f"{which}.{cv}_w", c.dim)
-            if c.dim % 128 == 0:
-                # Fuse as two tensor-core GEMMs (es_api.cu: fuse): all k transposed-conv taps at once
-                k = folded["fuse_g"].shape[0]
-                gcat = np.concatenate([folded["fuse_g"][t] for t in range(k)], axis=1)[None]       # [1][2d][k*d]
+            # Fuse as two tensor-core GEMMs (es_api.cu: fuse): all k transposed-conv taps at once
+            k = folded["fuse_g"].shape[0]
+            gcat = np.concatenate([folded["fuse_g"][t] for t in range(k)], axis=1)[None]       # [1][2d][k*d]
+            if c.dim % 128 == 0:                                        # streamed units (es_umma_wide.cu)
                 folded["fuse_u_h16"] = packing.canon_split_units(gcat, k * c.dim, 128)
                 folded["fuse_a0_h16"] = packing.canon_split_units(folded["fuse_a0"][None], c.dim, 128)
+            elif lib.es_dense_layout(2 * c.dim, k * c.dim, 1, 1) == 1 and lib.es_dense_layout(c.dim, c.dim, 1, 1) == 1:
+                folded["fuse_u_h16"] = packing.canon_split_taps(gcat, k * c.dim)       # resident image (es_umma_enc.cu)
+                folded["fuse_a0_h16"] = packing.canon_split_taps(folded["fuse_a0"][None], c.dim)
         if self.part == "decoder":
             # B operands of the tcgen05 kernels: W as [N][K], split into fp16 hi/lo, canonical order
             # dx2 == 128: whole-matrix image (weights stay resident in shared memory, es_umma_dec.cu);
@@ -252,7 +258,7 @@ class _Backend:
         h = C.c_void_p(None)
         _cabi.check(lib.es_model_create(C.byref(cc), C.byref(W), C.byref(h)))
         _cabi.check(lib.es_model_set_tensor_core(h, 1 if self.tensor_core else 0))
-        _cabi.check(lib.es_model_set_decoder_stack(h, 1 if self.decoder_stack else 0))
+        _cabi.check(lib.es_model_set_decoder_gather(h, int(self.gather_mode)))
         self.handle = h
         self.key = key
         return h
@@ -307,11 +313,13 @@ class MelDecoder(nn.Module):
         """True (default): tcgen05 split-fp16 decoder layers; False: fp32 SIMT kernels."""
         self._backend.tensor_core = bool(enable)
 
-    def set_decoder_stack(self, enable: bool) -> None:
-        """True: all depthwise layers + mel head as one persistent multi-layer launch when the batch is
-        large enough; False (default): one launch per layer.  Bit-identical results; measured slower on
-        B200 (0.41 ms vs 0.29 ms for tiny, B=256, T=768 -- DESIGN.md section 5.4), kept as an experiment."""
-        self._backend.decoder_stack = bool(enable)
+    def set_gather_mode(self, mode: int) -> None:
+        """How ``Phoneme2Mel`` joins the length regulator and this decoder (include/es_b200.h, ES_GATHER_*):
+        0 projection per frame with the gather in its operand load; 1 projection per phoneme + row-gather
+        kernel; 2 (default) projection per phoneme, the first block gathers the rows itself."""
+        if mode not in (0, 1, 2):
+            raise ValueError("gather mode must be 0, 1 or 2")
+        self._backend.gather_mode = int(mode)
 
     def forward(self, features):
         _require_cuda(features, "features")
@@ -333,7 +341,7 @@ class MelDecoder(nn.Module):
         with torch.cuda.device(dev):
             h = self._backend.ensure(dev)
             mel = torch.empty(B, T, self.n_mel_channels, dtype=torch.float32, device=dev)
-            ws, wsn = self._backend.scratch(dev, B, 0, T)
+            ws, wsn = self._backend.scratch(dev, B, N, T)
             _cabi.check(_cabi.load().es_decoder_forward_gathered(
                 h, _stream(dev), B, N, T, fused4.data_ptr(), dur_cum.data_ptr(), mel_len.data_ptr(),
                 1 if zero_padded else 0, mel.data_ptr(), ws, wsn))

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ES_ABI_VERSION 8
+#define ES_ABI_VERSION 9
 #define ES_MAX_ENC_BLOCKS 2
 #define ES_MAX_DEC_LAYERS 24
 #define ES_MAX_DEC_BLOCKS 8
@@ -152,11 +152,17 @@ int  es_model_create(const es_config_t* cfg, const es_weights_t* w, es_model_t**
 void es_model_destroy(es_model_t* m);
 /* 0: SIMT fp32 kernels everywhere; 1 (default): tcgen05 split-fp16 decoder layers where supported */
 int  es_model_set_tensor_core(es_model_t* m, int enable);
-/* 1: 128-channel decoders run all depthwise layers + the mel head (MelDecoder.forward,
- * networks.py:293-302) as ONE persistent multi-layer launch when the batch gives every SM >= 4 tiles;
- * 0 (default): one launch per layer.  Results are bit-identical either way; the single launch measured
- * slower on B200 and is kept as an opt-in experiment. */
-int  es_model_set_decoder_stack(es_model_t* m, int enable);
+/* How es_decoder_forward_gathered joins the length regulator and the decoder (default ES_GATHER_FUSED):
+ *   ES_GATHER_PER_FRAME    projection GEMM per frame with the gather in its operand load (first version)
+ *   ES_GATHER_MATERIALIZE  projection per phoneme, then a row-gather kernel writes skip [B,T,dx2]
+ *   ES_GATHER_FUSED        projection per phoneme; the first decoder block gathers rows of the table itself
+ *                          ([B,T,dx2] is never written); decoders without that kernel variant (dx2 = 256, SIMT
+ *                          mode) fall back to ES_GATHER_MATERIALIZE.
+ * All three compute the same function; results agree to fp32 rounding of one 4d-long dot product. */
+#define ES_GATHER_PER_FRAME   0
+#define ES_GATHER_MATERIALIZE 1
+#define ES_GATHER_FUSED       2
+int  es_model_set_decoder_gather(es_model_t* m, int mode);
 
 /* Scratch requirement (bytes) of the calls below for a batch of B utterances, N phonemes,
  * T frames (T may be 0 for encoder-only use). */
@@ -195,6 +201,15 @@ int es_length_regulate(es_model_t* m, void* stream, int B, int N, int T,
                        const float* fused4, const int32_t* dur_cum, const uint8_t* phoneme_mask,
                        float* features, uint8_t* frame_mask, int32_t* src);
 
+/*
+ * The length regulator as the index map the gathered decoder entry uses internally
+ * (FeatureUpsampler.forward, networks.py:228-258, as integers only):
+ *   rows[b,t] = b*N + min{n : dur_cum[b,n] > t}  for t < mel_len[b],  B*N (the zero-padded row) otherwise.
+ * rows [B,T] int32.  Exposed so that tests can check the map of the hot path bit-exactly.
+ */
+int es_frame_rows(es_model_t* m, void* stream, int B, int N, int T,
+                  const int32_t* dur_cum, const int32_t* mel_len, int32_t* rows);
+
 /* Replaces MelDecoder.forward (networks.py:291-304): features [B,T,4d] -> mel [B,T,n_mel]. */
 int es_decoder_forward(es_model_t* m, void* stream, int B, int T,
                        const float* features, float* mel,
@@ -202,9 +217,12 @@ int es_decoder_forward(es_model_t* m, void* stream, int B, int T,
 
 /*
  * Replaces the decoder half of Phoneme2Mel.forward (networks.py:422-427) without ever
- * materialising [B,T,4d]: the length-regulator gather is the prologue of the first decoder
- * kernel, and frames t >= mel_len[b] of the mel are zeroed when zero_padded_frames != 0
- * (the reference does so only when B > 1).
+ * materialising [B,T,4d].  MelDecoder.proj (networks.py:292) is row-wise and the length regulator
+ * (networks.py:228-258) is a row gather, so they commute: the projection runs once per PHONEME
+ * (B*N rows, + one row for the zero-padded frames), an integer kernel builds the frame -> row map,
+ * and the first decoder block reads its input / skip rows through that map.  Frames t >= mel_len[b]
+ * of the mel are zeroed when zero_padded_frames != 0 (the reference does so only when B > 1).
+ * Workspace: es_workspace_bytes(m, B, N, T).
  */
 int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T,
                                 const float* fused4, const int32_t* dur_cum, const int32_t* mel_len,
@@ -228,10 +246,6 @@ int es_check_async_errors(void* stream);
 /* Debug aid: when non-NULL, CTA 0 of every subsequent tcgen05 decoder launch writes clock64() stamps
  * [4 roles][32 tiles][8 events] (int64, device memory) -- tools/trace_decoder.py.  NULL turns it off. */
 int es_debug_set_trace(void* dev_buf_i64);
-/* Tests only: run the multi-layer decoder launch with `ctas` CTAs instead of one per SM (0 restores the
- * default), so that small problems exercise its cross-CTA layer hand-off. */
-int es_debug_set_decoder_stack_grid(int ctas);
-
 /* Number of kernels the library has launched since process start (bench.py's gpu_launches). */
 uint64_t es_launch_count(void);
 
@@ -250,7 +264,6 @@ uint64_t es_launch_count(void);
 #define ES_K_DEC_LAYER  8
 #define ES_K_MEL        9
 #define ES_K_POOLMASK   10
-#define ES_K_DEC_STACK  11   /* all depthwise decoder layers + mel head in one persistent launch */
 int es_profile_begin(int max_records);
 int es_profile_end(void);
 int es_profile_collect(int32_t* kinds_host, float* ms_host, int capacity, int* n_out);

@@ -244,37 +244,81 @@ def test_cuda_graph_replay_matches_eager():
     model.check_async_errors()
 
 
-@pytest.mark.parametrize("B,T,ctas", [(3, 700, 7), (5, 333, 4), (2, 1031, 5), (1, 64 * 12, 3)])
-def test_decoder_stack_matches_per_layer_launches(B, T, ctas):
-    """Multi-layer persistent decoder launch (cross-CTA layer hand-off through global flags) against one
-    launch per layer: bit-identical, and both within the mel bar of the oracle.  The CTA count is forced
-    down so that a small problem gives every CTA >= 4 tiles and neighbouring tiles live on different CTAs."""
-    cfg = VARIANTS["tiny"]
-    sd = init_state_dict(cfg, seed=9)
-    model = cuda_model("tiny", sd)
-    rng = np.random.default_rng(B * 1000 + T)
-    feats = rng.standard_normal((B, T, cfg.dx4)).astype(np.float32)
-    x = torch.from_numpy(feats).to(DEV)
+def test_frame_rows_exact_random():
+    """The frame -> table-row map of the gathered decoder entry (es_gather.cu) against the oracle's
+    FeatureUpsampler source indices: bit-exact, including zero-duration phonemes, empty utterances and
+    N beyond the shared-memory staging limit."""
+    model = cuda_model("tiny", init_state_dict(VARIANTS["tiny"], seed=1))
+    model.decoder._backend.ensure(torch.device(DEV))
     lib = _cabi.load()
-    l0 = lib.es_launch_count()
+    rng = np.random.default_rng(321)
+    shapes = [(int(rng.integers(1, 9)), int(rng.integers(1, 300))) for _ in range(20)] + [(2, 9000)]
+    for trial, (B, N) in enumerate(shapes):
+        dur = rng.integers(0, 9, size=(B, N)).astype(np.int32)
+        if trial % 5 == 0:
+            dur[rng.integers(0, B)] = 0
+        if trial % 7 == 0:
+            dur[:, : N // 2] = 0
+        feats = np.zeros((B, N, 4), np.float32)
+        _, _, ml, src = es_oracle.feature_upsampler(feats, np.zeros((B, N, 4), bool), dur)
+        T = int(ml.max())
+        if T == 0:
+            continue
+        want = np.where(src >= 0, src + np.arange(B)[:, None] * N, B * N).astype(np.int32)
+        cum = torch.from_numpy(np.cumsum(dur, axis=1).astype(np.int32)).to(DEV)
+        mlen = torch.from_numpy(ml.astype(np.int32)).to(DEV)
+        rows = torch.empty(B, T, dtype=torch.int32, device=DEV)
+        _cabi.check(lib.es_frame_rows(model.decoder._backend.handle, torch.cuda.current_stream().cuda_stream,
+                                      B, N, T, cum.data_ptr(), mlen.data_ptr(), rows.data_ptr()))
+        assert np.array_equal(npy(rows), want)
+
+
+@pytest.mark.parametrize("vname,B,N,max_dur", [("tiny", 5, 40, 9), ("tiny", 3, 129, 4), ("tiny", 1, 33, 7),
+                                               ("tiny", 4, 64, 40), ("small", 4, 33, 6), ("base", 2, 31, 6)])
+def test_gather_modes_agree(vname, B, N, max_dur):
+    """The three ways of joining the length regulator and the decoder (ES_GATHER_*): projection per frame,
+    projection per phoneme + row-gather kernel, projection per phoneme + gathered loads in the first block.
+    All within the mel bar of the oracle; the two per-phoneme forms are bit-identical."""
+    cfg = VARIANTS[vname]
+    sd = init_state_dict(cfg, seed=31 + N)
+    batch = make_batch(cfg, B, N, seed=N + B, ragged=B > 1, fixed_duration=None, max_dur=max_dur)
+    model = cuda_model(vname, sd)
+    x = to_dev(batch)
+    o = es_oracle.phoneme2mel(batch, sd, train=True)
+    got = {}
     try:
-        _cabi.check(lib.es_debug_set_decoder_stack_grid(ctas))
-        model.decoder.set_decoder_stack(True)
-        with torch.no_grad():
-            got_stack = npy(model.decoder(x))
-        n_stack = lib.es_launch_count() - l0
-        model.decoder.set_decoder_stack(False)
-        l0 = lib.es_launch_count()
-        with torch.no_grad():
-            got_layers = npy(model.decoder(x))
-        n_layers = lib.es_launch_count() - l0
+        for mode in (0, 1, 2):
+            model.decoder.set_gather_mode(mode)
+            with torch.no_grad():
+                got[mode] = npy(model(x, train=True)["mel"])
+            model.check_async_errors()
+            assert np.abs(got[mode] - o["mel"]).max() <= TOL_MEL, mode
     finally:
-        _cabi.check(lib.es_debug_set_decoder_stack_grid(0))
-        model.decoder.set_decoder_stack(False)
-    torch.cuda.synchronize()
-    es.Phoneme2Mel.check_async_errors()
-    assert n_stack == 2 and n_layers == cfg.n_dec_layers + 2, (n_stack, n_layers)   # proj + stack vs proj + L + mel
-    assert np.array_equal(got_stack, got_layers)
-    S = es_oracle._cast_state(sd, np.float32)
-    want = es_oracle.mel_decoder(feats, S, es_oracle.infer_config(S))
-    assert np.abs(got_stack - want).max() <= TOL_MEL
+        model.decoder.set_gather_mode(2)
+    assert np.array_equal(got[1], got[2])
+    assert np.abs(got[0] - got[1]).max() <= 5e-5
+
+
+def test_gather_fused_zero_duration_run():
+    """A 75-phoneme run of zero durations in the middle of an utterance: the distinct table rows of one tile
+    no longer fit the 68-row slot and the gathered layer falls back to one copy per frame (es_umma_dec.cu)."""
+    cfg = VARIANTS["tiny"]
+    sd = init_state_dict(cfg, seed=12)
+    batch = make_batch(cfg, 2, 200, seed=4, ragged=False, fixed_duration=None, max_dur=5)
+    batch["duration"][:, 20:95] = 0
+    batch["duration"][:, 19] = batch["duration"][:, 95] = 3
+    batch["mel_len"] = batch["duration"].sum(1).astype(np.int32)
+    model = cuda_model("tiny", sd)
+    x = to_dev(batch)
+    o = es_oracle.phoneme2mel(batch, sd, train=True)
+    got = {}
+    try:
+        for mode in (1, 2):
+            model.decoder.set_gather_mode(mode)
+            with torch.no_grad():
+                got[mode] = npy(model(x, train=True)["mel"])
+            model.check_async_errors()
+    finally:
+        model.decoder.set_gather_mode(2)
+    assert np.abs(got[2] - o["mel"]).max() <= TOL_MEL
+    assert np.array_equal(got[1], got[2])
