@@ -8,13 +8,13 @@ from typing import Optional
 
 from . import build as _build
 
-ES_ABI_VERSION = 9
+ES_ABI_VERSION = 10
 ES_GATHER_PER_FRAME, ES_GATHER_MATERIALIZE, ES_GATHER_FUSED = 0, 1, 2
 ES_MAX_ENC_BLOCKS = 2
 ES_MAX_DEC_LAYERS = 24
 ES_MAX_DEC_BLOCKS = 8
 KERNEL_KINDS = ["embed", "enc_gemm", "attention", "fuse", "predictor", "variance", "lenreg",
-                "dec_proj", "dec_layer", "mel", "poolmask"]
+                "dec_proj", "dec_layer", "mel", "poolmask", "phoneme"]
 
 _fp = C.c_void_p      # device pointers travel as integers
 
@@ -63,6 +63,7 @@ PROTOTYPES = {
     "es_model_destroy": (None, [_vp]),
     "es_model_set_tensor_core": (_i, [_vp, _i]),
     "es_model_set_decoder_gather": (_i, [_vp, _i]),
+    "es_model_set_fused_phoneme": (_i, [_vp, _i]),
     "es_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "es_encoder_forward": (_i, [_vp, _vp, _i, _i] + [_vp] * 12 + [_vp, _sz]),
     "es_length_regulate": (_i, [_vp, _vp, _i, _i, _i] + [_vp] * 6),

@@ -47,6 +47,7 @@ struct es_model {
     es_weights_t w;
     int use_tensor_core;
     int gather_mode;        // es_model_set_decoder_gather: ES_GATHER_* (how the length regulator meets the decoder)
+    int fused_phoneme;      // es_model_set_fused_phoneme: whole phoneme side in one kernel where supported
     // derived geometry
     int d, C[2], H[2], k[2], hC[2], dx4, dx2, n_layers;
 };
@@ -324,6 +325,7 @@ int es_model_create(const es_config_t* cfg, const es_weights_t* w, es_model_t** 
     m->w = *w;
     m->use_tensor_core = 1;
     m->gather_mode = ES_GATHER_FUSED;
+    m->fused_phoneme = 1;
     m->d = cfg->dim;
     m->C[0] = cfg->dim; m->C[1] = 2 * cfg->dim;
     m->H[0] = cfg->head; m->H[1] = 2 * cfg->head;
@@ -341,6 +343,12 @@ void es_model_destroy(es_model_t* m) { delete m; }
 int es_model_set_tensor_core(es_model_t* m, int enable) {
     ES_CHECK(m, "null model");
     m->use_tensor_core = enable ? 1 : 0;
+    return 0;
+}
+
+int es_model_set_fused_phoneme(es_model_t* m, int enable) {
+    ES_CHECK(m, "null model");
+    m->fused_phoneme = enable ? 1 : 0;
     return 0;
 }
 
@@ -375,6 +383,16 @@ int es_encoder_forward(es_model_t* m, void* stream, int B, int N,
     EncBufs e = plan_encoder(m, a, B, N);
     const int d = m->d, n1 = enc_n1(m, N);
 
+    // tiny geometry, N <= 128: the whole phoneme side in ONE kernel, activations never leave the SM (es_umma_phoneme.cu)
+    if (m->use_tensor_core && m->fused_phoneme) {
+        const int pool = (int)nearbyintf((float)((double)N / (double)n1));
+        int rc;
+        { ProfRange r(ES_K_PHONEME, s);
+          rc = launch_umma_phoneme(m->cfg, m->w, B, N, n1, pool, phoneme, phoneme_mask, pitch_tgt, energy_tgt, dur_tgt,
+                                   pitch_pred, energy_pred, dur_pred, fused4, dur_int, dur_cum, mel_len, e.xm1, e.qkv, s); }
+        if (rc > 0) return 1;
+        if (rc == 0) return 0;
+    }
     // block 0: embedding + merge conv + 1x1 as k table gathers (networks.py:54,64-67)
     { ProfRange r(ES_K_EMBED, s); if (launch_embed_merge(phoneme, m->w.enc[0].merge_w, e.x0, B, N, m->C[0], m->k[0], m->cfg.n_symbols, s)) return 1; }
     if (encoder_block(m, 0, B, N, e.x0, phoneme_mask, e, e.feat0, s)) return 1;

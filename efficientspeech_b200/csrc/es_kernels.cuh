@@ -57,6 +57,13 @@ int launch_umma_rowgemm_batch(const RowGemmParams* ps, const void* const* w_h16,
 // K-streamed row GEMM for the layers outside that envelope (es_umma_wide.cu); -1: not applicable
 int dense_layout(int K, int Nout, int taps, int stride);   // 0 none, 1 resident taps image, 2/3 streamed units (NT 128/256)
 int launch_umma_wide(const RowGemmParams& p, const void* w_units, cudaStream_t s, int nt_force = 0);
+// the whole phoneme side (PhonemeEncoder.forward up to the upsampler) in one kernel for the tiny geometry
+// (es_umma_phoneme.cu); -1: outside its envelope
+bool umma_phoneme_supported(const es_config_t& cfg, const es_weights_t& w, int N);
+int launch_umma_phoneme(const es_config_t& cfg, const es_weights_t& w, int B, int N, int n1, int pool,
+                        const int32_t* ids, const uint8_t* mask, const float* pitch_tgt, const float* energy_tgt,
+                        const int32_t* dur_tgt, float* pitch_pred, float* energy_pred, float* dur_pred, float* fused4,
+                        int32_t* dur_int, int32_t* dur_cum, int32_t* mel_len, float* sc_xm1, float* sc_u, cudaStream_t s);
 // tcgen05 attention (es_umma_attn.cu); -1: outside its envelope (n > 128 or C not in {32, 64})
 int launch_umma_attention(const float* qkv, float* out, int B, int n, int C, int H, float scale, cudaStream_t s);
 

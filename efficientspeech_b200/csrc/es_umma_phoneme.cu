@@ -1,0 +1,772 @@
+// The whole phoneme side of the acoustic path in ONE kernel (sm_100a: tcgen05 + TMEM + bulk copies):
+// PhonemeEncoder.forward up to the feature upsampler (layers/networks.py:336-384) for the tiny
+// geometry (d = 32: C = 32 / 64, heads 1 / 2, kernel 3, expansion 1) and N <= 128 phonemes.
+//
+// The per-layer path spends ~12 us per launch on 18 dependent launches (launch gap, prologue, 3-4 serial
+// 64-row tiles per CTA, drain) for a few hundred KB of activations per utterance.  Here one CTA of 128
+// threads owns one utterance at a time (persistent loop, one CTA per SM) and keeps every activation on
+// chip: thread r <-> phoneme row r <-> TMEM lane r, so LayerNorm / GELU / softmax / the scalar heads are
+// thread-local, and every dense layer is
+//     thread r writes its row of the A operand (split fp16 hi/lo, UMMA canonical K-major row-panel layout)
+//     -> fence + __syncthreads -> one elected thread issues the tcgen05.mma's (M = 128, 3 per K step:
+//     hi*hi + hi*lo + lo*hi) and commits to an mbarrier -> every thread reads its accumulator row out of TMEM.
+// Conv taps are descriptor row shifts over a tile with one zero halo row on each side (es_umma_enc.cu);
+// attention is S = Q K^T, thread-per-row softmax out of TMEM, O = P V (es_umma_attn.cu).  Weights are the
+// same packed split-fp16 images the per-layer kernels use, streamed through two 48 KB shared-memory
+// buffers by bulk copies issued two layers ahead.  Level-1 rows (n1 = ceil(N/2) <= 64) live in threads
+// 0..n1-1; the M = 128 GEMMs simply carry zero rows.  Two small per-utterance scratch arrays in global
+// memory (L2) hand rows between threads where the row -> thread map changes (stride-2 merge conv, the
+// stride-2 transposed-conv scatter of Fuse).
+//
+// Layer list per utterance (reference lines in es_api.cu next to the per-layer launches):
+//   embed+merge0 (3 table gathers) | qkv0, attention0, proj0+res+LN1+mask, conv3(ffn1)+GELU, ffn2+res+LN2+mask |
+//   merge1 (stride 2) | qkv1 (q, k, v), attention1 x 2 heads, proj1+.., ffn1, ffn2 | Fuse (U, A0 + scatter) |
+//   3 predictors x (conv3+ReLU+LN+ReLU, conv3+ReLU+scalar head [+LN2 for duration]) |
+//   bucketize + embeddings + concat -> fused4, duration rounding, block scan -> dur_cum, mel_len.
+#include <math.h>
+#include <string.h>
+
+#include "es_common.cuh"
+#include "es_kernels.cuh"
+#include "es_umma.cuh"
+
+namespace es {
+namespace {
+
+using namespace umma;
+
+constexpr int PM = 128;                          // rows = threads = TMEM lanes
+constexpr int D0 = 32, D1 = 64;                  // channel widths of the two pyramid levels
+constexpr uint32_t PANEL = PM * 16;              // 2048: one K panel (8 elements) of 128 rows, no halo
+constexpr uint32_t XA_LBO = (PM + 2) * 16;       // 2080: one K panel of 130 rows (zero halo row on each side)
+constexpr uint32_t XA_PLANE = 8 * XA_LBO;        // 16640: up to K = 64
+constexpr uint32_t Y1_PLANE = 4 * XA_LBO;        // 8320: K = 32 halo tile
+constexpr uint32_t Y1_TILE = 2 * Y1_PLANE;       // 16640
+constexpr uint32_t WB_BYTES = 48 * 1024;
+
+constexpr uint32_t OFF_OP = 0;                                 // 64 KB: attention Q/K then P | proj1 A tile | predictor y1 tiles
+constexpr uint32_t OFF_VT = OFF_OP + 65536;                    // 16 KB: V^T hi, lo
+constexpr uint32_t OFF_XA = OFF_VT + 16384;                    // halo A tile (hi plane, lo plane)
+constexpr uint32_t OFF_WB = OFF_XA + 2 * XA_PLANE;             // two weight buffers
+constexpr uint32_t OFF_MISC = OFF_WB + 2 * WB_BYTES;           // scan scratch
+constexpr uint32_t OFF_BAR = OFF_MISC + 64;                    // bar_mma, bar_w[2], tmem slot
+constexpr uint32_t PH_SMEM = OFF_BAR + 64;
+static_assert(OFF_WB % 16 == 0 && OFF_XA % 16 == 0, "bulk copies need 16-byte aligned destinations");
+static_assert(PH_SMEM <= 227 * 1024, "shared memory budget");
+static_assert(3 * Y1_TILE <= 65536, "predictor tiles live in the attention region");
+
+constexpr int NW = 15;                           // weight loads per utterance (see wload)
+
+struct PhonemeParams {
+    int B, N, n1, pool, n_symbols;
+    const int32_t* ids;
+    const uint8_t* mask;
+    const float* pitch_tgt; const float* energy_tgt; const int32_t* dur_tgt;
+    es_enc_block_w_t enc[2];
+    const void* fuse_u_h16; const float* fuse_gb; const void* fuse_a0_h16; const float* fuse_c;
+    es_predictor_w_t pred[3];                    // pitch, energy, duration
+    float* pitch_pred; float* energy_pred; float* dur_pred; float* fused4;
+    int32_t* dur_int; int32_t* dur_cum; int32_t* mel_len;
+    float* sc_xm1;                               // [B][n1][64]  block-1 input rows (residual of proj1)
+    float* sc_u;                                 // [B][n1][96]  Fuse: U rows of the half-rate positions
+    float scale_log2e;                           // (C // H)^-0.5 * log2(e): 32^-0.5 at both levels
+    int* err;
+};
+
+__device__ __forceinline__ float ex2f_approx(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+    return e;
+}
+
+#define PHASE_SYNC()               \
+    do {                           \
+        fence_proxy_async_smem();  \
+        tc_fence_before_sync();    \
+        __syncthreads();           \
+        tc_fence_after_sync();     \
+    } while (0)
+
+// K fp32 values of one row -> split fp16 hi/lo rows of a row-panel tile (tile row `trow`)
+template <int K>
+__device__ __forceinline__ void stage_row(uint8_t* tile, uint32_t lbo, uint32_t plane, int trow, const float* v, bool live) {
+#pragma unroll
+    for (int pc = 0; pc < K / 8; ++pc) {
+        float a[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] = live ? v[8 * pc + e] : 0.f;
+        uint4 hi, lo;
+        split8(a, hi, lo);
+        *reinterpret_cast<uint4*>(tile + (uint32_t)pc * lbo + (uint32_t)trow * 16u) = hi;
+        *reinterpret_cast<uint4*>(tile + plane + (uint32_t)pc * lbo + (uint32_t)trow * 16u) = lo;
+    }
+}
+
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tm_load32(uint32_t trow, int col, float* v) {
+    uint32_t rr[32];
+    tmem_ld32(trow + (uint32_t)col, rr);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+}
+
+// D[tmem_d] = A . W^T over `taps` row-shifted views of the A tile (issued by warp 0; `elected` = its issuing lane)
+__device__ __forceinline__ void issue_gemm(bool elected, uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_plane,
+                                           uint32_t w_addr, int K, int N, int taps) {
+    const uint32_t idesc = make_idesc_f16(PM, N);
+    const uint32_t lbo_b = (uint32_t)N * 16u, w_plane = (uint32_t)N * (uint32_t)K * 2u;
+    uint32_t acc = 0;
+    for (int t = 0; t < taps; ++t) {
+        for (int ks = 0; ks < (K >> 4); ++ks) {
+            const uint32_t a_off = (uint32_t)t * 16u + (uint32_t)(2 * ks) * a_lbo;
+            const uint64_t dah = make_smem_desc(a_addr + a_off, a_lbo, 128u);
+            const uint64_t dal = make_smem_desc(a_addr + a_plane + a_off, a_lbo, 128u);
+            const uint32_t b_off = (uint32_t)(t * 2) * w_plane + (uint32_t)(2 * ks) * lbo_b;
+            const uint64_t dbh = make_smem_desc(w_addr + b_off, lbo_b, 128u);
+            const uint64_t dbl = make_smem_desc(w_addr + w_plane + b_off, lbo_b, 128u);
+            if (elected) {
+                mma_f16_ss(tmem_d, dah, dbh, idesc, acc);
+                mma_f16_ss(tmem_d, dah, dbl, idesc, 1u);
+                mma_f16_ss(tmem_d, dal, dbh, idesc, 1u);
+            }
+            acc = 1;
+        }
+    }
+}
+
+// thread-local LayerNorm over n values (two-pass, biased variance, eps 1e-5: nn.LayerNorm)
+template <int NV>
+__device__ __forceinline__ void ln_row(float* v, const float* __restrict__ g, const float* __restrict__ be) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s += v[j];
+    const float mean = s * (1.f / NV);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { const float dlt = v[j] - mean; q = fmaf(dlt, dlt, q); }
+    const float rstd = rsqrtf(q * (1.f / NV) + kLnEps);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = (v[j] - mean) * rstd * __ldg(g + j) + __ldg(be + j);
+}
+
+__device__ __forceinline__ int bucket_left(const float* __restrict__ bins, int nb, float v) {
+    int lo = 0, hi = nb;                          // #{j : bins[j] < v}   (torch.bucketize, right=False; networks.py:130-141)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(bins + mid) < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(PM, 1)
+umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = tid;                                         // this thread's row
+    uint8_t* op = smem + OFF_OP;
+    uint8_t* vt = smem + OFF_VT;
+    uint8_t* xa = smem + OFF_XA;
+    int* s_wtot = reinterpret_cast<int*>(smem + OFF_MISC);
+    const uint32_t bar_mma = smem_u32(smem + OFF_BAR);
+    const uint32_t bar_w = bar_mma + 8;                        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 32);
+    const uint32_t xa_addr = smem_u32(xa), op_addr = smem_u32(op), vt_addr = smem_u32(vt);
+    const uint32_t wb_addr = smem_u32(smem + OFF_WB);
+
+    const int N = p.N, n1 = p.n1;
+    const int my_utts = (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_w = my_utts * NW;
+
+    // weight load g of this CTA (phase g % NW of utterance g / NW) into buffer g & 1; thread 0 only
+    auto wload = [&](int g) {
+        if (g >= total_w) return;
+        const int ph = g % NW;
+        const uint32_t dst = wb_addr + (uint32_t)(g & 1) * WB_BYTES;
+        const uint32_t bar = bar_w + 8u * (uint32_t)(g & 1);
+        auto one = [&](const void* src, uint32_t bytes) {
+            mbar_arrive_expect_tx(bar, bytes);
+            bulk_g2s(dst, src, bytes, bar);
+        };
+        switch (ph) {
+            case 0: one(p.enc[0].qkv_w_h16, 96u * D0 * 4u); break;
+            case 1: one(p.enc[0].proj_w_h16, D0 * D0 * 4u); break;
+            case 2: one(p.enc[0].ffn1_w_h16, 3u * D0 * D0 * 4u); break;
+            case 3: one(p.enc[0].ffn2_w_h16, D0 * D0 * 4u); break;
+            case 4: one(p.enc[1].merge_w_h16, D1 * D0 * 4u); break;
+            case 5: case 6: case 7: {
+                // q | k | v slice (128 of the 384 output rows) of the [2][8][384][8] image -> compact [2][8][128][8]
+                const uint8_t* img = reinterpret_cast<const uint8_t*>(p.enc[1].qkv_w_h16) + (uint32_t)(ph - 5) * 2048u;
+                mbar_arrive_expect_tx(bar, 32768u);
+                for (int pl = 0; pl < 2; ++pl)
+                    for (int pc = 0; pc < 8; ++pc)
+                        bulk_g2s(dst + (uint32_t)pl * 16384u + (uint32_t)pc * 2048u, img + (size_t)pl * 49152u + (size_t)pc * 6144u, 2048u, bar);
+                break;
+            }
+            case 8: one(p.enc[1].proj_w_h16, D1 * 128u * 4u); break;
+            case 9: one(p.enc[1].ffn1_w_h16, 3u * D1 * D1 * 4u); break;
+            case 10: one(p.enc[1].ffn2_w_h16, D1 * D1 * 4u); break;
+            case 11: one(p.fuse_u_h16, 96u * D1 * 4u); break;
+            case 12: one(p.fuse_a0_h16, D0 * D0 * 4u); break;
+            case 13:
+                mbar_arrive_expect_tx(bar, 3u * 12288u);
+                for (int i = 0; i < 3; ++i) bulk_g2s(dst + (uint32_t)i * 12288u, p.pred[i].conv1_w_h16, 12288u, bar);
+                break;
+            default:
+                mbar_arrive_expect_tx(bar, 3u * 12288u);
+                for (int i = 0; i < 3; ++i) bulk_g2s(dst + (uint32_t)i * 12288u, p.pred[i].conv2_w_h16, 12288u, bar);
+                break;
+        }
+    };
+
+    // ---- one-time setup -------------------------------------------------------------------------
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);       // [0,128) S / layer accumulators, [128,512) q | k | v (O over q)
+    if (tid == 0) {
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_w, 1);
+        mbar_init(bar_w + 8, 1);
+        fence_mbar_init();
+    }
+    // zero halo rows (tile rows 0 and 129) of the A tile: never written afterwards
+    if (tid < 32) {
+        const int pc = tid & 7, pl = (tid >> 3) & 1, which = tid >> 4;
+        *reinterpret_cast<uint4*>(xa + (uint32_t)pl * XA_PLANE + (uint32_t)pc * XA_LBO + (which ? (PM + 1) * 16u : 0u)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    if (tid == 0) { wload(0); wload(1); }                      // weights do not depend on the predecessor kernel
+    pdl_launch_dependents();
+    pdl_wait();
+
+    const bool elected = (warp == 0) && elect_one();
+    bool failed = false;
+    uint32_t mph = 0;                                           // bar_mma phase parity
+    int wg = 0;                                                 // next weight phase to be consumed (global index)
+
+    // warp 0 waits for weight load `wg`; returns its shared-memory address
+    auto w_wait = [&]() -> uint32_t {
+        if (warp == 0 && !mbar_wait(bar_w + 8u * (uint32_t)(wg & 1), (uint32_t)(wg >> 1) & 1u)) failed = true;
+        return wb_addr + (uint32_t)(wg & 1) * WB_BYTES;
+    };
+    // commit the issued MMAs, wait for them, then refill the weight buffer they used (two phases ahead)
+    auto gemm_done = [&](bool used_weights) {
+        if (warp == 0) {
+            if (elected) mma_commit(bar_mma);
+            __syncwarp();
+        }
+        if (!mbar_wait(bar_mma, mph)) failed = true;
+        mph ^= 1;
+        tc_fence_after_sync();
+        if (used_weights) {
+            if (tid == 0) wload(wg + 2);
+            ++wg;
+        }
+    };
+
+    // softmax(Q K^T) V for one head: q/k/v rows are in TMEM columns qc/kc/vc (C wide), output -> columns oc
+    auto attention = [&](const int C, const int NK, const int n, const int qc, const int kc, const int vc, const int oc) {
+        const uint32_t qk_plane = (uint32_t)(C >> 3) * PANEL;
+        const uint32_t vt_lbo = (uint32_t)C * 16u, vt_plane = (uint32_t)(NK >> 3) * vt_lbo;
+        const uint32_t p_plane = (uint32_t)(NK >> 3) * PANEL;
+        // 1. stage Q, K (row panels) and V^T; rows >= n are zero rows of the GEMM that produced them
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            float q[32], k[32], v[32];
+            tm_load32(trow, qc + c0, q);
+            tm_load32(trow, kc + c0, k);
+            tm_load32(trow, vc + c0, v);
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc) {
+                float a[8];
+                uint4 hi, lo;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] = q[8 * pc + e];
+                split8(a, hi, lo);
+                const uint32_t off = (uint32_t)((c0 >> 3) + pc) * PANEL + (uint32_t)r * 16u;
+                *reinterpret_cast<uint4*>(op + off) = hi;
+                *reinterpret_cast<uint4*>(op + qk_plane + off) = lo;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] = k[8 * pc + e];
+                split8(a, hi, lo);
+                *reinterpret_cast<uint4*>(op + 2 * qk_plane + off) = hi;
+                *reinterpret_cast<uint4*>(op + 3 * qk_plane + off) = lo;
+            }
+            if (r < NK) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const __half vh = __float2half_rn(v[e]);
+                    const __half vl = __float2half_rn(v[e] - __half2float(vh));
+                    const uint32_t off = (uint32_t)(r >> 3) * vt_lbo + (uint32_t)(c0 + e) * 16u + (uint32_t)(r & 7) * 2u;
+                    *reinterpret_cast<__half*>(vt + off) = vh;
+                    *reinterpret_cast<__half*>(vt + vt_plane + off) = vl;
+                }
+            }
+        }
+        PHASE_SYNC();
+        // 2. S = Q K^T  -> columns [0, NK)
+        if (warp == 0) {
+            const uint32_t idesc = make_idesc_f16(PM, NK);
+            for (int ks = 0; ks < (C >> 4); ++ks) {
+                const uint32_t o = (uint32_t)(2 * ks) * PANEL;
+                const uint64_t dqh = make_smem_desc(op_addr + o, PANEL, 128u), dql = make_smem_desc(op_addr + qk_plane + o, PANEL, 128u);
+                const uint64_t dkh = make_smem_desc(op_addr + 2 * qk_plane + o, PANEL, 128u);
+                const uint64_t dkl = make_smem_desc(op_addr + 3 * qk_plane + o, PANEL, 128u);
+                if (elected) {
+                    mma_f16_ss(tmem, dqh, dkh, idesc, ks > 0 ? 1u : 0u);
+                    mma_f16_ss(tmem, dqh, dkl, idesc, 1u);
+                    mma_f16_ss(tmem, dql, dkh, idesc, 1u);
+                }
+            }
+        }
+        gemm_done(false);
+        // 3. softmax over the n keys (unmasked: blocks.py:59-63), P -> split fp16 over the dead Q/K tiles
+        {
+            const float sc = p.scale_log2e;
+            float mx = -INFINITY;
+            for (int c0 = 0; c0 < NK; c0 += 32) {
+                float s[32];
+                tm_load32(trow, c0, s);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < n) mx = fmaxf(mx, s[j]);
+            }
+            const float nm = -mx * sc;
+            float sum = 0.f;
+            for (int c0 = 0; c0 < NK; c0 += 32) {
+                float s[32];
+                tm_load32(trow, c0, s);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float e = ex2f_approx(fmaf(s[j], sc, nm));
+                    if (c0 + j < n) sum += e;
+                }
+            }
+            const float inv = 1.f / sum;
+            for (int c0 = 0; c0 < NK; c0 += 32) {
+                float s[32];
+                tm_load32(trow, c0, s);
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    float pv[8];
+#pragma unroll
+                    for (int e8 = 0; e8 < 8; ++e8) {
+                        const int col = c0 + j8 * 8 + e8;
+                        pv[e8] = col < n ? ex2f_approx(fmaf(s[j8 * 8 + e8], sc, nm)) * inv : 0.f;
+                    }
+                    uint4 hi, lo;
+                    split8(pv, hi, lo);
+                    const uint32_t off = (uint32_t)((c0 >> 3) + j8) * PANEL + (uint32_t)r * 16u;
+                    *reinterpret_cast<uint4*>(op + off) = hi;
+                    *reinterpret_cast<uint4*>(op + p_plane + off) = lo;
+                }
+            }
+        }
+        PHASE_SYNC();
+        // 4. O = P V  -> columns [oc, oc + C)
+        if (warp == 0) {
+            const uint32_t idesc = make_idesc_f16(PM, C);
+            for (int ks = 0; ks < (NK >> 4); ++ks) {
+                const uint64_t dph = make_smem_desc(op_addr + (uint32_t)(2 * ks) * PANEL, PANEL, 128u);
+                const uint64_t dpl = make_smem_desc(op_addr + p_plane + (uint32_t)(2 * ks) * PANEL, PANEL, 128u);
+                const uint64_t dvh = make_smem_desc(vt_addr + (uint32_t)(2 * ks) * vt_lbo, vt_lbo, 128u);
+                const uint64_t dvl = make_smem_desc(vt_addr + vt_plane + (uint32_t)(2 * ks) * vt_lbo, vt_lbo, 128u);
+                if (elected) {
+                    mma_f16_ss(tmem + (uint32_t)oc, dph, dvh, idesc, ks > 0 ? 1u : 0u);
+                    mma_f16_ss(tmem + (uint32_t)oc, dph, dvl, idesc, 1u);
+                    mma_f16_ss(tmem + (uint32_t)oc, dpl, dvh, idesc, 1u);
+                }
+            }
+        }
+        gemm_done(false);
+    };
+
+    for (int ui = 0; ui < my_utts; ++ui) {
+        const int b = (int)blockIdx.x + ui * (int)gridDim.x;
+        const size_t row = (size_t)b * N + r;
+        const bool act0 = r < N, act1 = r < n1;
+        const bool pad0 = act0 && p.mask && p.mask[row];
+        bool pad1 = false;                                      // pooled mask of block 1 (blocks.py:51-57)
+        if (act1 && p.mask) {
+            for (int q = 0; q < p.pool; ++q) {
+                const int t = r * p.pool + q;
+                pad1 = pad1 || (t < N ? p.mask[(size_t)b * N + t] != 0 : true);
+            }
+        }
+        const float* xm1_row = p.sc_xm1 + ((size_t)b * n1 + r) * D1;   // valid for r < n1
+
+        // ================================================================= block 0
+        // x0 = sum_tau Tab[tau][id[t + tau - 1]]   (embedding + merge conv + 1x1 folded into 3 gather tables)
+        float x0[D0];
+#pragma unroll
+        for (int c = 0; c < D0; ++c) x0[c] = 0.f;
+        if (act0) {
+            for (int tau = 0; tau < 3; ++tau) {
+                const int ti = r + tau - 1;
+                if (ti < 0 || ti >= N) continue;
+                int id = __ldg(p.ids + (size_t)b * N + ti);
+                id = min(max(id, 0), p.n_symbols - 1);
+                const float4* tp = reinterpret_cast<const float4*>(p.enc[0].merge_w + ((size_t)tau * p.n_symbols + id) * D0);
+#pragma unroll
+                for (int c4 = 0; c4 < D0 / 4; ++c4) {
+                    const float4 v = __ldg(tp + c4);
+                    x0[4 * c4] += v.x; x0[4 * c4 + 1] += v.y; x0[4 * c4 + 2] += v.z; x0[4 * c4 + 3] += v.w;
+                }
+            }
+        }
+        stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, x0, act0);
+        PHASE_SYNC();
+        {   // qkv0: [32] -> [96] into columns [128, 224)
+            const uint32_t w = w_wait();
+            if (warp == 0) issue_gemm(elected, tmem + 128, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, 96, 1);
+            gemm_done(true);
+        }
+        attention(D0, PM, N, 128, 160, 192, 128);
+        float x1[D0];
+        {   // proj0 + residual + LN1 + mask
+            float o[D0];
+            tm_load32(trow, 128, o);
+            stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, o, act0);
+            PHASE_SYNC();
+            const uint32_t w = w_wait();
+            if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
+            gemm_done(true);
+            tm_load32(trow, 0, x1);
+#pragma unroll
+            for (int c = 0; c < D0; ++c) x1[c] += __ldg(p.enc[0].proj_b + c) + x0[c];
+            ln_row<D0>(x1, p.enc[0].ln1_g, p.enc[0].ln1_b);
+            if (pad0) {
+#pragma unroll
+                for (int c = 0; c < D0; ++c) x1[c] = 0.f;
+            }
+            stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, x1, act0);
+            PHASE_SYNC();
+        }
+        float f0[D0];
+        {   // MixFFN: conv3 (mlp1 folded) + GELU, mlp2 + residual + LN2 + mask
+            uint32_t w = w_wait();
+            if (warp == 0) issue_gemm(elected, tmem, xa_addr, XA_LBO, XA_PLANE, w, D0, D0, 3);
+            gemm_done(true);
+            float h[D0];
+            tm_load32(trow, 0, h);
+            const float m0 = (r - 1 >= 0 && r - 1 < N) ? 1.f : 0.f, m2 = (r + 1 < N) ? 1.f : 0.f;
+#pragma unroll
+            for (int c = 0; c < D0; ++c) {
+                float v = h[c] + __ldg(p.enc[0].ffn1_b + c);
+                v = fmaf(m0, __ldg(p.enc[0].ffn1_tapb + c), v);
+                v += __ldg(p.enc[0].ffn1_tapb + D0 + c);
+                v = fmaf(m2, __ldg(p.enc[0].ffn1_tapb + 2 * D0 + c), v);
+                h[c] = gelu_erf_f(v);
+            }
+            stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, h, act0);
+            PHASE_SYNC();
+            w = w_wait();
+            if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
+            gemm_done(true);
+            tm_load32(trow, 0, f0);
+#pragma unroll
+            for (int c = 0; c < D0; ++c) f0[c] += __ldg(p.enc[0].ffn2_b + c) + x1[c];
+            ln_row<D0>(f0, p.enc[0].ln2_g, p.enc[0].ln2_b);
+            if (pad0) {
+#pragma unroll
+                for (int c = 0; c < D0; ++c) f0[c] = 0.f;
+            }
+            stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, f0, act0);
+            PHASE_SYNC();
+        }
+        // ================================================================= block 1
+        {   // merge conv (1 tap, stride 2): xm1[j] = W feat0[2j]; computed for every row, even rows are kept
+            const uint32_t w = w_wait();
+            if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D1, 1);
+            gemm_done(true);
+            float y[D1];
+            tm_load32(trow, 0, y);
+            tm_load32(trow, 32, y + 32);
+            if (act0 && !(r & 1)) {
+                const int j = r >> 1;                            // < n1
+                float4* dst = reinterpret_cast<float4*>(p.sc_xm1 + ((size_t)b * n1 + j) * D1);
+#pragma unroll
+                for (int c4 = 0; c4 < D1 / 4; ++c4) dst[c4] = make_float4(y[4 * c4], y[4 * c4 + 1], y[4 * c4 + 2], y[4 * c4 + 3]);
+                stage_row<D1>(xa, XA_LBO, XA_PLANE, j + 1, y, true);
+            }
+            if (r >= n1) stage_row<D1>(xa, XA_LBO, XA_PLANE, r + 1, y, false);      // zero rows n1..127
+            PHASE_SYNC();
+        }
+        for (int s = 0; s < 3; ++s) {   // q | k | v of both heads: [64] -> [128] into columns 128 + 128 s
+            const uint32_t w = w_wait();
+            if (warp == 0) issue_gemm(elected, tmem + 128 + 128 * s, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, 128, 1);
+            gemm_done(true);
+        }
+        for (int hd = 0; hd < 2; ++hd) attention(D1, 64, n1, 128 + 64 * hd, 256 + 64 * hd, 384 + 64 * hd, 128 + 64 * hd);
+        float x1b[D1];
+        {   // proj1: A = [O_0 | O_1] (K = 128) in the attention region; + residual + LN1 + mask
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                float o[32];
+                tm_load32(trow, 128 + c0, o);
+                stage_row<32>(op + (uint32_t)(c0 >> 3) * PANEL, PANEL, 16 * PANEL, r, o, act1);
+            }
+            PHASE_SYNC();
+            const uint32_t w = w_wait();
+            if (warp == 0) issue_gemm(elected, tmem, op_addr, PANEL, 16 * PANEL, w, 128, D1, 1);
+            gemm_done(true);
+            tm_load32(trow, 0, x1b);
+            tm_load32(trow, 32, x1b + 32);
+            if (act1) {
+                const float4* rp = reinterpret_cast<const float4*>(xm1_row);
+#pragma unroll
+                for (int c4 = 0; c4 < D1 / 4; ++c4) {
+                    const float4 v = __ldcg(rp + c4);
+                    x1b[4 * c4] += v.x; x1b[4 * c4 + 1] += v.y; x1b[4 * c4 + 2] += v.z; x1b[4 * c4 + 3] += v.w;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < D1; ++c) x1b[c] += __ldg(p.enc[1].proj_b + c);
+            ln_row<D1>(x1b, p.enc[1].ln1_g, p.enc[1].ln1_b);
+            if (pad1) {
+#pragma unroll
+                for (int c = 0; c < D1; ++c) x1b[c] = 0.f;
+            }
+            stage_row<D1>(xa, XA_LBO, XA_PLANE, r + 1, x1b, act1);
+            PHASE_SYNC();
+        }
+        {   // MixFFN of block 1
+            uint32_t w = w_wait();
+            if (warp == 0) issue_gemm(elected, tmem, xa_addr, XA_LBO, XA_PLANE, w, D1, D1, 3);
+            gemm_done(true);
+            float h[D1];
+            tm_load32(trow, 0, h);
+            tm_load32(trow, 32, h + 32);
+            const float m0 = (r - 1 >= 0 && r - 1 < n1) ? 1.f : 0.f, m2 = (r + 1 < n1) ? 1.f : 0.f;
+#pragma unroll
+            for (int c = 0; c < D1; ++c) {
+                float v = h[c] + __ldg(p.enc[1].ffn1_b + c);
+                v = fmaf(m0, __ldg(p.enc[1].ffn1_tapb + c), v);
+                v += __ldg(p.enc[1].ffn1_tapb + D1 + c);
+                v = fmaf(m2, __ldg(p.enc[1].ffn1_tapb + 2 * D1 + c), v);
+                h[c] = gelu_erf_f(v);
+            }
+            stage_row<D1>(xa, XA_LBO, XA_PLANE, r + 1, h, act1);
+            PHASE_SYNC();
+            w = w_wait();
+            if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, D1, 1);
+            gemm_done(true);
+            tm_load32(trow, 0, h);
+            tm_load32(trow, 32, h + 32);
+#pragma unroll
+            for (int c = 0; c < D1; ++c) h[c] += __ldg(p.enc[1].ffn2_b + c) + x1b[c];
+            ln_row<D1>(h, p.enc[1].ln2_g, p.enc[1].ln2_b);        // feat1
+            if (pad1) {
+#pragma unroll
+                for (int c = 0; c < D1; ++c) h[c] = 0.f;
+            }
+            stage_row<D1>(xa, XA_LBO, XA_PLANE, r + 1, h, act1);
+            PHASE_SYNC();
+        }
+        // ================================================================= Fuse (networks.py:189-219, folded)
+        float fz[D0];
+        {
+            uint32_t w = w_wait();                               // U = feat1 [G_0 | G_1 | G_2] + [g_0 | g_1 | g_2]
+            if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, 96, 1);
+            gemm_done(true);
+#pragma unroll 1
+            for (int c0 = 0; c0 < 96; c0 += 32) {
+                float u[32];
+                tm_load32(trow, c0, u);
+                if (act1) {
+                    float4* dst = reinterpret_cast<float4*>(p.sc_u + ((size_t)b * n1 + r) * 96 + c0);
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4)
+                        dst[c4] = make_float4(u[4 * c4] + __ldg(p.fuse_gb + c0 + 4 * c4), u[4 * c4 + 1] + __ldg(p.fuse_gb + c0 + 4 * c4 + 1),
+                                              u[4 * c4 + 2] + __ldg(p.fuse_gb + c0 + 4 * c4 + 2), u[4 * c4 + 3] + __ldg(p.fuse_gb + c0 + 4 * c4 + 3));
+                }
+            }
+            stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, f0, act0);
+            PHASE_SYNC();                                        // also publishes the U rows to the CTA
+            w = w_wait();                                        // fused = mask(c + A0 feat0 + stride-2 scatter of U)
+            if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
+            gemm_done(true);
+            tm_load32(trow, 0, fz);
+#pragma unroll
+            for (int c = 0; c < D0; ++c) fz[c] += __ldg(p.fuse_c + c);
+            if (act0) {
+                for (int tau = r & 1; tau < 3; tau += 2) {
+                    const int j = (r - tau) >> 1;
+                    if (r < tau || j >= n1) continue;
+                    const float4* up = reinterpret_cast<const float4*>(p.sc_u + ((size_t)b * n1 + j) * 96 + tau * D0);
+#pragma unroll
+                    for (int c4 = 0; c4 < D0 / 4; ++c4) {
+                        const float4 v = __ldcg(up + c4);
+                        fz[4 * c4] += v.x; fz[4 * c4 + 1] += v.y; fz[4 * c4 + 2] += v.z; fz[4 * c4 + 3] += v.w;
+                    }
+                }
+            }
+            if (pad0) {
+#pragma unroll
+                for (int c = 0; c < D0; ++c) fz[c] = 0.f;
+            }
+            if (act0) {
+                float4* dst = reinterpret_cast<float4*>(p.fused4 + row * 128);
+#pragma unroll
+                for (int c4 = 0; c4 < D0 / 4; ++c4) dst[c4] = make_float4(fz[4 * c4], fz[4 * c4 + 1], fz[4 * c4 + 2], fz[4 * c4 + 3]);
+            }
+            stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, fz, act0);
+            // halo rows of the three predictor tiles (the attention region is free from here on)
+            if (tid < 48) {
+                const int i = tid >> 4, pc = tid & 3, pl = (tid >> 2) & 1, which = (tid >> 3) & 1;
+                *reinterpret_cast<uint4*>(op + (uint32_t)i * Y1_TILE + (uint32_t)pl * Y1_PLANE + (uint32_t)pc * XA_LBO +
+                                          (which ? (PM + 1) * 16u : 0u)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            PHASE_SYNC();
+        }
+        // ================================================================= predictors (networks.py:151-165)
+        float pred[3];
+        {
+            uint32_t w = w_wait();                               // conv1 of the three predictors -> columns 0 | 32 | 64
+            if (warp == 0)
+                for (int i = 0; i < 3; ++i) issue_gemm(elected, tmem + 32 * i, xa_addr, XA_LBO, XA_PLANE, w + (uint32_t)i * 12288u, D0, D0, 3);
+            gemm_done(true);
+#pragma unroll 1
+            for (int i = 0; i < 3; ++i) {
+                float y[D0];
+                tm_load32(trow, 32 * i, y);
+#pragma unroll
+                for (int c = 0; c < D0; ++c) y[c] = fmaxf(y[c] + __ldg(p.pred[i].conv1_b + c), 0.f);
+                ln_row<D0>(y, p.pred[i].ln1_g, p.pred[i].ln1_b);
+#pragma unroll
+                for (int c = 0; c < D0; ++c) y[c] = fmaxf(y[c], 0.f);
+                stage_row<D0>(op + (uint32_t)i * Y1_TILE, XA_LBO, Y1_PLANE, r + 1, y, act0);
+            }
+            PHASE_SYNC();
+            w = w_wait();                                        // conv2 + ReLU, scalar head on the pre-LN2 values
+            if (warp == 0)
+                for (int i = 0; i < 3; ++i)
+                    issue_gemm(elected, tmem + 32 * i, op_addr + (uint32_t)i * Y1_TILE, XA_LBO, Y1_PLANE, w + (uint32_t)i * 12288u, D0, D0, 3);
+            gemm_done(true);
+#pragma unroll 1
+            for (int i = 0; i < 3; ++i) {
+                float y[D0];
+                tm_load32(trow, 32 * i, y);
+                float dot = 0.f;
+#pragma unroll
+                for (int c = 0; c < D0; ++c) {
+                    y[c] = fmaxf(y[c] + __ldg(p.pred[i].conv2_b + c), 0.f);
+                    dot = fmaf(y[c], __ldg(p.pred[i].lin_w + c), dot);
+                }
+                dot += __ldg(p.pred[i].lin_b);
+                if (i == 2) {
+                    dot = fmaxf(dot, 0.f);                       // duration: extra ReLU (networks.py:161-163)
+                    ln_row<D0>(y, p.pred[2].ln2_g, p.pred[2].ln2_b);   // features = LN2(y), consumed for duration only
+                    if (act0) {
+                        float4* dst = reinterpret_cast<float4*>(p.fused4 + row * 128 + 3 * D0);
+#pragma unroll
+                        for (int c4 = 0; c4 < D0 / 4; ++c4)
+                            dst[c4] = pad0 ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(y[4 * c4], y[4 * c4 + 1], y[4 * c4 + 2], y[4 * c4 + 3]);
+                    }
+                }
+                pred[i] = dot;
+            }
+            if (act0) {
+                p.pitch_pred[row] = pred[0];
+                p.energy_pred[row] = pred[1];
+                p.dur_pred[row] = pred[2];
+            }
+        }
+        // ================================================================= variance embeddings, durations, scan
+        {
+            int dv = 0;
+            if (act0) {
+                float df = p.dur_tgt ? (float)p.dur_tgt[row] : rintf(pred[2]);       // torch.round: half to even (networks.py:379)
+                if (pad0) df = 0.f;
+                df = fminf(fmaxf(df, 0.f), 65535.f);
+                dv = (int)df;
+                p.dur_int[row] = dv;
+                const float pv = p.pitch_tgt ? p.pitch_tgt[row] : pred[0];
+                const float ev = p.energy_tgt ? p.energy_tgt[row] : pred[1];
+                const int pi = bucket_left(p.pred[0].bins, D0 - 1, pv);
+                const int ei = bucket_left(p.pred[1].bins, D0 - 1, ev);
+                const float4* pt = reinterpret_cast<const float4*>(p.pred[0].table + (size_t)pi * D0);
+                const float4* et = reinterpret_cast<const float4*>(p.pred[1].table + (size_t)ei * D0);
+                float4* dp = reinterpret_cast<float4*>(p.fused4 + row * 128 + D0);
+                float4* de = reinterpret_cast<float4*>(p.fused4 + row * 128 + 2 * D0);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c4 = 0; c4 < D0 / 4; ++c4) {
+                    dp[c4] = pad0 ? z : __ldg(pt + c4);
+                    de[c4] = pad0 ? z : __ldg(et + c4);
+                }
+            }
+            int incl = dv;                                      // warp-shuffle inclusive scan, then the 4 warp totals
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (lane == 31) s_wtot[warp] = incl;
+            __syncthreads();
+            int prefix = 0;
+            for (int w = 0; w < warp; ++w) prefix += s_wtot[w];
+            if (act0) p.dur_cum[row] = prefix + incl;
+            if (tid == PM - 1) p.mel_len[b] = prefix + incl;
+            // s_wtot is rewritten only after several __syncthreads of the next utterance
+        }
+    }
+
+    if (failed) atomicExch(p.err, 1);
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+bool umma_phoneme_supported(const es_config_t& cfg, const es_weights_t& w, int N) {
+    if (cfg.dim != D0 || cfg.head != 1 || cfg.kernel_size != 3 || cfg.expansion != 1) return false;
+    if (N < 2 || N > PM) return false;
+    if (!w.enc[0].qkv_w_h16 || !w.enc[0].proj_w_h16 || !w.enc[0].ffn1_w_h16 || !w.enc[0].ffn2_w_h16) return false;
+    if (!w.enc[1].merge_w_h16 || !w.enc[1].qkv_w_h16 || !w.enc[1].proj_w_h16 || !w.enc[1].ffn1_w_h16 || !w.enc[1].ffn2_w_h16) return false;
+    if (!w.fuse_u_h16 || !w.fuse_a0_h16) return false;
+    const es_predictor_w_t* pr[3] = {&w.pitch, &w.energy, &w.duration};
+    for (int i = 0; i < 3; ++i) if (!pr[i]->conv1_w_h16 || !pr[i]->conv2_w_h16) return false;
+    return w.pitch.bins && w.pitch.table && w.energy.bins && w.energy.table;
+}
+
+// sc_xm1: B*n1*64 floats, sc_u: B*n1*96 floats of scratch.  -1: outside the kernel's envelope.
+int launch_umma_phoneme(const es_config_t& cfg, const es_weights_t& w, int B, int N, int n1, int pool,
+                        const int32_t* ids, const uint8_t* mask, const float* pitch_tgt, const float* energy_tgt,
+                        const int32_t* dur_tgt, float* pitch_pred, float* energy_pred, float* dur_pred, float* fused4,
+                        int32_t* dur_int, int32_t* dur_cum, int32_t* mel_len, float* sc_xm1, float* sc_u, cudaStream_t s) {
+    if (!umma_phoneme_supported(cfg, w, N) || n1 > 64 || n1 < 1) return -1;
+    int* err_flag = umma_err_flag();
+    ES_CHECK(err_flag, "cannot allocate the device error flag");
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        ES_CUDA(cudaGetDevice(&dev));
+        ES_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        ES_CUDA(cudaFuncSetAttribute(umma_phoneme_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
+        attr_set = true;
+    }
+    PhonemeParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.N = N; p.n1 = n1; p.pool = pool; p.n_symbols = cfg.n_symbols;
+    p.ids = ids; p.mask = mask; p.pitch_tgt = pitch_tgt; p.energy_tgt = energy_tgt; p.dur_tgt = dur_tgt;
+    p.enc[0] = w.enc[0]; p.enc[1] = w.enc[1];
+    p.fuse_u_h16 = w.fuse_u_h16; p.fuse_gb = w.fuse_gb; p.fuse_a0_h16 = w.fuse_a0_h16; p.fuse_c = w.fuse_c;
+    p.pred[0] = w.pitch; p.pred[1] = w.energy; p.pred[2] = w.duration;
+    p.pitch_pred = pitch_pred; p.energy_pred = energy_pred; p.dur_pred = dur_pred; p.fused4 = fused4;
+    p.dur_int = dur_int; p.dur_cum = dur_cum; p.mel_len = mel_len;
+    p.sc_xm1 = sc_xm1; p.sc_u = sc_u;
+    p.scale_log2e = 1.4426950408889634f / sqrtf(32.f);
+    p.err = err_flag;
+    const int grid = B < n_sm ? B : n_sm;
+    ES_CUDA(launch_pdl(umma_phoneme_kernel, grid, PM, PH_SMEM, s, p));
+    ES_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace es

@@ -153,6 +153,7 @@ class _Backend:
         self.tensor_core = True
         # ES_DEC_GATHER_MODE (0/1/2) overrides the default for A/B runs of the same command line
         self.gather_mode = int(os.environ.get("ES_DEC_GATHER_MODE", _cabi.ES_GATHER_FUSED))
+        self.fused_phoneme = os.environ.get("ES_FUSED_PHONEME", "1") != "0"
 
     def __del__(self):
         try:
@@ -168,7 +169,7 @@ class _Backend:
 
     def ensure(self, device: torch.device) -> C.c_void_p:
         params = list(self.owner.parameters())
-        key = (str(device), self.tensor_core, self.gather_mode) + \
+        key = (str(device), self.tensor_core, self.gather_mode, self.fused_phoneme) + \
             tuple((p.data_ptr(), p._version) for p in params)
         if key == self.key:
             return self.handle
@@ -259,6 +260,7 @@ class _Backend:
         _cabi.check(lib.es_model_create(C.byref(cc), C.byref(W), C.byref(h)))
         _cabi.check(lib.es_model_set_tensor_core(h, 1 if self.tensor_core else 0))
         _cabi.check(lib.es_model_set_decoder_gather(h, int(self.gather_mode)))
+        _cabi.check(lib.es_model_set_fused_phoneme(h, 1 if self.fused_phoneme else 0))
         self.handle = h
         self.key = key
         return h
@@ -380,6 +382,11 @@ class PhonemeEncoder(nn.Module):
         # True: forward() materialises "features"/"masks" like the reference.  Phoneme2Mel sets
         # it per call: the decoder consumes the un-expanded tensors, so inference never needs them.
         self.materialize_features = True
+
+    def set_fused_phoneme(self, enable: bool) -> None:
+        """True (default): the whole phoneme side runs as ONE kernel when the geometry allows it (tiny,
+        N <= 128; include/es_b200.h: es_model_set_fused_phoneme); False: one launch per layer."""
+        self._backend.fused_phoneme = bool(enable)
 
     def _core(self, x, train):
         phoneme = x["phoneme"]

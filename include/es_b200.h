@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ES_ABI_VERSION 9
+#define ES_ABI_VERSION 10
 #define ES_MAX_ENC_BLOCKS 2
 #define ES_MAX_DEC_LAYERS 24
 #define ES_MAX_DEC_BLOCKS 8
@@ -152,6 +152,11 @@ int  es_model_create(const es_config_t* cfg, const es_weights_t* w, es_model_t**
 void es_model_destroy(es_model_t* m);
 /* 0: SIMT fp32 kernels everywhere; 1 (default): tcgen05 split-fp16 decoder layers where supported */
 int  es_model_set_tensor_core(es_model_t* m, int enable);
+/* 1 (default): es_encoder_forward runs the whole phoneme side as ONE kernel (one CTA per utterance, every
+ * activation on chip) when the geometry allows it: dim 32, head 1, kernel_size 3, expansion 1 (tiny), 2 <= N <= 128.
+ * 0: one launch per layer, as for every other geometry.  Same function, same parity bars. */
+int  es_model_set_fused_phoneme(es_model_t* m, int enable);
+
 /* How es_decoder_forward_gathered joins the length regulator and the decoder (default ES_GATHER_FUSED):
  *   ES_GATHER_PER_FRAME    projection GEMM per frame with the gather in its operand load (first version)
  *   ES_GATHER_MATERIALIZE  projection per phoneme, then a row-gather kernel writes skip [B,T,dx2]
@@ -264,6 +269,7 @@ uint64_t es_launch_count(void);
 #define ES_K_DEC_LAYER  8
 #define ES_K_MEL        9
 #define ES_K_POOLMASK   10
+#define ES_K_PHONEME    11   /* whole phoneme side in one launch (es_umma_phoneme.cu) */
 int es_profile_begin(int max_records);
 int es_profile_end(void);
 int es_profile_collect(int32_t* kinds_host, float* ms_host, int capacity, int* n_out);

@@ -322,3 +322,41 @@ def test_gather_fused_zero_duration_run():
         model.decoder.set_gather_mode(2)
     assert np.abs(got[2] - o["mel"]).max() <= TOL_MEL
     assert np.array_equal(got[1], got[2])
+
+
+@pytest.mark.parametrize("B,N,ragged,train", [(5, 40, True, True), (3, 128, True, False), (1, 19, False, True),
+                                              (150, 50, True, True), (2, 2, False, False), (4, 127, True, True),
+                                              (300, 9, True, False)])
+def test_fused_phoneme_kernel_matches_per_layer(B, N, ragged, train):
+    """The one-kernel phoneme side (es_umma_phoneme.cu, tiny geometry, N <= 128) against the per-layer launches:
+    integers identical, floats within fp32 rounding of each other, and the end-to-end mel within the bar of the
+    oracle.  B > 148 makes CTAs loop over several utterances; odd N exercises the ragged half-rate level."""
+    cfg = VARIANTS["tiny"]
+    sd = init_state_dict(cfg, seed=40 + N)
+    batch = make_batch(cfg, B, N, seed=B + 3 * N, ragged=ragged, fixed_duration=None, max_dur=5)
+    model = cuda_model("tiny", sd)
+    x = to_dev(batch)
+    lib = _cabi.load()
+    out = {}
+    try:
+        for fused in (True, False):
+            model.encoder.set_fused_phoneme(fused)
+            l0 = lib.es_launch_count()
+            with torch.no_grad():
+                y = model.encoder(x, train=train)
+            out[fused] = {k: npy(y[k]) for k in ("pitch", "energy", "duration", "mel_len", "_fused4", "_dur_int", "_dur_cum")}
+            out[fused]["launches"] = lib.es_launch_count() - l0
+            model.check_async_errors()
+    finally:
+        model.encoder.set_fused_phoneme(True)
+    assert out[True]["launches"] < out[False]["launches"] and out[True]["launches"] <= 2      # fused kernel (+ length regulator)
+    for k in ("mel_len", "_dur_int", "_dur_cum"):
+        assert np.array_equal(out[True][k], out[False][k]), k
+    for k in ("pitch", "energy", "duration"):
+        assert np.abs(out[True][k] - out[False][k]).max() <= 2e-5, k
+    assert np.abs(out[True]["_fused4"] - out[False]["_fused4"]).max() <= 5e-5
+    if B <= 8:
+        o = es_oracle.phoneme2mel(batch, sd, train=train)
+        with torch.no_grad():
+            mel = model(x, train=True)["mel"] if train else model(x, train=False)[0]
+        assert np.abs(npy(mel) - o["mel"]).max() <= TOL_MEL
