@@ -3,19 +3,25 @@
 // geometry (d = 32: C = 32 / 64, heads 1 / 2, kernel 3, expansion 1) and N <= 128 phonemes.
 //
 // The per-layer path spends ~12 us per launch on 18 dependent launches (launch gap, prologue, 3-4 serial
-// 64-row tiles per CTA, drain) for a few hundred KB of activations per utterance.  Here one CTA of 128
-// threads owns one utterance at a time (persistent loop, one CTA per SM) and keeps every activation on
-// chip: thread r <-> phoneme row r <-> TMEM lane r, so LayerNorm / GELU / softmax / the scalar heads are
-// thread-local, and every dense layer is
-//     thread r writes its row of the A operand (split fp16 hi/lo, UMMA canonical K-major row-panel layout)
+// 64-row tiles per CTA, drain) for a few hundred KB of activations per utterance.  Here one CTA owns one
+// utterance at a time (persistent loop, one CTA per SM) and keeps every activation on chip.
+//
+// 512 threads = 16 warps: phoneme row r <-> TMEM lane r is shared by FOUR threads (warps w, w+4, w+8, w+12
+// all address lane quarter w % 4), each owning one quarter of the columns of whatever layer is being
+// finished.  (A first version with one thread per row was correct but latency-bound: 4 warps per SM cannot
+// hide a ~20 k-instruction dependent chain per row.)  Every dense layer is
+//     the row's four threads write their K/4 slices of the A operand (split fp16 hi/lo, UMMA canonical
+//     K-major row-panel layout: addr(row, k) = (k/8)*LBO + row*16 + (k%8)*2)
 //     -> fence + __syncthreads -> one elected thread issues the tcgen05.mma's (M = 128, 3 per K step:
-//     hi*hi + hi*lo + lo*hi) and commits to an mbarrier -> every thread reads its accumulator row out of TMEM.
-// Conv taps are descriptor row shifts over a tile with one zero halo row on each side (es_umma_enc.cu);
-// attention is S = Q K^T, thread-per-row softmax out of TMEM, O = P V (es_umma_attn.cu).  Weights are the
-// same packed split-fp16 images the per-layer kernels use, streamed through two 48 KB shared-memory
-// buffers by bulk copies issued two layers ahead.  Level-1 rows (n1 = ceil(N/2) <= 64) live in threads
-// 0..n1-1; the M = 128 GEMMs simply carry zero rows.  Two small per-utterance scratch arrays in global
-// memory (L2) hand rows between threads where the row -> thread map changes (stride-2 merge conv, the
+//     hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM) and commits to an mbarrier
+//     -> every thread reads its N/4 accumulator columns (tcgen05.ld 32x32b) and runs the epilogue in registers;
+// row statistics (LayerNorm, softmax max / sum, the scalar heads) are combined across the four threads through
+// a ping-pong shared-memory array and one __syncthreads.  Conv taps are descriptor row shifts over a tile with
+// one zero halo row on each side (es_umma_enc.cu); attention is S = Q K^T, softmax out of TMEM, O = P V
+// (es_umma_attn.cu).  Weights are the packed split-fp16 images of the per-layer kernels, streamed through two
+// 48 KB shared-memory buffers by bulk copies issued two layers ahead.  Level-1 rows (n1 = ceil(N/2) <= 64)
+// live in rows 0..n1-1; the M = 128 GEMMs simply carry zero rows.  Two small per-utterance scratch arrays in
+// global memory (L2) hand rows between threads where the row -> thread map changes (stride-2 merge conv, the
 // stride-2 transposed-conv scatter of Fuse).
 //
 // Layer list per utterance (reference lines in es_api.cu next to the per-layer launches):
@@ -26,6 +32,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "es_common.cuh"
 #include "es_kernels.cuh"
 #include "es_umma.cuh"
@@ -35,7 +43,8 @@ namespace {
 
 using namespace umma;
 
-constexpr int PM = 128;                          // rows = threads = TMEM lanes
+constexpr int PM = 128;                          // rows = TMEM lanes
+constexpr int NTHR = 4 * PM;                     // four threads per row (column quarters)
 constexpr int D0 = 32, D1 = 64;                  // channel widths of the two pyramid levels
 constexpr uint32_t PANEL = PM * 16;              // 2048: one K panel (8 elements) of 128 rows, no halo
 constexpr uint32_t XA_LBO = (PM + 2) * 16;       // 2080: one K panel of 130 rows (zero halo row on each side)
@@ -48,7 +57,8 @@ constexpr uint32_t OFF_OP = 0;                                 // 64 KB: attenti
 constexpr uint32_t OFF_VT = OFF_OP + 65536;                    // 16 KB: V^T hi, lo
 constexpr uint32_t OFF_XA = OFF_VT + 16384;                    // halo A tile (hi plane, lo plane)
 constexpr uint32_t OFF_WB = OFF_XA + 2 * XA_PLANE;             // two weight buffers
-constexpr uint32_t OFF_MISC = OFF_WB + 2 * WB_BYTES;           // scan scratch
+constexpr uint32_t OFF_RED = OFF_WB + 2 * WB_BYTES;            // row reductions: [2][4][128] float2
+constexpr uint32_t OFF_MISC = OFF_RED + 2 * 4 * PM * 8;        // scan scratch
 constexpr uint32_t OFF_BAR = OFF_MISC + 64;                    // bar_mma, bar_w[2], tmem slot
 constexpr uint32_t PH_SMEM = OFF_BAR + 64;
 static_assert(OFF_WB % 16 == 0 && OFF_XA % 16 == 0, "bulk copies need 16-byte aligned destinations");
@@ -79,6 +89,23 @@ __device__ __forceinline__ float ex2f_approx(float x) {
     return e;
 }
 
+// Latency-critical waits (an MMA round trip is ~0.3 us, and ~25 of them are serial per utterance): plain try_wait
+// spin instead of the suspend-hint form of es_umma.cuh, whose wake-up granularity showed up as ~1 us per wait.
+// Out of line: the kernel is one long straight-line pass per utterance and instruction fetch is a measured cost.
+// Bounded like every wait in this library.
+__device__ __noinline__ bool spin_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 28); ++i) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
 #define PHASE_SYNC()               \
     do {                           \
         fence_proxy_async_smem();  \
@@ -87,37 +114,45 @@ __device__ __forceinline__ float ex2f_approx(float x) {
         tc_fence_after_sync();     \
     } while (0)
 
-// K fp32 values of one row -> split fp16 hi/lo rows of a row-panel tile (tile row `trow`)
-template <int K>
-__device__ __forceinline__ void stage_row(uint8_t* tile, uint32_t lbo, uint32_t plane, int trow, const float* v, bool live) {
+// NV (8 | 16 | 32) fp32 values = NV/8 consecutive K panels starting at panel pc0 -> split fp16 hi/lo rows of a
+// row-panel tile (tile row `trow`)
+template <int NV>
+__device__ __forceinline__ void stage_cols(uint8_t* tile, uint32_t lbo, uint32_t plane, int trow, int pc0, const float* v, bool live) {
 #pragma unroll
-    for (int pc = 0; pc < K / 8; ++pc) {
+    for (int pc = 0; pc < NV / 8; ++pc) {
         float a[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) a[e] = live ? v[8 * pc + e] : 0.f;
         uint4 hi, lo;
         split8(a, hi, lo);
-        *reinterpret_cast<uint4*>(tile + (uint32_t)pc * lbo + (uint32_t)trow * 16u) = hi;
-        *reinterpret_cast<uint4*>(tile + plane + (uint32_t)pc * lbo + (uint32_t)trow * 16u) = lo;
+        const uint32_t off = (uint32_t)(pc0 + pc) * lbo + (uint32_t)trow * 16u;
+        *reinterpret_cast<uint4*>(tile + off) = hi;
+        *reinterpret_cast<uint4*>(tile + plane + off) = lo;
     }
 }
 
-// 32 consecutive accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tm_load32(uint32_t trow, int col, float* v) {
-    uint32_t rr[32];
-    tmem_ld32(trow + (uint32_t)col, rr);
+// NV consecutive accumulator columns of this thread's TMEM lane
+template <int NV>
+__device__ __forceinline__ void tm_load(uint32_t taddr, float* v) {
+    static_assert(NV == 8 || NV == 16 || NV == 32, "8, 16 or 32 columns");
+    uint32_t rr[NV];
+    if constexpr (NV == 8) tmem_ld32x8(taddr, rr);
+    else if constexpr (NV == 16) tmem_ld32x16(taddr, rr);
+    else tmem_ld32(taddr, rr);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+    for (int j = 0; j < NV; ++j) v[j] = __uint_as_float(rr[j]);
 }
 
 // D[tmem_d] = A . W^T over `taps` row-shifted views of the A tile (issued by warp 0; `elected` = its issuing lane)
-__device__ __forceinline__ void issue_gemm(bool elected, uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_plane,
-                                           uint32_t w_addr, int K, int N, int taps) {
+__device__ __noinline__ void issue_gemm(bool elected, uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_plane,
+                                        uint32_t w_addr, int K, int N, int taps) {
     const uint32_t idesc = make_idesc_f16(PM, N);
     const uint32_t lbo_b = (uint32_t)N * 16u, w_plane = (uint32_t)N * (uint32_t)K * 2u;
     uint32_t acc = 0;
+#pragma unroll 1
     for (int t = 0; t < taps; ++t) {
+#pragma unroll 1
         for (int ks = 0; ks < (K >> 4); ++ks) {
             const uint32_t a_off = (uint32_t)t * 16u + (uint32_t)(2 * ks) * a_lbo;
             const uint64_t dah = make_smem_desc(a_addr + a_off, a_lbo, 128u);
@@ -135,19 +170,15 @@ __device__ __forceinline__ void issue_gemm(bool elected, uint32_t tmem_d, uint32
     }
 }
 
-// thread-local LayerNorm over n values (two-pass, biased variance, eps 1e-5: nn.LayerNorm)
+// NV (multiple of 4) consecutive per-channel parameters (bias, LayerNorm gain, ...) with 128-bit loads; the
+// packed parameter vectors are 256-byte aligned and every thread's first column is a multiple of 8
 template <int NV>
-__device__ __forceinline__ void ln_row(float* v, const float* __restrict__ g, const float* __restrict__ be) {
-    float s = 0.f;
+__device__ __forceinline__ void ldv(const float* __restrict__ src, float* v) {
 #pragma unroll
-    for (int j = 0; j < NV; ++j) s += v[j];
-    const float mean = s * (1.f / NV);
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) { const float dlt = v[j] - mean; q = fmaf(dlt, dlt, q); }
-    const float rstd = rsqrtf(q * (1.f / NV) + kLnEps);
-#pragma unroll
-    for (int j = 0; j < NV; ++j) v[j] = (v[j] - mean) * rstd * __ldg(g + j) + __ldg(be + j);
+    for (int c4 = 0; c4 < NV / 4; ++c4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src) + c4);
+        v[4 * c4] = t.x; v[4 * c4 + 1] = t.y; v[4 * c4 + 2] = t.z; v[4 * c4 + 3] = t.w;
+    }
 }
 
 __device__ __forceinline__ int bucket_left(const float* __restrict__ bins, int nb, float v) {
@@ -159,14 +190,16 @@ __device__ __forceinline__ int bucket_left(const float* __restrict__ bins, int n
     return lo;
 }
 
-__global__ void __launch_bounds__(PM, 1)
+__global__ void __launch_bounds__(NTHR, 1)
 umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int r = tid;                                         // this thread's row
+    const int rq = warp & 3, cq = warp >> 2;                   // TMEM lane quarter, column quarter
+    const int r = 32 * rq + lane;                              // this thread's row
     uint8_t* op = smem + OFF_OP;
     uint8_t* vt = smem + OFF_VT;
     uint8_t* xa = smem + OFF_XA;
+    float2* red = reinterpret_cast<float2*>(smem + OFF_RED);
     int* s_wtot = reinterpret_cast<int*>(smem + OFF_MISC);
     const uint32_t bar_mma = smem_u32(smem + OFF_BAR);
     const uint32_t bar_w = bar_mma + 8;                        // [2]
@@ -236,7 +269,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)(rq * 32) << 16);
     if (tid == 0) { wload(0); wload(1); }                      // weights do not depend on the predecessor kernel
     pdl_launch_dependents();
     pdl_wait();
@@ -245,10 +278,11 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
     bool failed = false;
     uint32_t mph = 0;                                           // bar_mma phase parity
     int wg = 0;                                                 // next weight phase to be consumed (global index)
+    int flip = 0;                                               // ping-pong half of `red`
 
     // warp 0 waits for weight load `wg`; returns its shared-memory address
     auto w_wait = [&]() -> uint32_t {
-        if (warp == 0 && !mbar_wait(bar_w + 8u * (uint32_t)(wg & 1), (uint32_t)(wg >> 1) & 1u)) failed = true;
+        if (warp == 0 && !spin_wait(bar_w + 8u * (uint32_t)(wg & 1), (uint32_t)(wg >> 1) & 1u)) failed = true;
         return wb_addr + (uint32_t)(wg & 1) * WB_BYTES;
     };
     // commit the issued MMAs, wait for them, then refill the weight buffer they used (two phases ahead)
@@ -257,7 +291,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             if (elected) mma_commit(bar_mma);
             __syncwarp();
         }
-        if (!mbar_wait(bar_mma, mph)) failed = true;
+        if (!spin_wait(bar_mma, mph)) failed = true;
         mph ^= 1;
         tc_fence_after_sync();
         if (used_weights) {
@@ -265,40 +299,66 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             ++wg;
         }
     };
+    // combine two per-thread partials over the four threads of a row (same order in all four -> identical results).
+    // One barrier per call: the buffer halves alternate, and a half is rewritten only after the barrier of the
+    // following call, which every reader of this call has passed.
+    auto row_sum2 = [&](float a, float b2) -> float2 {
+        float2* bf = red + flip * (4 * PM);
+        flip ^= 1;
+        bf[cq * PM + r] = make_float2(a, b2);
+        __syncthreads();
+        const float2 t0 = bf[r], t1 = bf[PM + r], t2 = bf[2 * PM + r], t3 = bf[3 * PM + r];
+        return make_float2((t0.x + t1.x) + (t2.x + t3.x), (t0.y + t1.y) + (t2.y + t3.y));
+    };
+    auto row_max = [&](float a) -> float {
+        float2* bf = red + flip * (4 * PM);
+        flip ^= 1;
+        bf[cq * PM + r].x = a;
+        __syncthreads();
+        return fmaxf(fmaxf(bf[r].x, bf[PM + r].x), fmaxf(bf[2 * PM + r].x, bf[3 * PM + r].x));
+    };
+    // LayerNorm over n_tot = 4 * NV columns of the row; this thread holds NV of them, g / be point at its first column
+    // (single-pass statistics like the per-layer tensor-core kernels: inputs are O(1))
+    auto ln_cols = [&](auto nv_tag, float* v, const float* g, const float* be) {
+        constexpr int NV = decltype(nv_tag)::value;
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { s += v[j]; q = fmaf(v[j], v[j], q); }
+        const float2 t = row_sum2(s, q);
+        const float inv_n = 1.f / (4 * NV);
+        const float mean = t.x * inv_n;
+        const float rstd = rsqrtf(fmaxf(fmaf(t.y, inv_n, -mean * mean), 0.f) + kLnEps);
+        float gg[NV], bb[NV];
+        ldv<NV>(g, gg);
+        ldv<NV>(be, bb);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = fmaf((v[j] - mean) * rstd, gg[j], bb[j]);
+    };
+    using I8 = std::integral_constant<int, 8>;
+    using I16 = std::integral_constant<int, 16>;
 
-    // softmax(Q K^T) V for one head: q/k/v rows are in TMEM columns qc/kc/vc (C wide), output -> columns oc
-    auto attention = [&](const int C, const int NK, const int n, const int qc, const int kc, const int vc, const int oc) {
-        const uint32_t qk_plane = (uint32_t)(C >> 3) * PANEL;
-        const uint32_t vt_lbo = (uint32_t)C * 16u, vt_plane = (uint32_t)(NK >> 3) * vt_lbo;
-        const uint32_t p_plane = (uint32_t)(NK >> 3) * PANEL;
+    // softmax(Q K^T) V for one head: q/k/v rows are in TMEM columns qc/kc/vc (C wide), output -> columns oc.
+    // This thread owns CV = C/4 channels of its row and SV = NK/4 keys of its score row.
+    auto attention = [&](auto c_tag, auto nk_tag, const int n, const int qc, const int kc, const int vc, const int oc) {
+        constexpr int C = decltype(c_tag)::value, NK = decltype(nk_tag)::value;
+        constexpr int CV = C / 4, SV = NK / 4;
+        constexpr uint32_t qk_plane = (uint32_t)(C >> 3) * PANEL;
+        constexpr uint32_t vt_lbo = (uint32_t)C * 16u, vt_plane = (uint32_t)(NK >> 3) * vt_lbo;
+        constexpr uint32_t p_plane = (uint32_t)(NK >> 3) * PANEL;
         // 1. stage Q, K (row panels) and V^T; rows >= n are zero rows of the GEMM that produced them
-        for (int c0 = 0; c0 < C; c0 += 32) {
-            float q[32], k[32], v[32];
-            tm_load32(trow, qc + c0, q);
-            tm_load32(trow, kc + c0, k);
-            tm_load32(trow, vc + c0, v);
-#pragma unroll
-            for (int pc = 0; pc < 4; ++pc) {
-                float a[8];
-                uint4 hi, lo;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) a[e] = q[8 * pc + e];
-                split8(a, hi, lo);
-                const uint32_t off = (uint32_t)((c0 >> 3) + pc) * PANEL + (uint32_t)r * 16u;
-                *reinterpret_cast<uint4*>(op + off) = hi;
-                *reinterpret_cast<uint4*>(op + qk_plane + off) = lo;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) a[e] = k[8 * pc + e];
-                split8(a, hi, lo);
-                *reinterpret_cast<uint4*>(op + 2 * qk_plane + off) = hi;
-                *reinterpret_cast<uint4*>(op + 3 * qk_plane + off) = lo;
-            }
+        {
+            float q[CV], k[CV], v[CV];
+            tm_load<CV>(trow + (uint32_t)(qc + CV * cq), q);
+            tm_load<CV>(trow + (uint32_t)(kc + CV * cq), k);
+            tm_load<CV>(trow + (uint32_t)(vc + CV * cq), v);
+            stage_cols<CV>(op, PANEL, qk_plane, r, (CV / 8) * cq, q, true);
+            stage_cols<CV>(op + 2 * qk_plane, PANEL, qk_plane, r, (CV / 8) * cq, k, true);
             if (r < NK) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
+                for (int e = 0; e < CV; ++e) {
                     const __half vh = __float2half_rn(v[e]);
                     const __half vl = __float2half_rn(v[e] - __half2float(vh));
-                    const uint32_t off = (uint32_t)(r >> 3) * vt_lbo + (uint32_t)(c0 + e) * 16u + (uint32_t)(r & 7) * 2u;
+                    const uint32_t off = (uint32_t)(r >> 3) * vt_lbo + (uint32_t)(CV * cq + e) * 16u + (uint32_t)(r & 7) * 2u;
                     *reinterpret_cast<__half*>(vt + off) = vh;
                     *reinterpret_cast<__half*>(vt + vt_plane + off) = vl;
                 }
@@ -308,6 +368,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         // 2. S = Q K^T  -> columns [0, NK)
         if (warp == 0) {
             const uint32_t idesc = make_idesc_f16(PM, NK);
+#pragma unroll 1
             for (int ks = 0; ks < (C >> 4); ++ks) {
                 const uint32_t o = (uint32_t)(2 * ks) * PANEL;
                 const uint64_t dqh = make_smem_desc(op_addr + o, PANEL, 128u), dql = make_smem_desc(op_addr + qk_plane + o, PANEL, 128u);
@@ -324,49 +385,31 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         // 3. softmax over the n keys (unmasked: blocks.py:59-63), P -> split fp16 over the dead Q/K tiles
         {
             const float sc = p.scale_log2e;
+            float s[SV];
+            tm_load<SV>(trow + (uint32_t)(SV * cq), s);
             float mx = -INFINITY;
-            for (int c0 = 0; c0 < NK; c0 += 32) {
-                float s[32];
-                tm_load32(trow, c0, s);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c0 + j < n) mx = fmaxf(mx, s[j]);
-            }
+            for (int j = 0; j < SV; ++j)
+                if (SV * cq + j < n) mx = fmaxf(mx, s[j]);
+            mx = row_max(mx);
             const float nm = -mx * sc;
             float sum = 0.f;
-            for (int c0 = 0; c0 < NK; c0 += 32) {
-                float s[32];
-                tm_load32(trow, c0, s);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float e = ex2f_approx(fmaf(s[j], sc, nm));
-                    if (c0 + j < n) sum += e;
-                }
+            for (int j = 0; j < SV; ++j) {
+                const float e = ex2f_approx(fmaf(s[j], sc, nm));
+                s[j] = (SV * cq + j < n) ? e : 0.f;
+                sum += s[j];
             }
-            const float inv = 1.f / sum;
-            for (int c0 = 0; c0 < NK; c0 += 32) {
-                float s[32];
-                tm_load32(trow, c0, s);
+            const float inv = 1.f / row_sum2(sum, 0.f).x;
 #pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) {
-                    float pv[8];
-#pragma unroll
-                    for (int e8 = 0; e8 < 8; ++e8) {
-                        const int col = c0 + j8 * 8 + e8;
-                        pv[e8] = col < n ? ex2f_approx(fmaf(s[j8 * 8 + e8], sc, nm)) * inv : 0.f;
-                    }
-                    uint4 hi, lo;
-                    split8(pv, hi, lo);
-                    const uint32_t off = (uint32_t)((c0 >> 3) + j8) * PANEL + (uint32_t)r * 16u;
-                    *reinterpret_cast<uint4*>(op + off) = hi;
-                    *reinterpret_cast<uint4*>(op + p_plane + off) = lo;
-                }
-            }
+            for (int j = 0; j < SV; ++j) s[j] *= inv;
+            stage_cols<SV>(op, PANEL, p_plane, r, (SV / 8) * cq, s, true);
         }
         PHASE_SYNC();
         // 4. O = P V  -> columns [oc, oc + C)
         if (warp == 0) {
             const uint32_t idesc = make_idesc_f16(PM, C);
+#pragma unroll 1
             for (int ks = 0; ks < (NK >> 4); ++ks) {
                 const uint64_t dph = make_smem_desc(op_addr + (uint32_t)(2 * ks) * PANEL, PANEL, 128u);
                 const uint64_t dpl = make_smem_desc(op_addr + p_plane + (uint32_t)(2 * ks) * PANEL, PANEL, 128u);
@@ -382,6 +425,8 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         gemm_done(false);
     };
 
+    const int c8 = 8 * cq, c16 = 16 * cq;                       // this thread's first column of a 32- / 64-wide row
+
     for (int ui = 0; ui < my_utts; ++ui) {
         const int b = (int)blockIdx.x + ui * (int)gridDim.x;
         const size_t row = (size_t)b * N + r;
@@ -394,103 +439,108 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 pad1 = pad1 || (t < N ? p.mask[(size_t)b * N + t] != 0 : true);
             }
         }
-        const float* xm1_row = p.sc_xm1 + ((size_t)b * n1 + r) * D1;   // valid for r < n1
 
-        // ================================================================= block 0
+        // ================================================================= block 0 (8 columns per thread)
         // x0 = sum_tau Tab[tau][id[t + tau - 1]]   (embedding + merge conv + 1x1 folded into 3 gather tables)
-        float x0[D0];
+        float x0[8];
 #pragma unroll
-        for (int c = 0; c < D0; ++c) x0[c] = 0.f;
+        for (int c = 0; c < 8; ++c) x0[c] = 0.f;
         if (act0) {
             for (int tau = 0; tau < 3; ++tau) {
                 const int ti = r + tau - 1;
                 if (ti < 0 || ti >= N) continue;
                 int id = __ldg(p.ids + (size_t)b * N + ti);
                 id = min(max(id, 0), p.n_symbols - 1);
-                const float4* tp = reinterpret_cast<const float4*>(p.enc[0].merge_w + ((size_t)tau * p.n_symbols + id) * D0);
-#pragma unroll
-                for (int c4 = 0; c4 < D0 / 4; ++c4) {
-                    const float4 v = __ldg(tp + c4);
-                    x0[4 * c4] += v.x; x0[4 * c4 + 1] += v.y; x0[4 * c4 + 2] += v.z; x0[4 * c4 + 3] += v.w;
-                }
+                const float4* tp = reinterpret_cast<const float4*>(p.enc[0].merge_w + ((size_t)tau * p.n_symbols + id) * D0 + c8);
+                const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1);
+                x0[0] += v0.x; x0[1] += v0.y; x0[2] += v0.z; x0[3] += v0.w;
+                x0[4] += v1.x; x0[5] += v1.y; x0[6] += v1.z; x0[7] += v1.w;
             }
         }
-        stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, x0, act0);
+        stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, x0, act0);
         PHASE_SYNC();
         {   // qkv0: [32] -> [96] into columns [128, 224)
             const uint32_t w = w_wait();
             if (warp == 0) issue_gemm(elected, tmem + 128, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, 96, 1);
             gemm_done(true);
         }
-        attention(D0, PM, N, 128, 160, 192, 128);
-        float x1[D0];
+        attention(std::integral_constant<int, D0>{}, std::integral_constant<int, PM>{}, N, 128, 160, 192, 128);
+        float x1[8];
         {   // proj0 + residual + LN1 + mask
-            float o[D0];
-            tm_load32(trow, 128, o);
-            stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, o, act0);
+            float o[8];
+            tm_load<8>(trow + (uint32_t)(128 + c8), o);
+            stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, o, act0);
             PHASE_SYNC();
             const uint32_t w = w_wait();
             if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
             gemm_done(true);
-            tm_load32(trow, 0, x1);
+            tm_load<8>(trow + (uint32_t)c8, x1);
+            float pb[8];
+            ldv<8>(p.enc[0].proj_b + c8, pb);
 #pragma unroll
-            for (int c = 0; c < D0; ++c) x1[c] += __ldg(p.enc[0].proj_b + c) + x0[c];
-            ln_row<D0>(x1, p.enc[0].ln1_g, p.enc[0].ln1_b);
+            for (int c = 0; c < 8; ++c) x1[c] += pb[c] + x0[c];
+            ln_cols(I8{}, x1, p.enc[0].ln1_g + c8, p.enc[0].ln1_b + c8);
             if (pad0) {
 #pragma unroll
-                for (int c = 0; c < D0; ++c) x1[c] = 0.f;
+                for (int c = 0; c < 8; ++c) x1[c] = 0.f;
             }
-            stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, x1, act0);
+            stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, x1, act0);
             PHASE_SYNC();
         }
-        float f0[D0];
+        float f0[8];
         {   // MixFFN: conv3 (mlp1 folded) + GELU, mlp2 + residual + LN2 + mask
             uint32_t w = w_wait();
             if (warp == 0) issue_gemm(elected, tmem, xa_addr, XA_LBO, XA_PLANE, w, D0, D0, 3);
             gemm_done(true);
-            float h[D0];
-            tm_load32(trow, 0, h);
+            float h[8];
+            tm_load<8>(trow + (uint32_t)c8, h);
             const float m0 = (r - 1 >= 0 && r - 1 < N) ? 1.f : 0.f, m2 = (r + 1 < N) ? 1.f : 0.f;
+            float fb[8], t0[8], t1[8], t2[8];
+            ldv<8>(p.enc[0].ffn1_b + c8, fb);
+            ldv<8>(p.enc[0].ffn1_tapb + c8, t0);
+            ldv<8>(p.enc[0].ffn1_tapb + D0 + c8, t1);
+            ldv<8>(p.enc[0].ffn1_tapb + 2 * D0 + c8, t2);
 #pragma unroll
-            for (int c = 0; c < D0; ++c) {
-                float v = h[c] + __ldg(p.enc[0].ffn1_b + c);
-                v = fmaf(m0, __ldg(p.enc[0].ffn1_tapb + c), v);
-                v += __ldg(p.enc[0].ffn1_tapb + D0 + c);
-                v = fmaf(m2, __ldg(p.enc[0].ffn1_tapb + 2 * D0 + c), v);
+            for (int c = 0; c < 8; ++c) {
+                float v = h[c] + fb[c];
+                v = fmaf(m0, t0[c], v);
+                v += t1[c];
+                v = fmaf(m2, t2[c], v);
                 h[c] = gelu_erf_f(v);
             }
-            stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, h, act0);
+            stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, h, act0);
             PHASE_SYNC();
             w = w_wait();
             if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
             gemm_done(true);
-            tm_load32(trow, 0, f0);
+            tm_load<8>(trow + (uint32_t)c8, f0);
+            float f2b[8];
+            ldv<8>(p.enc[0].ffn2_b + c8, f2b);
 #pragma unroll
-            for (int c = 0; c < D0; ++c) f0[c] += __ldg(p.enc[0].ffn2_b + c) + x1[c];
-            ln_row<D0>(f0, p.enc[0].ln2_g, p.enc[0].ln2_b);
+            for (int c = 0; c < 8; ++c) f0[c] += f2b[c] + x1[c];
+            ln_cols(I8{}, f0, p.enc[0].ln2_g + c8, p.enc[0].ln2_b + c8);
             if (pad0) {
 #pragma unroll
-                for (int c = 0; c < D0; ++c) f0[c] = 0.f;
+                for (int c = 0; c < 8; ++c) f0[c] = 0.f;
             }
-            stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, f0, act0);
+            stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, f0, act0);
             PHASE_SYNC();
         }
-        // ================================================================= block 1
+        // ================================================================= block 1 (16 columns per thread)
         {   // merge conv (1 tap, stride 2): xm1[j] = W feat0[2j]; computed for every row, even rows are kept
             const uint32_t w = w_wait();
             if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D1, 1);
             gemm_done(true);
-            float y[D1];
-            tm_load32(trow, 0, y);
-            tm_load32(trow, 32, y + 32);
+            float y[16];
+            tm_load<16>(trow + (uint32_t)c16, y);
             if (act0 && !(r & 1)) {
                 const int j = r >> 1;                            // < n1
-                float4* dst = reinterpret_cast<float4*>(p.sc_xm1 + ((size_t)b * n1 + j) * D1);
+                float4* dst = reinterpret_cast<float4*>(p.sc_xm1 + ((size_t)b * n1 + j) * D1 + c16);
 #pragma unroll
-                for (int c4 = 0; c4 < D1 / 4; ++c4) dst[c4] = make_float4(y[4 * c4], y[4 * c4 + 1], y[4 * c4 + 2], y[4 * c4 + 3]);
-                stage_row<D1>(xa, XA_LBO, XA_PLANE, j + 1, y, true);
+                for (int c4 = 0; c4 < 4; ++c4) dst[c4] = make_float4(y[4 * c4], y[4 * c4 + 1], y[4 * c4 + 2], y[4 * c4 + 3]);
+                stage_cols<16>(xa, XA_LBO, XA_PLANE, j + 1, 2 * cq, y, true);
             }
-            if (r >= n1) stage_row<D1>(xa, XA_LBO, XA_PLANE, r + 1, y, false);      // zero rows n1..127
+            if (r >= n1) stage_cols<16>(xa, XA_LBO, XA_PLANE, r + 1, 2 * cq, y, false);      // zero rows n1..127
             PHASE_SYNC();
         }
         for (int s = 0; s < 3; ++s) {   // q | k | v of both heads: [64] -> [128] into columns 128 + 128 s
@@ -498,120 +548,127 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             if (warp == 0) issue_gemm(elected, tmem + 128 + 128 * s, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, 128, 1);
             gemm_done(true);
         }
-        for (int hd = 0; hd < 2; ++hd) attention(D1, 64, n1, 128 + 64 * hd, 256 + 64 * hd, 384 + 64 * hd, 128 + 64 * hd);
-        float x1b[D1];
+        for (int hd = 0; hd < 2; ++hd)
+            attention(std::integral_constant<int, D1>{}, std::integral_constant<int, 64>{}, n1,
+                      128 + 64 * hd, 256 + 64 * hd, 384 + 64 * hd, 128 + 64 * hd);
+        float x1b[16];
         {   // proj1: A = [O_0 | O_1] (K = 128) in the attention region; + residual + LN1 + mask
-#pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
-                float o[32];
-                tm_load32(trow, 128 + c0, o);
-                stage_row<32>(op + (uint32_t)(c0 >> 3) * PANEL, PANEL, 16 * PANEL, r, o, act1);
-            }
+            float o[32];
+            tm_load<32>(trow + (uint32_t)(128 + 32 * cq), o);
+            stage_cols<32>(op, PANEL, 16 * PANEL, r, 4 * cq, o, act1);
             PHASE_SYNC();
             const uint32_t w = w_wait();
             if (warp == 0) issue_gemm(elected, tmem, op_addr, PANEL, 16 * PANEL, w, 128, D1, 1);
             gemm_done(true);
-            tm_load32(trow, 0, x1b);
-            tm_load32(trow, 32, x1b + 32);
+            tm_load<16>(trow + (uint32_t)c16, x1b);
             if (act1) {
-                const float4* rp = reinterpret_cast<const float4*>(xm1_row);
+                const float4* rp = reinterpret_cast<const float4*>(p.sc_xm1 + ((size_t)b * n1 + r) * D1 + c16);
 #pragma unroll
-                for (int c4 = 0; c4 < D1 / 4; ++c4) {
+                for (int c4 = 0; c4 < 4; ++c4) {
                     const float4 v = __ldcg(rp + c4);
                     x1b[4 * c4] += v.x; x1b[4 * c4 + 1] += v.y; x1b[4 * c4 + 2] += v.z; x1b[4 * c4 + 3] += v.w;
                 }
             }
+            float pb[16];
+            ldv<16>(p.enc[1].proj_b + c16, pb);
 #pragma unroll
-            for (int c = 0; c < D1; ++c) x1b[c] += __ldg(p.enc[1].proj_b + c);
-            ln_row<D1>(x1b, p.enc[1].ln1_g, p.enc[1].ln1_b);
+            for (int c = 0; c < 16; ++c) x1b[c] += pb[c];
+            ln_cols(I16{}, x1b, p.enc[1].ln1_g + c16, p.enc[1].ln1_b + c16);
             if (pad1) {
 #pragma unroll
-                for (int c = 0; c < D1; ++c) x1b[c] = 0.f;
+                for (int c = 0; c < 16; ++c) x1b[c] = 0.f;
             }
-            stage_row<D1>(xa, XA_LBO, XA_PLANE, r + 1, x1b, act1);
+            stage_cols<16>(xa, XA_LBO, XA_PLANE, r + 1, 2 * cq, x1b, act1);
             PHASE_SYNC();
         }
         {   // MixFFN of block 1
             uint32_t w = w_wait();
             if (warp == 0) issue_gemm(elected, tmem, xa_addr, XA_LBO, XA_PLANE, w, D1, D1, 3);
             gemm_done(true);
-            float h[D1];
-            tm_load32(trow, 0, h);
-            tm_load32(trow, 32, h + 32);
+            float h[16];
+            tm_load<16>(trow + (uint32_t)c16, h);
             const float m0 = (r - 1 >= 0 && r - 1 < n1) ? 1.f : 0.f, m2 = (r + 1 < n1) ? 1.f : 0.f;
+            float fb[16], t0[16], t1[16], t2[16];
+            ldv<16>(p.enc[1].ffn1_b + c16, fb);
+            ldv<16>(p.enc[1].ffn1_tapb + c16, t0);
+            ldv<16>(p.enc[1].ffn1_tapb + D1 + c16, t1);
+            ldv<16>(p.enc[1].ffn1_tapb + 2 * D1 + c16, t2);
 #pragma unroll
-            for (int c = 0; c < D1; ++c) {
-                float v = h[c] + __ldg(p.enc[1].ffn1_b + c);
-                v = fmaf(m0, __ldg(p.enc[1].ffn1_tapb + c), v);
-                v += __ldg(p.enc[1].ffn1_tapb + D1 + c);
-                v = fmaf(m2, __ldg(p.enc[1].ffn1_tapb + 2 * D1 + c), v);
+            for (int c = 0; c < 16; ++c) {
+                float v = h[c] + fb[c];
+                v = fmaf(m0, t0[c], v);
+                v += t1[c];
+                v = fmaf(m2, t2[c], v);
                 h[c] = gelu_erf_f(v);
             }
-            stage_row<D1>(xa, XA_LBO, XA_PLANE, r + 1, h, act1);
+            stage_cols<16>(xa, XA_LBO, XA_PLANE, r + 1, 2 * cq, h, act1);
             PHASE_SYNC();
             w = w_wait();
             if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, D1, 1);
             gemm_done(true);
-            tm_load32(trow, 0, h);
-            tm_load32(trow, 32, h + 32);
+            tm_load<16>(trow + (uint32_t)c16, h);
+            float f2b[16];
+            ldv<16>(p.enc[1].ffn2_b + c16, f2b);
 #pragma unroll
-            for (int c = 0; c < D1; ++c) h[c] += __ldg(p.enc[1].ffn2_b + c) + x1b[c];
-            ln_row<D1>(h, p.enc[1].ln2_g, p.enc[1].ln2_b);        // feat1
+            for (int c = 0; c < 16; ++c) h[c] += f2b[c] + x1b[c];
+            ln_cols(I16{}, h, p.enc[1].ln2_g + c16, p.enc[1].ln2_b + c16);        // feat1
             if (pad1) {
 #pragma unroll
-                for (int c = 0; c < D1; ++c) h[c] = 0.f;
+                for (int c = 0; c < 16; ++c) h[c] = 0.f;
             }
-            stage_row<D1>(xa, XA_LBO, XA_PLANE, r + 1, h, act1);
+            stage_cols<16>(xa, XA_LBO, XA_PLANE, r + 1, 2 * cq, h, act1);
             PHASE_SYNC();
         }
         // ================================================================= Fuse (networks.py:189-219, folded)
-        float fz[D0];
+        float fz[8];
         {
             uint32_t w = w_wait();                               // U = feat1 [G_0 | G_1 | G_2] + [g_0 | g_1 | g_2]
             if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, 96, 1);
             gemm_done(true);
 #pragma unroll 1
-            for (int c0 = 0; c0 < 96; c0 += 32) {
-                float u[32];
-                tm_load32(trow, c0, u);
+            for (int i = 0; i < 3; ++i) {   // 3 of the 12 8-column groups of U per thread
+                const int c0 = 8 * (cq + 4 * i);
+                float u[8];
+                tm_load<8>(trow + (uint32_t)c0, u);
                 if (act1) {
                     float4* dst = reinterpret_cast<float4*>(p.sc_u + ((size_t)b * n1 + r) * 96 + c0);
-#pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4)
-                        dst[c4] = make_float4(u[4 * c4] + __ldg(p.fuse_gb + c0 + 4 * c4), u[4 * c4 + 1] + __ldg(p.fuse_gb + c0 + 4 * c4 + 1),
-                                              u[4 * c4 + 2] + __ldg(p.fuse_gb + c0 + 4 * c4 + 2), u[4 * c4 + 3] + __ldg(p.fuse_gb + c0 + 4 * c4 + 3));
+                    float gb[8];
+                    ldv<8>(p.fuse_gb + c0, gb);
+                    dst[0] = make_float4(u[0] + gb[0], u[1] + gb[1], u[2] + gb[2], u[3] + gb[3]);
+                    dst[1] = make_float4(u[4] + gb[4], u[5] + gb[5], u[6] + gb[6], u[7] + gb[7]);
                 }
             }
-            stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, f0, act0);
+            stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, f0, act0);
+            // rows of the K = 64 tile beyond panel 3 are not read by the K = 32 GEMMs that follow
             PHASE_SYNC();                                        // also publishes the U rows to the CTA
             w = w_wait();                                        // fused = mask(c + A0 feat0 + stride-2 scatter of U)
             if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
             gemm_done(true);
-            tm_load32(trow, 0, fz);
+            tm_load<8>(trow + (uint32_t)c8, fz);
+            float fc[8];
+            ldv<8>(p.fuse_c + c8, fc);
 #pragma unroll
-            for (int c = 0; c < D0; ++c) fz[c] += __ldg(p.fuse_c + c);
+            for (int c = 0; c < 8; ++c) fz[c] += fc[c];
             if (act0) {
                 for (int tau = r & 1; tau < 3; tau += 2) {
                     const int j = (r - tau) >> 1;
                     if (r < tau || j >= n1) continue;
-                    const float4* up = reinterpret_cast<const float4*>(p.sc_u + ((size_t)b * n1 + j) * 96 + tau * D0);
-#pragma unroll
-                    for (int c4 = 0; c4 < D0 / 4; ++c4) {
-                        const float4 v = __ldcg(up + c4);
-                        fz[4 * c4] += v.x; fz[4 * c4 + 1] += v.y; fz[4 * c4 + 2] += v.z; fz[4 * c4 + 3] += v.w;
-                    }
+                    const float4* up = reinterpret_cast<const float4*>(p.sc_u + ((size_t)b * n1 + j) * 96 + tau * D0 + c8);
+                    const float4 v0 = __ldcg(up), v1 = __ldcg(up + 1);
+                    fz[0] += v0.x; fz[1] += v0.y; fz[2] += v0.z; fz[3] += v0.w;
+                    fz[4] += v1.x; fz[5] += v1.y; fz[6] += v1.z; fz[7] += v1.w;
                 }
             }
             if (pad0) {
 #pragma unroll
-                for (int c = 0; c < D0; ++c) fz[c] = 0.f;
+                for (int c = 0; c < 8; ++c) fz[c] = 0.f;
             }
             if (act0) {
-                float4* dst = reinterpret_cast<float4*>(p.fused4 + row * 128);
-#pragma unroll
-                for (int c4 = 0; c4 < D0 / 4; ++c4) dst[c4] = make_float4(fz[4 * c4], fz[4 * c4 + 1], fz[4 * c4 + 2], fz[4 * c4 + 3]);
+                float4* dst = reinterpret_cast<float4*>(p.fused4 + row * 128 + c8);
+                dst[0] = make_float4(fz[0], fz[1], fz[2], fz[3]);
+                dst[1] = make_float4(fz[4], fz[5], fz[6], fz[7]);
             }
-            stage_row<D0>(xa, XA_LBO, XA_PLANE, r + 1, fz, act0);
+            stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, fz, act0);
             // halo rows of the three predictor tiles (the attention region is free from here on)
             if (tid < 48) {
                 const int i = tid >> 4, pc = tid & 3, pl = (tid >> 2) & 1, which = (tid >> 3) & 1;
@@ -629,14 +686,16 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             gemm_done(true);
 #pragma unroll 1
             for (int i = 0; i < 3; ++i) {
-                float y[D0];
-                tm_load32(trow, 32 * i, y);
+                float y[8];
+                tm_load<8>(trow + (uint32_t)(32 * i + c8), y);
+                float cb[8];
+                ldv<8>(p.pred[i].conv1_b + c8, cb);
 #pragma unroll
-                for (int c = 0; c < D0; ++c) y[c] = fmaxf(y[c] + __ldg(p.pred[i].conv1_b + c), 0.f);
-                ln_row<D0>(y, p.pred[i].ln1_g, p.pred[i].ln1_b);
+                for (int c = 0; c < 8; ++c) y[c] = fmaxf(y[c] + cb[c], 0.f);
+                ln_cols(I8{}, y, p.pred[i].ln1_g + c8, p.pred[i].ln1_b + c8);
 #pragma unroll
-                for (int c = 0; c < D0; ++c) y[c] = fmaxf(y[c], 0.f);
-                stage_row<D0>(op + (uint32_t)i * Y1_TILE, XA_LBO, Y1_PLANE, r + 1, y, act0);
+                for (int c = 0; c < 8; ++c) y[c] = fmaxf(y[c], 0.f);
+                stage_cols<8>(op + (uint32_t)i * Y1_TILE, XA_LBO, Y1_PLANE, r + 1, cq, y, act0);
             }
             PHASE_SYNC();
             w = w_wait();                                        // conv2 + ReLU, scalar head on the pre-LN2 values
@@ -644,33 +703,36 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 for (int i = 0; i < 3; ++i)
                     issue_gemm(elected, tmem + 32 * i, op_addr + (uint32_t)i * Y1_TILE, XA_LBO, Y1_PLANE, w + (uint32_t)i * 12288u, D0, D0, 3);
             gemm_done(true);
-#pragma unroll 1
+            float y2[3][8], dot[3];
+#pragma unroll
             for (int i = 0; i < 3; ++i) {
-                float y[D0];
-                tm_load32(trow, 32 * i, y);
-                float dot = 0.f;
+                tm_load<8>(trow + (uint32_t)(32 * i + c8), y2[i]);
+                dot[i] = 0.f;
+                float cb[8], lw[8];
+                ldv<8>(p.pred[i].conv2_b + c8, cb);
+                ldv<8>(p.pred[i].lin_w + c8, lw);
 #pragma unroll
-                for (int c = 0; c < D0; ++c) {
-                    y[c] = fmaxf(y[c] + __ldg(p.pred[i].conv2_b + c), 0.f);
-                    dot = fmaf(y[c], __ldg(p.pred[i].lin_w + c), dot);
+                for (int c = 0; c < 8; ++c) {
+                    y2[i][c] = fmaxf(y2[i][c] + cb[c], 0.f);
+                    dot[i] = fmaf(y2[i][c], lw[c], dot[i]);
                 }
-                dot += __ldg(p.pred[i].lin_b);
-                if (i == 2) {
-                    dot = fmaxf(dot, 0.f);                       // duration: extra ReLU (networks.py:161-163)
-                    ln_row<D0>(y, p.pred[2].ln2_g, p.pred[2].ln2_b);   // features = LN2(y), consumed for duration only
-                    if (act0) {
-                        float4* dst = reinterpret_cast<float4*>(p.fused4 + row * 128 + 3 * D0);
-#pragma unroll
-                        for (int c4 = 0; c4 < D0 / 4; ++c4)
-                            dst[c4] = pad0 ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(y[4 * c4], y[4 * c4 + 1], y[4 * c4 + 2], y[4 * c4 + 3]);
-                    }
-                }
-                pred[i] = dot;
             }
+            const float2 d01 = row_sum2(dot[0], dot[1]);
+            const float2 d2 = row_sum2(dot[2], 0.f);
+            pred[0] = d01.x + __ldg(p.pred[0].lin_b);
+            pred[1] = d01.y + __ldg(p.pred[1].lin_b);
+            pred[2] = fmaxf(d2.x + __ldg(p.pred[2].lin_b), 0.f);  // duration: extra ReLU (networks.py:161-163)
+            ln_cols(I8{}, y2[2], p.pred[2].ln2_g + c8, p.pred[2].ln2_b + c8);   // features = LN2(y), consumed for duration only
             if (act0) {
-                p.pitch_pred[row] = pred[0];
-                p.energy_pred[row] = pred[1];
-                p.dur_pred[row] = pred[2];
+                float4* dst = reinterpret_cast<float4*>(p.fused4 + row * 128 + 3 * D0 + c8);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                dst[0] = pad0 ? z : make_float4(y2[2][0], y2[2][1], y2[2][2], y2[2][3]);
+                dst[1] = pad0 ? z : make_float4(y2[2][4], y2[2][5], y2[2][6], y2[2][7]);
+                if (cq == 0) {
+                    p.pitch_pred[row] = pred[0];
+                    p.energy_pred[row] = pred[1];
+                    p.dur_pred[row] = pred[2];
+                }
             }
         }
         // ================================================================= variance embeddings, durations, scan
@@ -681,34 +743,34 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 if (pad0) df = 0.f;
                 df = fminf(fmaxf(df, 0.f), 65535.f);
                 dv = (int)df;
-                p.dur_int[row] = dv;
+                if (cq == 0) p.dur_int[row] = dv;
                 const float pv = p.pitch_tgt ? p.pitch_tgt[row] : pred[0];
                 const float ev = p.energy_tgt ? p.energy_tgt[row] : pred[1];
                 const int pi = bucket_left(p.pred[0].bins, D0 - 1, pv);
                 const int ei = bucket_left(p.pred[1].bins, D0 - 1, ev);
-                const float4* pt = reinterpret_cast<const float4*>(p.pred[0].table + (size_t)pi * D0);
-                const float4* et = reinterpret_cast<const float4*>(p.pred[1].table + (size_t)ei * D0);
-                float4* dp = reinterpret_cast<float4*>(p.fused4 + row * 128 + D0);
-                float4* de = reinterpret_cast<float4*>(p.fused4 + row * 128 + 2 * D0);
+                const float4* pt = reinterpret_cast<const float4*>(p.pred[0].table + (size_t)pi * D0 + c8);
+                const float4* et = reinterpret_cast<const float4*>(p.pred[1].table + (size_t)ei * D0 + c8);
+                float4* dp = reinterpret_cast<float4*>(p.fused4 + row * 128 + D0 + c8);
+                float4* de = reinterpret_cast<float4*>(p.fused4 + row * 128 + 2 * D0 + c8);
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int c4 = 0; c4 < D0 / 4; ++c4) {
-                    dp[c4] = pad0 ? z : __ldg(pt + c4);
-                    de[c4] = pad0 ? z : __ldg(et + c4);
-                }
+                dp[0] = pad0 ? z : __ldg(pt); dp[1] = pad0 ? z : __ldg(pt + 1);
+                de[0] = pad0 ? z : __ldg(et); de[1] = pad0 ? z : __ldg(et + 1);
             }
-            int incl = dv;                                      // warp-shuffle inclusive scan, then the 4 warp totals
+            // block scan over the 128 rows: done by the cq == 0 threads (warps 0..3), warp-shuffle scan + 4 warp totals
+            int incl = dv;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int y = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += y;
             }
-            if (lane == 31) s_wtot[warp] = incl;
+            if (cq == 0 && lane == 31) s_wtot[rq] = incl;
             __syncthreads();
-            int prefix = 0;
-            for (int w = 0; w < warp; ++w) prefix += s_wtot[w];
-            if (act0) p.dur_cum[row] = prefix + incl;
-            if (tid == PM - 1) p.mel_len[b] = prefix + incl;
+            if (cq == 0) {
+                int prefix = 0;
+                for (int w = 0; w < rq; ++w) prefix += s_wtot[w];
+                if (act0) p.dur_cum[row] = prefix + incl;
+                if (r == PM - 1) p.mel_len[b] = prefix + incl;
+            }
             // s_wtot is rewritten only after several __syncthreads of the next utterance
         }
     }
@@ -764,7 +826,7 @@ int launch_umma_phoneme(const es_config_t& cfg, const es_weights_t& w, int B, in
     p.scale_log2e = 1.4426950408889634f / sqrtf(32.f);
     p.err = err_flag;
     const int grid = B < n_sm ? B : n_sm;
-    ES_CUDA(launch_pdl(umma_phoneme_kernel, grid, PM, PH_SMEM, s, p));
+    ES_CUDA(launch_pdl(umma_phoneme_kernel, grid, NTHR, PH_SMEM, s, p));
     ES_LAUNCH_OK();
     return 0;
 }
