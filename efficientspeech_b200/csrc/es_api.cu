@@ -384,7 +384,7 @@ int es_encoder_forward(es_model_t* m, void* stream, int B, int N,
     const int d = m->d, n1 = enc_n1(m, N);
 
     // tiny geometry, N <= 128: the whole phoneme side in ONE kernel, activations never leave the SM (es_umma_phoneme.cu)
-    if (m->use_tensor_core && m->fused_phoneme) {
+    if (m->use_tensor_core && m->fused_phoneme && umma_phoneme_supported(m->cfg, m->w, N) && n1 <= 64) {
         const int pool = (int)nearbyintf((float)((double)N / (double)n1));
         int rc;
         { ProfRange r(ES_K_PHONEME, s);
