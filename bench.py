@@ -213,6 +213,10 @@ def run_b200_arm(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, set on some boxes)
+        # would precede it, so anything below WARN is raised to WARN unless the caller asked for INFO / TRACE
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = es.VARIANTS[a.variant]
@@ -401,6 +405,22 @@ def run_b200_arm(a):
                 "share_of_step": float(np.sum(dl)) / float(sum(np.sum(v) for v in per_kind.values())),
                 "timed_region": "second pass of the same K steps: eager launches queued behind a device-side spin, "
                                 "CUDA events around every kernel on the launching stream"}
+    if roof is not None and len(dl) == L * a.steps:
+        # the same numbers per layer position (launch order within a step): the four launches are different
+        # instantiations with different algorithmic bytes, and the average above hides which one is how far off
+        row_b = B * T * cfg.dx2 * 4
+        tab_b = (B * N + 1) * cfg.dx2 * 4
+        per_layer = []
+        for l in range(L):
+            blk, pos = divmod(l, cfg.block_depth)
+            last = pos == cfg.block_depth - 1
+            x_b = tab_b if (gather_fused and l == 0) else row_b
+            skip_b = 0 if not last else (tab_b if (gather_fused and blk == 0) else row_b)
+            by = x_b + skip_b + row_b
+            ms_l = float(np.mean(dl[l::L]))
+            per_layer.append({"layer": l, "block_end": bool(last), "gathered": bool(gather_fused and blk == 0 and (l == 0 or last)),
+                              "algorithmic_bytes": by, "ms": ms_l, "frac": by / (ms_l * 1e-3) / 1e9 / hbm_peak})
+        roof["per_layer"] = per_layer
     kernel_ms = {k: float(np.sum(v)) / a.steps for k, v in per_kind.items()}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,

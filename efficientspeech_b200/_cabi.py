@@ -73,6 +73,7 @@ PROTOTYPES = {
     "es_dense_layout": (_i, [_i, _i, _i, _i]),
     "es_check_async_errors": (_i, [_vp]),
     "es_debug_set_trace": (_i, [_vp]),
+    "es_debug_set_phoneme_trace": (_i, [_vp]),
     "es_launch_count": (C.c_uint64, []),
     "es_profile_begin": (_i, [_i]),
     "es_profile_end": (_i, []),
@@ -84,7 +85,8 @@ _lib: Optional[C.CDLL] = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # $ES_B200_LIB: an alternative build of the same sources (A/B experiments, efficientspeech_b200/build.py)
+    return os.environ.get("ES_B200_LIB") or _build.LIB_PATH
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:

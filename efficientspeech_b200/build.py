@@ -39,10 +39,12 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB_PATH) -> str:
+    """`defines` / `out`: experiment builds (e.g. -DES_MBAR_SUSPEND_NS=0 into a second .so selected with
+    $ES_B200_LIB); the default build takes neither."""
+    if not force and not defines and out == LIB_PATH and not needs_build():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + sources() + ["-o", LIB_PATH, "-lcudart"]
+    cmd = [find_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + sources() + ["-o", out, "-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(PKG_DIR, "build.log"), "w") as f:
@@ -52,8 +54,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libes_b200.so")
     if verbose:
         print(log)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose=not defs, defines=defs, out=outs[0] if outs else LIB_PATH))

@@ -268,6 +268,7 @@ int es_abi_version(void) { return ES_ABI_VERSION; }
 const char* es_last_error(void) { return es::g_error.c_str(); }
 uint64_t es_launch_count(void) { return es::g_launches.load(); }
 int es_debug_set_trace(void* dev_buf_i64) { es::umma_dec_set_trace(static_cast<long long*>(dev_buf_i64)); return 0; }
+int es_debug_set_phoneme_trace(void* dev_buf_i64) { es::umma_phoneme_set_trace(static_cast<long long*>(dev_buf_i64)); return 0; }
 int es_dense_layout(int K, int n_out, int taps, int stride) { return es::dense_layout(K, n_out, taps, stride); }
 int es_check_async_errors(void* stream) { return es::umma_dec_check_errors(static_cast<cudaStream_t>(stream)); }
 

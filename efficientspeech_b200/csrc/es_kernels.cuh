@@ -60,6 +60,7 @@ int launch_umma_wide(const RowGemmParams& p, const void* w_units, cudaStream_t s
 // the whole phoneme side (PhonemeEncoder.forward up to the upsampler) in one kernel for the tiny geometry
 // (es_umma_phoneme.cu); -1: outside its envelope
 bool umma_phoneme_supported(const es_config_t& cfg, const es_weights_t& w, int N);
+void umma_phoneme_set_trace(long long* buf);   // debug: [2][128] (clock64, event code) pairs of CTA 0, or null
 int launch_umma_phoneme(const es_config_t& cfg, const es_weights_t& w, int B, int N, int n1, int pool,
                         const int32_t* ids, const uint8_t* mask, const float* pitch_tgt, const float* energy_tgt,
                         const int32_t* dur_tgt, float* pitch_pred, float* energy_pred, float* dur_pred, float* fused4,

@@ -44,14 +44,25 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 }
 // suspend-time hint: a waiting thread may sleep in hardware until the phase completes (or this many
 // ns pass) instead of re-issuing the test -- the spinning warps otherwise compete for issue slots
-constexpr uint32_t kMbarSuspendNs = 20000;
+#ifndef ES_MBAR_SUSPEND_NS
+#define ES_MBAR_SUSPEND_NS 20000
+#endif
+constexpr uint32_t kMbarSuspendNs = ES_MBAR_SUSPEND_NS;      // 0: plain try_wait (implementation-defined short limit)
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity), "r"(kMbarSuspendNs) : "memory");
+    if (kMbarSuspendNs != 0) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(kMbarSuspendNs) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
     return ok != 0;
 }
 // Bounded wait: a wrong descriptor must not hang the GPU.  Returns false on timeout (~seconds).

@@ -59,7 +59,8 @@ constexpr uint32_t OFF_XA = OFF_VT + 16384;                    // halo A tile (h
 constexpr uint32_t OFF_WB = OFF_XA + 2 * XA_PLANE;             // two weight buffers
 constexpr uint32_t OFF_RED = OFF_WB + 2 * WB_BYTES;            // row reductions: [2][4][128] float2
 constexpr uint32_t OFF_MISC = OFF_RED + 2 * 4 * PM * 8;        // scan scratch
-constexpr uint32_t OFF_BAR = OFF_MISC + 64;                    // bar_mma, bar_w[2], tmem slot
+constexpr uint32_t OFF_BINS = OFF_MISC + 64;                   // pitch | energy bucket boundaries: 2 x 32 floats
+constexpr uint32_t OFF_BAR = OFF_BINS + 2 * 32 * 4;            // bar_mma, bar_w[2], tmem slot
 constexpr uint32_t PH_SMEM = OFF_BAR + 64;
 static_assert(OFF_WB % 16 == 0 && OFF_XA % 16 == 0, "bulk copies need 16-byte aligned destinations");
 static_assert(PH_SMEM <= 227 * 1024, "shared memory budget");
@@ -81,6 +82,7 @@ struct PhonemeParams {
     float* sc_u;                                 // [B][n1][96]  Fuse: U rows of the half-rate positions
     float scale_log2e;                           // (C // H)^-0.5 * log2(e): 32^-0.5 at both levels
     int* err;
+    long long* trace;                            // debug: clock64 stamps of CTA 0 / thread 0, [2 utterances][128 events], or null
 };
 
 __device__ __forceinline__ float ex2f_approx(float x) {
@@ -144,30 +146,39 @@ __device__ __forceinline__ void tm_load(uint32_t taddr, float* v) {
     for (int j = 0; j < NV; ++j) v[j] = __uint_as_float(rr[j]);
 }
 
-// D[tmem_d] = A . W^T over `taps` row-shifted views of the A tile (issued by warp 0; `elected` = its issuing lane)
+// D[tmem_d] = A . B^T, issued by warp 0 (`elected` = its issuing lane).  A: row-panel tile (K panel stride a_lbo,
+// lo plane at +a_plane); conv tap t reads it shifted by t rows (16 bytes).  B: [N rows][K] in the same layout
+// (panel stride b_lbo, lo plane at +b_plane, tap t at +t*b_tap).  The four descriptors advance by a constant per
+// K step (start-address field, 16-byte units), so a K step costs 4 adds + 3 tcgen05.mma.
 __device__ __noinline__ void issue_gemm(bool elected, uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_plane,
-                                        uint32_t w_addr, int K, int N, int taps) {
+                                        uint32_t b_addr, uint32_t b_lbo, uint32_t b_plane, uint32_t b_tap,
+                                        int ksteps, int N, int taps) {
     const uint32_t idesc = make_idesc_f16(PM, N);
-    const uint32_t lbo_b = (uint32_t)N * 16u, w_plane = (uint32_t)N * (uint32_t)K * 2u;
+    const uint64_t da_step = (uint64_t)((2u * a_lbo) >> 4), db_step = (uint64_t)((2u * b_lbo) >> 4);
     uint32_t acc = 0;
 #pragma unroll 1
     for (int t = 0; t < taps; ++t) {
+        uint64_t dah = make_smem_desc(a_addr + (uint32_t)t * 16u, a_lbo, 128u);
+        uint64_t dal = make_smem_desc(a_addr + a_plane + (uint32_t)t * 16u, a_lbo, 128u);
+        uint64_t dbh = make_smem_desc(b_addr + (uint32_t)t * b_tap, b_lbo, 128u);
+        uint64_t dbl = make_smem_desc(b_addr + b_plane + (uint32_t)t * b_tap, b_lbo, 128u);
 #pragma unroll 1
-        for (int ks = 0; ks < (K >> 4); ++ks) {
-            const uint32_t a_off = (uint32_t)t * 16u + (uint32_t)(2 * ks) * a_lbo;
-            const uint64_t dah = make_smem_desc(a_addr + a_off, a_lbo, 128u);
-            const uint64_t dal = make_smem_desc(a_addr + a_plane + a_off, a_lbo, 128u);
-            const uint32_t b_off = (uint32_t)(t * 2) * w_plane + (uint32_t)(2 * ks) * lbo_b;
-            const uint64_t dbh = make_smem_desc(w_addr + b_off, lbo_b, 128u);
-            const uint64_t dbl = make_smem_desc(w_addr + w_plane + b_off, lbo_b, 128u);
+        for (int ks = 0; ks < ksteps; ++ks) {
             if (elected) {
                 mma_f16_ss(tmem_d, dah, dbh, idesc, acc);
                 mma_f16_ss(tmem_d, dah, dbl, idesc, 1u);
                 mma_f16_ss(tmem_d, dal, dbh, idesc, 1u);
             }
             acc = 1;
+            dah += da_step; dal += da_step; dbh += db_step; dbl += db_step;
         }
     }
+}
+// dense layer with packed weights [taps][hi, lo][K/8][N][8]
+__device__ __forceinline__ void issue_layer(bool elected, uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_plane,
+                                            uint32_t w_addr, int K, int N, int taps) {
+    const uint32_t w_plane = (uint32_t)N * (uint32_t)K * 2u;
+    issue_gemm(elected, tmem_d, a_addr, a_lbo, a_plane, w_addr, (uint32_t)N * 16u, w_plane, 2u * w_plane, K >> 4, N, taps);
 }
 
 // NV (multiple of 4) consecutive per-channel parameters (bias, LayerNorm gain, ...) with 128-bit loads; the
@@ -181,11 +192,11 @@ __device__ __forceinline__ void ldv(const float* __restrict__ src, float* v) {
     }
 }
 
-__device__ __forceinline__ int bucket_left(const float* __restrict__ bins, int nb, float v) {
+__device__ __forceinline__ int bucket_left(const float* bins, int nb, float v) {      // bins: shared memory
     int lo = 0, hi = nb;                          // #{j : bins[j] < v}   (torch.bucketize, right=False; networks.py:130-141)
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (__ldg(bins + mid) < v) lo = mid + 1; else hi = mid;
+        if (bins[mid] < v) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -201,6 +212,8 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
     uint8_t* xa = smem + OFF_XA;
     float2* red = reinterpret_cast<float2*>(smem + OFF_RED);
     int* s_wtot = reinterpret_cast<int*>(smem + OFF_MISC);
+    float* s_bins = reinterpret_cast<float*>(smem + OFF_BINS);
+    float* u_s = reinterpret_cast<float*>(smem + OFF_OP);      // Fuse: U rows [n1][96] (the attention region is free by then)
     const uint32_t bar_mma = smem_u32(smem + OFF_BAR);
     const uint32_t bar_w = bar_mma + 8;                        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 32);
@@ -260,6 +273,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         mbar_init(bar_w + 8, 1);
         fence_mbar_init();
     }
+    if (tid < 64) s_bins[tid] = (tid & 31) < D0 - 1 ? __ldg((tid < 32 ? p.pred[0].bins : p.pred[1].bins) + (tid & 31)) : 0.f;
     // zero halo rows (tile rows 0 and 129) of the A tile: never written afterwards
     if (tid < 32) {
         const int pc = tid & 7, pl = (tid >> 3) & 1, which = tid >> 4;
@@ -279,10 +293,21 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
     uint32_t mph = 0;                                           // bar_mma phase parity
     int wg = 0;                                                 // next weight phase to be consumed (global index)
     int flip = 0;                                               // ping-pong half of `red`
+    // debug timeline (tools/trace_phoneme.py): thread 0 of CTA 0 stamps every GEMM completion (odd codes) and phase sync
+    int tr_k = 0, tr_u = 0;
+    auto stamp = [&](int code) {
+        if (p.trace && blockIdx.x == 0 && tid == 0 && tr_u < 2 && tr_k < 128) {
+            p.trace[tr_u * 256 + 2 * tr_k] = clock64();
+            p.trace[tr_u * 256 + 2 * tr_k + 1] = code;
+            ++tr_k;
+        }
+    };
 
     // warp 0 waits for weight load `wg`; returns its shared-memory address
     auto w_wait = [&]() -> uint32_t {
+        stamp(4);
         if (warp == 0 && !spin_wait(bar_w + 8u * (uint32_t)(wg & 1), (uint32_t)(wg >> 1) & 1u)) failed = true;
+        stamp(5);
         return wb_addr + (uint32_t)(wg & 1) * WB_BYTES;
     };
     // commit the issued MMAs, wait for them, then refill the weight buffer they used (two phases ahead)
@@ -298,6 +323,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             if (tid == 0) wload(wg + 2);
             ++wg;
         }
+        stamp(used_weights ? 1 : 3);
     };
     // combine two per-thread partials over the four threads of a row (same order in all four -> identical results).
     // One barrier per call: the buffer halves alternate, and a half is rewritten only after the barrier of the
@@ -307,6 +333,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         flip ^= 1;
         bf[cq * PM + r] = make_float2(a, b2);
         __syncthreads();
+        stamp(6);
         const float2 t0 = bf[r], t1 = bf[PM + r], t2 = bf[2 * PM + r], t3 = bf[3 * PM + r];
         return make_float2((t0.x + t1.x) + (t2.x + t3.x), (t0.y + t1.y) + (t2.y + t3.y));
     };
@@ -364,23 +391,9 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 }
             }
         }
-        PHASE_SYNC();
+        PHASE_SYNC(); stamp(2);
         // 2. S = Q K^T  -> columns [0, NK)
-        if (warp == 0) {
-            const uint32_t idesc = make_idesc_f16(PM, NK);
-#pragma unroll 1
-            for (int ks = 0; ks < (C >> 4); ++ks) {
-                const uint32_t o = (uint32_t)(2 * ks) * PANEL;
-                const uint64_t dqh = make_smem_desc(op_addr + o, PANEL, 128u), dql = make_smem_desc(op_addr + qk_plane + o, PANEL, 128u);
-                const uint64_t dkh = make_smem_desc(op_addr + 2 * qk_plane + o, PANEL, 128u);
-                const uint64_t dkl = make_smem_desc(op_addr + 3 * qk_plane + o, PANEL, 128u);
-                if (elected) {
-                    mma_f16_ss(tmem, dqh, dkh, idesc, ks > 0 ? 1u : 0u);
-                    mma_f16_ss(tmem, dqh, dkl, idesc, 1u);
-                    mma_f16_ss(tmem, dql, dkh, idesc, 1u);
-                }
-            }
-        }
+        if (warp == 0) issue_gemm(elected, tmem, op_addr, PANEL, qk_plane, op_addr + 2 * qk_plane, PANEL, qk_plane, 0u, C >> 4, NK, 1);
         gemm_done(false);
         // 3. softmax over the n keys (unmasked: blocks.py:59-63), P -> split fp16 over the dead Q/K tiles
         {
@@ -405,47 +418,20 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             for (int j = 0; j < SV; ++j) s[j] *= inv;
             stage_cols<SV>(op, PANEL, p_plane, r, (SV / 8) * cq, s, true);
         }
-        PHASE_SYNC();
+        PHASE_SYNC(); stamp(2);
         // 4. O = P V  -> columns [oc, oc + C)
-        if (warp == 0) {
-            const uint32_t idesc = make_idesc_f16(PM, C);
-#pragma unroll 1
-            for (int ks = 0; ks < (NK >> 4); ++ks) {
-                const uint64_t dph = make_smem_desc(op_addr + (uint32_t)(2 * ks) * PANEL, PANEL, 128u);
-                const uint64_t dpl = make_smem_desc(op_addr + p_plane + (uint32_t)(2 * ks) * PANEL, PANEL, 128u);
-                const uint64_t dvh = make_smem_desc(vt_addr + (uint32_t)(2 * ks) * vt_lbo, vt_lbo, 128u);
-                const uint64_t dvl = make_smem_desc(vt_addr + vt_plane + (uint32_t)(2 * ks) * vt_lbo, vt_lbo, 128u);
-                if (elected) {
-                    mma_f16_ss(tmem + (uint32_t)oc, dph, dvh, idesc, ks > 0 ? 1u : 0u);
-                    mma_f16_ss(tmem + (uint32_t)oc, dph, dvl, idesc, 1u);
-                    mma_f16_ss(tmem + (uint32_t)oc, dpl, dvh, idesc, 1u);
-                }
-            }
-        }
+        if (warp == 0) issue_gemm(elected, tmem + (uint32_t)oc, op_addr, PANEL, p_plane, vt_addr, vt_lbo, vt_plane, 0u, NK >> 4, C, 1);
         gemm_done(false);
     };
 
     const int c8 = 8 * cq, c16 = 16 * cq;                       // this thread's first column of a 32- / 64-wide row
 
-    for (int ui = 0; ui < my_utts; ++ui) {
-        const int b = (int)blockIdx.x + ui * (int)gridDim.x;
-        const size_t row = (size_t)b * N + r;
-        const bool act0 = r < N, act1 = r < n1;
-        const bool pad0 = act0 && p.mask && p.mask[row];
-        bool pad1 = false;                                      // pooled mask of block 1 (blocks.py:51-57)
-        if (act1 && p.mask) {
-            for (int q = 0; q < p.pool; ++q) {
-                const int t = r * p.pool + q;
-                pad1 = pad1 || (t < N ? p.mask[(size_t)b * N + t] != 0 : true);
-            }
-        }
-
-        // ================================================================= block 0 (8 columns per thread)
-        // x0 = sum_tau Tab[tau][id[t + tau - 1]]   (embedding + merge conv + 1x1 folded into 3 gather tables)
-        float x0[8];
+    // x0 = sum_tau Tab[tau][id[t + tau - 1]]   (embedding + merge conv + 1x1 folded into 3 gather tables);
+    // two dependent global loads, so the row of the NEXT utterance is fetched while this one runs its predictors
+    auto gather_x0 = [&](int b, float* x0) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) x0[c] = 0.f;
-        if (act0) {
+        if (r < N) {
             for (int tau = 0; tau < 3; ++tau) {
                 const int ti = r + tau - 1;
                 if (ti < 0 || ti >= N) continue;
@@ -457,11 +443,42 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 x0[4] += v1.x; x0[5] += v1.y; x0[6] += v1.z; x0[7] += v1.w;
             }
         }
+    };
+    float x0n[8];
+    if (my_utts > 0) gather_x0((int)blockIdx.x, x0n);
+
+    for (int ui = 0; ui < my_utts; ++ui) {
+        const int b = (int)blockIdx.x + ui * (int)gridDim.x;
+        const size_t row = (size_t)b * N + r;
+        const bool act0 = r < N, act1 = r < n1;
+        tr_k = 0; tr_u = ui;
+        stamp(0);
+        const bool pad0 = act0 && p.mask && p.mask[row];
+        bool pad1 = false;                                      // pooled mask of block 1 (blocks.py:51-57)
+        if (act1 && p.mask) {
+            for (int q = 0; q < p.pool; ++q) {
+                const int t = r * p.pool + q;
+                pad1 = pad1 || (t < N ? p.mask[(size_t)b * N + t] != 0 : true);
+            }
+        }
+
+        // ================================================================= block 0 (8 columns per thread)
+        float x0[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x0[c] = x0n[c];
+        // per-row scalars of the variance stage: requested now, consumed ~70 us later
+        float tgt_p = 0.f, tgt_e = 0.f;
+        int tgt_d = 0;
+        if (act0) {
+            if (p.pitch_tgt) tgt_p = __ldg(p.pitch_tgt + row);
+            if (p.energy_tgt) tgt_e = __ldg(p.energy_tgt + row);
+            if (p.dur_tgt) tgt_d = __ldg(p.dur_tgt + row);
+        }
         stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, x0, act0);
-        PHASE_SYNC();
+        PHASE_SYNC(); stamp(2);
         {   // qkv0: [32] -> [96] into columns [128, 224)
             const uint32_t w = w_wait();
-            if (warp == 0) issue_gemm(elected, tmem + 128, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, 96, 1);
+            if (warp == 0) issue_layer(elected, tmem + 128, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, 96, 1);
             gemm_done(true);
         }
         attention(std::integral_constant<int, D0>{}, std::integral_constant<int, PM>{}, N, 128, 160, 192, 128);
@@ -470,9 +487,9 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             float o[8];
             tm_load<8>(trow + (uint32_t)(128 + c8), o);
             stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, o, act0);
-            PHASE_SYNC();
+            PHASE_SYNC(); stamp(2);
             const uint32_t w = w_wait();
-            if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
+            if (warp == 0) issue_layer(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
             gemm_done(true);
             tm_load<8>(trow + (uint32_t)c8, x1);
             float pb[8];
@@ -485,12 +502,12 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 for (int c = 0; c < 8; ++c) x1[c] = 0.f;
             }
             stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, x1, act0);
-            PHASE_SYNC();
+            PHASE_SYNC(); stamp(2);
         }
         float f0[8];
         {   // MixFFN: conv3 (mlp1 folded) + GELU, mlp2 + residual + LN2 + mask
             uint32_t w = w_wait();
-            if (warp == 0) issue_gemm(elected, tmem, xa_addr, XA_LBO, XA_PLANE, w, D0, D0, 3);
+            if (warp == 0) issue_layer(elected, tmem, xa_addr, XA_LBO, XA_PLANE, w, D0, D0, 3);
             gemm_done(true);
             float h[8];
             tm_load<8>(trow + (uint32_t)c8, h);
@@ -509,9 +526,9 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 h[c] = gelu_erf_f(v);
             }
             stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, h, act0);
-            PHASE_SYNC();
+            PHASE_SYNC(); stamp(2);
             w = w_wait();
-            if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
+            if (warp == 0) issue_layer(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
             gemm_done(true);
             tm_load<8>(trow + (uint32_t)c8, f0);
             float f2b[8];
@@ -524,12 +541,12 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 for (int c = 0; c < 8; ++c) f0[c] = 0.f;
             }
             stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, f0, act0);
-            PHASE_SYNC();
+            PHASE_SYNC(); stamp(2);
         }
         // ================================================================= block 1 (16 columns per thread)
         {   // merge conv (1 tap, stride 2): xm1[j] = W feat0[2j]; computed for every row, even rows are kept
             const uint32_t w = w_wait();
-            if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D1, 1);
+            if (warp == 0) issue_layer(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D1, 1);
             gemm_done(true);
             float y[16];
             tm_load<16>(trow + (uint32_t)c16, y);
@@ -541,11 +558,11 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 stage_cols<16>(xa, XA_LBO, XA_PLANE, j + 1, 2 * cq, y, true);
             }
             if (r >= n1) stage_cols<16>(xa, XA_LBO, XA_PLANE, r + 1, 2 * cq, y, false);      // zero rows n1..127
-            PHASE_SYNC();
+            PHASE_SYNC(); stamp(2);
         }
         for (int s = 0; s < 3; ++s) {   // q | k | v of both heads: [64] -> [128] into columns 128 + 128 s
             const uint32_t w = w_wait();
-            if (warp == 0) issue_gemm(elected, tmem + 128 + 128 * s, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, 128, 1);
+            if (warp == 0) issue_layer(elected, tmem + 128 + 128 * s, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, 128, 1);
             gemm_done(true);
         }
         for (int hd = 0; hd < 2; ++hd)
@@ -556,9 +573,9 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             float o[32];
             tm_load<32>(trow + (uint32_t)(128 + 32 * cq), o);
             stage_cols<32>(op, PANEL, 16 * PANEL, r, 4 * cq, o, act1);
-            PHASE_SYNC();
+            PHASE_SYNC(); stamp(2);
             const uint32_t w = w_wait();
-            if (warp == 0) issue_gemm(elected, tmem, op_addr, PANEL, 16 * PANEL, w, 128, D1, 1);
+            if (warp == 0) issue_layer(elected, tmem, op_addr, PANEL, 16 * PANEL, w, 128, D1, 1);
             gemm_done(true);
             tm_load<16>(trow + (uint32_t)c16, x1b);
             if (act1) {
@@ -579,11 +596,11 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 for (int c = 0; c < 16; ++c) x1b[c] = 0.f;
             }
             stage_cols<16>(xa, XA_LBO, XA_PLANE, r + 1, 2 * cq, x1b, act1);
-            PHASE_SYNC();
+            PHASE_SYNC(); stamp(2);
         }
         {   // MixFFN of block 1
             uint32_t w = w_wait();
-            if (warp == 0) issue_gemm(elected, tmem, xa_addr, XA_LBO, XA_PLANE, w, D1, D1, 3);
+            if (warp == 0) issue_layer(elected, tmem, xa_addr, XA_LBO, XA_PLANE, w, D1, D1, 3);
             gemm_done(true);
             float h[16];
             tm_load<16>(trow + (uint32_t)c16, h);
@@ -602,9 +619,9 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 h[c] = gelu_erf_f(v);
             }
             stage_cols<16>(xa, XA_LBO, XA_PLANE, r + 1, 2 * cq, h, act1);
-            PHASE_SYNC();
+            PHASE_SYNC(); stamp(2);
             w = w_wait();
-            if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, D1, 1);
+            if (warp == 0) issue_layer(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, D1, 1);
             gemm_done(true);
             tm_load<16>(trow + (uint32_t)c16, h);
             float f2b[16];
@@ -617,13 +634,13 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 for (int c = 0; c < 16; ++c) h[c] = 0.f;
             }
             stage_cols<16>(xa, XA_LBO, XA_PLANE, r + 1, 2 * cq, h, act1);
-            PHASE_SYNC();
+            PHASE_SYNC(); stamp(2);
         }
         // ================================================================= Fuse (networks.py:189-219, folded)
         float fz[8];
         {
             uint32_t w = w_wait();                               // U = feat1 [G_0 | G_1 | G_2] + [g_0 | g_1 | g_2]
-            if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, 96, 1);
+            if (warp == 0) issue_layer(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, 96, 1);
             gemm_done(true);
 #pragma unroll 1
             for (int i = 0; i < 3; ++i) {   // 3 of the 12 8-column groups of U per thread
@@ -631,7 +648,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 float u[8];
                 tm_load<8>(trow + (uint32_t)c0, u);
                 if (act1) {
-                    float4* dst = reinterpret_cast<float4*>(p.sc_u + ((size_t)b * n1 + r) * 96 + c0);
+                    float4* dst = reinterpret_cast<float4*>(u_s + r * 96 + c0);
                     float gb[8];
                     ldv<8>(p.fuse_gb + c0, gb);
                     dst[0] = make_float4(u[0] + gb[0], u[1] + gb[1], u[2] + gb[2], u[3] + gb[3]);
@@ -640,9 +657,9 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             }
             stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, f0, act0);
             // rows of the K = 64 tile beyond panel 3 are not read by the K = 32 GEMMs that follow
-            PHASE_SYNC();                                        // also publishes the U rows to the CTA
+            PHASE_SYNC(); stamp(2);                                        // also publishes the U rows (shared memory) to the CTA
             w = w_wait();                                        // fused = mask(c + A0 feat0 + stride-2 scatter of U)
-            if (warp == 0) issue_gemm(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
+            if (warp == 0) issue_layer(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
             gemm_done(true);
             tm_load<8>(trow + (uint32_t)c8, fz);
             float fc[8];
@@ -653,8 +670,8 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 for (int tau = r & 1; tau < 3; tau += 2) {
                     const int j = (r - tau) >> 1;
                     if (r < tau || j >= n1) continue;
-                    const float4* up = reinterpret_cast<const float4*>(p.sc_u + ((size_t)b * n1 + j) * 96 + tau * D0 + c8);
-                    const float4 v0 = __ldcg(up), v1 = __ldcg(up + 1);
+                    const float4* up = reinterpret_cast<const float4*>(u_s + j * 96 + tau * D0 + c8);
+                    const float4 v0 = up[0], v1 = up[1];
                     fz[0] += v0.x; fz[1] += v0.y; fz[2] += v0.z; fz[3] += v0.w;
                     fz[4] += v1.x; fz[5] += v1.y; fz[6] += v1.z; fz[7] += v1.w;
                 }
@@ -669,21 +686,23 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 dst[1] = make_float4(fz[4], fz[5], fz[6], fz[7]);
             }
             stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, fz, act0);
-            // halo rows of the three predictor tiles (the attention region is free from here on)
-            if (tid < 48) {
-                const int i = tid >> 4, pc = tid & 3, pl = (tid >> 2) & 1, which = (tid >> 3) & 1;
-                *reinterpret_cast<uint4*>(op + (uint32_t)i * Y1_TILE + (uint32_t)pl * Y1_PLANE + (uint32_t)pc * XA_LBO +
-                                          (which ? (PM + 1) * 16u : 0u)) = make_uint4(0u, 0u, 0u, 0u);
-            }
-            PHASE_SYNC();
+            PHASE_SYNC(); stamp(2);                                        // every U read is done: the region becomes the predictor tiles
         }
         // ================================================================= predictors (networks.py:151-165)
         float pred[3];
         {
             uint32_t w = w_wait();                               // conv1 of the three predictors -> columns 0 | 32 | 64
             if (warp == 0)
-                for (int i = 0; i < 3; ++i) issue_gemm(elected, tmem + 32 * i, xa_addr, XA_LBO, XA_PLANE, w + (uint32_t)i * 12288u, D0, D0, 3);
+                for (int i = 0; i < 3; ++i) issue_layer(elected, tmem + 32 * i, xa_addr, XA_LBO, XA_PLANE, w + (uint32_t)i * 12288u, D0, D0, 3);
             gemm_done(true);
+            // next utterance's embedding row: in flight during the predictor and variance stages
+            if (ui + 1 < my_utts) gather_x0(b + (int)gridDim.x, x0n);
+            // halo rows of the three predictor tiles
+            if (tid < 48) {
+                const int i = tid >> 4, pc = tid & 3, pl = (tid >> 2) & 1, which = (tid >> 3) & 1;
+                *reinterpret_cast<uint4*>(op + (uint32_t)i * Y1_TILE + (uint32_t)pl * Y1_PLANE + (uint32_t)pc * XA_LBO +
+                                          (which ? (PM + 1) * 16u : 0u)) = make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll 1
             for (int i = 0; i < 3; ++i) {
                 float y[8];
@@ -697,11 +716,11 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
                 for (int c = 0; c < 8; ++c) y[c] = fmaxf(y[c], 0.f);
                 stage_cols<8>(op + (uint32_t)i * Y1_TILE, XA_LBO, Y1_PLANE, r + 1, cq, y, act0);
             }
-            PHASE_SYNC();
+            PHASE_SYNC(); stamp(2);
             w = w_wait();                                        // conv2 + ReLU, scalar head on the pre-LN2 values
             if (warp == 0)
                 for (int i = 0; i < 3; ++i)
-                    issue_gemm(elected, tmem + 32 * i, op_addr + (uint32_t)i * Y1_TILE, XA_LBO, Y1_PLANE, w + (uint32_t)i * 12288u, D0, D0, 3);
+                    issue_layer(elected, tmem + 32 * i, op_addr + (uint32_t)i * Y1_TILE, XA_LBO, Y1_PLANE, w + (uint32_t)i * 12288u, D0, D0, 3);
             gemm_done(true);
             float y2[3][8], dot[3];
 #pragma unroll
@@ -739,15 +758,15 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         {
             int dv = 0;
             if (act0) {
-                float df = p.dur_tgt ? (float)p.dur_tgt[row] : rintf(pred[2]);       // torch.round: half to even (networks.py:379)
+                float df = p.dur_tgt ? (float)tgt_d : rintf(pred[2]);                // torch.round: half to even (networks.py:379)
                 if (pad0) df = 0.f;
                 df = fminf(fmaxf(df, 0.f), 65535.f);
                 dv = (int)df;
                 if (cq == 0) p.dur_int[row] = dv;
-                const float pv = p.pitch_tgt ? p.pitch_tgt[row] : pred[0];
-                const float ev = p.energy_tgt ? p.energy_tgt[row] : pred[1];
-                const int pi = bucket_left(p.pred[0].bins, D0 - 1, pv);
-                const int ei = bucket_left(p.pred[1].bins, D0 - 1, ev);
+                const float pv = p.pitch_tgt ? tgt_p : pred[0];
+                const float ev = p.energy_tgt ? tgt_e : pred[1];
+                const int pi = bucket_left(s_bins, D0 - 1, pv);
+                const int ei = bucket_left(s_bins + 32, D0 - 1, ev);
                 const float4* pt = reinterpret_cast<const float4*>(p.pred[0].table + (size_t)pi * D0 + c8);
                 const float4* et = reinterpret_cast<const float4*>(p.pred[1].table + (size_t)ei * D0 + c8);
                 float4* dp = reinterpret_cast<float4*>(p.fused4 + row * 128 + D0 + c8);
@@ -773,6 +792,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             }
             // s_wtot is rewritten only after several __syncthreads of the next utterance
         }
+        stamp(9);
     }
 
     if (failed) atomicExch(p.err, 1);
@@ -782,6 +802,9 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
 }
 
 }  // namespace
+
+static long long* g_ph_trace = nullptr;
+void umma_phoneme_set_trace(long long* buf) { g_ph_trace = buf; }
 
 bool umma_phoneme_supported(const es_config_t& cfg, const es_weights_t& w, int N) {
     if (cfg.dim != D0 || cfg.head != 1 || cfg.kernel_size != 3 || cfg.expansion != 1) return false;
@@ -825,6 +848,7 @@ int launch_umma_phoneme(const es_config_t& cfg, const es_weights_t& w, int B, in
     p.sc_xm1 = sc_xm1; p.sc_u = sc_u;
     p.scale_log2e = 1.4426950408889634f / sqrtf(32.f);
     p.err = err_flag;
+    p.trace = g_ph_trace;
     const int grid = B < n_sm ? B : n_sm;
     ES_CUDA(launch_pdl(umma_phoneme_kernel, grid, NTHR, PH_SMEM, s, p));
     ES_LAUNCH_OK();

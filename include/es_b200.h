@@ -251,6 +251,9 @@ int es_check_async_errors(void* stream);
 /* Debug aid: when non-NULL, CTA 0 of every subsequent tcgen05 decoder launch writes clock64() stamps
  * [4 roles][32 tiles][8 events] (int64, device memory) -- tools/trace_decoder.py.  NULL turns it off. */
 int es_debug_set_trace(void* dev_buf_i64);
+/* Same for the fused phoneme kernel: [2 utterances][128] (clock64, event code) int64 pairs of CTA 0 -- one pair per
+ * GEMM completion, weight wait, phase sync and row reduction (tools/trace_phoneme.py).  NULL turns it off. */
+int es_debug_set_phoneme_trace(void* dev_buf_i64);
 /* Number of kernels the library has launched since process start (bench.py's gpu_launches). */
 uint64_t es_launch_count(void);
 
