@@ -146,39 +146,70 @@ __device__ __forceinline__ void tm_load(uint32_t taddr, float* v) {
     for (int j = 0; j < NV; ++j) v[j] = __uint_as_float(rr[j]);
 }
 
-// D[tmem_d] = A . B^T, issued by warp 0 (`elected` = its issuing lane).  A: row-panel tile (K panel stride a_lbo,
+// D[tmem_d] = A . B^T, called by all lanes of warp 0 with warp-uniform arguments.  A: row-panel tile (K panel stride a_lbo,
 // lo plane at +a_plane); conv tap t reads it shifted by t rows (16 bytes).  B: [N rows][K] in the same layout
 // (panel stride b_lbo, lo plane at +b_plane, tap t at +t*b_tap).  The four descriptors advance by a constant per
-// K step (start-address field, 16-byte units), so a K step costs 4 adds + 3 tcgen05.mma.
-__device__ __noinline__ void issue_gemm(bool elected, uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_plane,
-                                        uint32_t b_addr, uint32_t b_lbo, uint32_t b_plane, uint32_t b_tap,
-                                        int ksteps, int N, int taps) {
+// K step (start-address field, 16-byte units), so a K step costs 4 adds + 3 tcgen05.mma.  Inlined, with an
+// elect.sync predicate around the MMAs only, so the descriptors live in UNIFORM registers: as an out-of-line
+// function taking a per-thread `elected` flag every MMA paid a chain of R2UR moves (~100 cycles per MMA in the
+// timeline).  The loops stay rolled to keep the code small (instruction fetch is a measured cost here).
+template <int KSTEPS, int TAPS>
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_plane,
+                                           uint32_t b_addr, uint32_t b_lbo, uint32_t b_plane, uint32_t b_tap, int N) {
+    const bool elected = elect_one();
     const uint32_t idesc = make_idesc_f16(PM, N);
-    const uint64_t da_step = (uint64_t)((2u * a_lbo) >> 4), db_step = (uint64_t)((2u * b_lbo) >> 4);
-    uint32_t acc = 0;
-#pragma unroll 1
-    for (int t = 0; t < taps; ++t) {
-        uint64_t dah = make_smem_desc(a_addr + (uint32_t)t * 16u, a_lbo, 128u);
-        uint64_t dal = make_smem_desc(a_addr + a_plane + (uint32_t)t * 16u, a_lbo, 128u);
-        uint64_t dbh = make_smem_desc(b_addr + (uint32_t)t * b_tap, b_lbo, 128u);
-        uint64_t dbl = make_smem_desc(b_addr + b_plane + (uint32_t)t * b_tap, b_lbo, 128u);
-#pragma unroll 1
-        for (int ks = 0; ks < ksteps; ++ks) {
+    const uint64_t dah0 = make_smem_desc(a_addr, a_lbo, 128u), dal0 = make_smem_desc(a_addr + a_plane, a_lbo, 128u);
+    const uint64_t dbh0 = make_smem_desc(b_addr, b_lbo, 128u), dbl0 = make_smem_desc(b_addr + b_plane, b_lbo, 128u);
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            // offsets in the 16-byte units of the descriptors' start-address field
+            const uint64_t da = (uint64_t)(((uint32_t)t * 16u + (uint32_t)(2 * ks) * a_lbo) >> 4);
+            const uint64_t db = (uint64_t)(((uint32_t)t * b_tap + (uint32_t)(2 * ks) * b_lbo) >> 4);
             if (elected) {
-                mma_f16_ss(tmem_d, dah, dbh, idesc, acc);
-                mma_f16_ss(tmem_d, dah, dbl, idesc, 1u);
-                mma_f16_ss(tmem_d, dal, dbh, idesc, 1u);
+                mma_f16_ss(tmem_d, dah0 + da, dbh0 + db, idesc, (t | ks) ? 1u : 0u);
+                mma_f16_ss(tmem_d, dah0 + da, dbl0 + db, idesc, 1u);
+                mma_f16_ss(tmem_d, dal0 + da, dbh0 + db, idesc, 1u);
+            }
+        }
+    }
+}
+
+// Three independent layers of identical geometry (the three predictors): problem i uses A tile a_addr + i*a_step,
+// weights w_addr + i*w_step, accumulator columns tmem_d + i*N.  Their MMAs are interleaved so that consecutive
+// tcgen05.mma's never target the same accumulator: back-to-back MMAs into ONE accumulator serialise on the
+// accumulate dependency (~117 cycles each at M = 128 whatever N is; tools/trace_phoneme.py), independent ones pipeline.
+__device__ __forceinline__ void issue_layer_x3(uint32_t tmem_d, uint32_t a_addr, uint32_t a_step, uint32_t a_lbo,
+                                               uint32_t a_plane, uint32_t w_addr, uint32_t w_step, int K, int N, int taps) {
+    const bool elected = elect_one();
+    const uint32_t idesc = make_idesc_f16(PM, N);
+    const uint32_t b_lbo = (uint32_t)N * 16u, w_plane = (uint32_t)N * (uint32_t)K * 2u;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t ao = (uint32_t)t * 16u + (uint32_t)(2 * ks) * a_lbo;
+            const uint32_t bo = (uint32_t)(2 * t) * w_plane + (uint32_t)(2 * ks) * b_lbo;
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {               // hi*hi, hi*lo, lo*hi
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const uint64_t da = make_smem_desc(a_addr + (uint32_t)i * a_step + (term == 2 ? a_plane : 0u) + ao, a_lbo, 128u);
+                    const uint64_t db = make_smem_desc(w_addr + (uint32_t)i * w_step + (term == 1 ? w_plane : 0u) + bo, b_lbo, 128u);
+                    if (elected) mma_f16_ss(tmem_d + (uint32_t)(i * N), da, db, idesc, term == 0 ? acc : 1u);
+                }
             }
             acc = 1;
-            dah += da_step; dal += da_step; dbh += db_step; dbl += db_step;
         }
     }
 }
 // dense layer with packed weights [taps][hi, lo][K/8][N][8]
-__device__ __forceinline__ void issue_layer(bool elected, uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_plane,
-                                            uint32_t w_addr, int K, int N, int taps) {
+template <int K, int TAPS>
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_plane, uint32_t w_addr, int N) {
     const uint32_t w_plane = (uint32_t)N * (uint32_t)K * 2u;
-    issue_gemm(elected, tmem_d, a_addr, a_lbo, a_plane, w_addr, (uint32_t)N * 16u, w_plane, 2u * w_plane, K >> 4, N, taps);
+    issue_gemm<K / 16, TAPS>(tmem_d, a_addr, a_lbo, a_plane, w_addr, (uint32_t)N * 16u, w_plane, 2u * w_plane, N);
 }
 
 // NV (multiple of 4) consecutive per-channel parameters (bias, LayerNorm gain, ...) with 128-bit loads; the
@@ -201,6 +232,8 @@ __device__ __forceinline__ int bucket_left(const float* bins, int nb, float v) {
     return lo;
 }
 
+// TRACE: compiled-in clock64 stamps (tools/trace_phoneme.py); the production instantiation carries none
+template <bool TRACE>
 __global__ void __launch_bounds__(NTHR, 1)
 umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -288,7 +321,6 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
     pdl_launch_dependents();
     pdl_wait();
 
-    const bool elected = (warp == 0) && elect_one();
     bool failed = false;
     uint32_t mph = 0;                                           // bar_mma phase parity
     int wg = 0;                                                 // next weight phase to be consumed (global index)
@@ -296,7 +328,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
     // debug timeline (tools/trace_phoneme.py): thread 0 of CTA 0 stamps every GEMM completion (odd codes) and phase sync
     int tr_k = 0, tr_u = 0;
     auto stamp = [&](int code) {
-        if (p.trace && blockIdx.x == 0 && tid == 0 && tr_u < 2 && tr_k < 128) {
+        if (TRACE && p.trace && blockIdx.x == 0 && tid == 0 && tr_u < 2 && tr_k < 128) {
             p.trace[tr_u * 256 + 2 * tr_k] = clock64();
             p.trace[tr_u * 256 + 2 * tr_k + 1] = code;
             ++tr_k;
@@ -313,7 +345,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
     // commit the issued MMAs, wait for them, then refill the weight buffer they used (two phases ahead)
     auto gemm_done = [&](bool used_weights) {
         if (warp == 0) {
-            if (elected) mma_commit(bar_mma);
+            if (elect_one()) mma_commit(bar_mma);
             __syncwarp();
         }
         if (!spin_wait(bar_mma, mph)) failed = true;
@@ -326,13 +358,14 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         stamp(used_weights ? 1 : 3);
     };
     // combine two per-thread partials over the four threads of a row (same order in all four -> identical results).
-    // One barrier per call: the buffer halves alternate, and a half is rewritten only after the barrier of the
-    // following call, which every reader of this call has passed.
+    // One barrier per call, among the four warps of this lane quarter only (rows of other quarters are independent):
+    // the buffer halves alternate, and a half is rewritten only after the barrier of the following call, which
+    // every reader of this call has passed.
     auto row_sum2 = [&](float a, float b2) -> float2 {
         float2* bf = red + flip * (4 * PM);
         flip ^= 1;
         bf[cq * PM + r] = make_float2(a, b2);
-        __syncthreads();
+        named_bar_sync(1 + rq, PM);                          // only the four warps that share these 32 rows
         stamp(6);
         const float2 t0 = bf[r], t1 = bf[PM + r], t2 = bf[2 * PM + r], t3 = bf[3 * PM + r];
         return make_float2((t0.x + t1.x) + (t2.x + t3.x), (t0.y + t1.y) + (t2.y + t3.y));
@@ -341,7 +374,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         float2* bf = red + flip * (4 * PM);
         flip ^= 1;
         bf[cq * PM + r].x = a;
-        __syncthreads();
+        named_bar_sync(1 + rq, PM);
         return fmaxf(fmaxf(bf[r].x, bf[PM + r].x), fmaxf(bf[2 * PM + r].x, bf[3 * PM + r].x));
     };
     // LayerNorm over n_tot = 4 * NV columns of the row; this thread holds NV of them, g / be point at its first column
@@ -393,7 +426,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         }
         PHASE_SYNC(); stamp(2);
         // 2. S = Q K^T  -> columns [0, NK)
-        if (warp == 0) issue_gemm(elected, tmem, op_addr, PANEL, qk_plane, op_addr + 2 * qk_plane, PANEL, qk_plane, 0u, C >> 4, NK, 1);
+        if (warp == 0) issue_gemm<C / 16, 1>(tmem, op_addr, PANEL, qk_plane, op_addr + 2 * qk_plane, PANEL, qk_plane, 0u, NK);
         gemm_done(false);
         // 3. softmax over the n keys (unmasked: blocks.py:59-63), P -> split fp16 over the dead Q/K tiles
         {
@@ -420,7 +453,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         }
         PHASE_SYNC(); stamp(2);
         // 4. O = P V  -> columns [oc, oc + C)
-        if (warp == 0) issue_gemm(elected, tmem + (uint32_t)oc, op_addr, PANEL, p_plane, vt_addr, vt_lbo, vt_plane, 0u, NK >> 4, C, 1);
+        if (warp == 0) issue_gemm<NK / 16, 1>(tmem + (uint32_t)oc, op_addr, PANEL, p_plane, vt_addr, vt_lbo, vt_plane, 0u, C);
         gemm_done(false);
     };
 
@@ -478,7 +511,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         PHASE_SYNC(); stamp(2);
         {   // qkv0: [32] -> [96] into columns [128, 224)
             const uint32_t w = w_wait();
-            if (warp == 0) issue_layer(elected, tmem + 128, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, 96, 1);
+            if (warp == 0) issue_layer<D0, 1>(tmem + 128, xa_addr + 16, XA_LBO, XA_PLANE, w, 96);
             gemm_done(true);
         }
         attention(std::integral_constant<int, D0>{}, std::integral_constant<int, PM>{}, N, 128, 160, 192, 128);
@@ -489,7 +522,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, o, act0);
             PHASE_SYNC(); stamp(2);
             const uint32_t w = w_wait();
-            if (warp == 0) issue_layer(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
+            if (warp == 0) issue_layer<D0, 1>(tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0);
             gemm_done(true);
             tm_load<8>(trow + (uint32_t)c8, x1);
             float pb[8];
@@ -507,7 +540,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         float f0[8];
         {   // MixFFN: conv3 (mlp1 folded) + GELU, mlp2 + residual + LN2 + mask
             uint32_t w = w_wait();
-            if (warp == 0) issue_layer(elected, tmem, xa_addr, XA_LBO, XA_PLANE, w, D0, D0, 3);
+            if (warp == 0) issue_layer<D0, 3>(tmem, xa_addr, XA_LBO, XA_PLANE, w, D0);
             gemm_done(true);
             float h[8];
             tm_load<8>(trow + (uint32_t)c8, h);
@@ -528,7 +561,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             stage_cols<8>(xa, XA_LBO, XA_PLANE, r + 1, cq, h, act0);
             PHASE_SYNC(); stamp(2);
             w = w_wait();
-            if (warp == 0) issue_layer(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
+            if (warp == 0) issue_layer<D0, 1>(tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0);
             gemm_done(true);
             tm_load<8>(trow + (uint32_t)c8, f0);
             float f2b[8];
@@ -546,7 +579,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         // ================================================================= block 1 (16 columns per thread)
         {   // merge conv (1 tap, stride 2): xm1[j] = W feat0[2j]; computed for every row, even rows are kept
             const uint32_t w = w_wait();
-            if (warp == 0) issue_layer(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D1, 1);
+            if (warp == 0) issue_layer<D0, 1>(tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D1);
             gemm_done(true);
             float y[16];
             tm_load<16>(trow + (uint32_t)c16, y);
@@ -562,7 +595,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         }
         for (int s = 0; s < 3; ++s) {   // q | k | v of both heads: [64] -> [128] into columns 128 + 128 s
             const uint32_t w = w_wait();
-            if (warp == 0) issue_layer(elected, tmem + 128 + 128 * s, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, 128, 1);
+            if (warp == 0) issue_layer<D1, 1>(tmem + 128 + 128 * s, xa_addr + 16, XA_LBO, XA_PLANE, w, 128);
             gemm_done(true);
         }
         for (int hd = 0; hd < 2; ++hd)
@@ -575,7 +608,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             stage_cols<32>(op, PANEL, 16 * PANEL, r, 4 * cq, o, act1);
             PHASE_SYNC(); stamp(2);
             const uint32_t w = w_wait();
-            if (warp == 0) issue_layer(elected, tmem, op_addr, PANEL, 16 * PANEL, w, 128, D1, 1);
+            if (warp == 0) issue_layer<128, 1>(tmem, op_addr, PANEL, 16 * PANEL, w, D1);
             gemm_done(true);
             tm_load<16>(trow + (uint32_t)c16, x1b);
             if (act1) {
@@ -600,7 +633,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         }
         {   // MixFFN of block 1
             uint32_t w = w_wait();
-            if (warp == 0) issue_layer(elected, tmem, xa_addr, XA_LBO, XA_PLANE, w, D1, D1, 3);
+            if (warp == 0) issue_layer<D1, 3>(tmem, xa_addr, XA_LBO, XA_PLANE, w, D1);
             gemm_done(true);
             float h[16];
             tm_load<16>(trow + (uint32_t)c16, h);
@@ -621,7 +654,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             stage_cols<16>(xa, XA_LBO, XA_PLANE, r + 1, 2 * cq, h, act1);
             PHASE_SYNC(); stamp(2);
             w = w_wait();
-            if (warp == 0) issue_layer(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, D1, 1);
+            if (warp == 0) issue_layer<D1, 1>(tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D1);
             gemm_done(true);
             tm_load<16>(trow + (uint32_t)c16, h);
             float f2b[16];
@@ -640,7 +673,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         float fz[8];
         {
             uint32_t w = w_wait();                               // U = feat1 [G_0 | G_1 | G_2] + [g_0 | g_1 | g_2]
-            if (warp == 0) issue_layer(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D1, 96, 1);
+            if (warp == 0) issue_layer<D1, 1>(tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, 96);
             gemm_done(true);
 #pragma unroll 1
             for (int i = 0; i < 3; ++i) {   // 3 of the 12 8-column groups of U per thread
@@ -659,7 +692,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             // rows of the K = 64 tile beyond panel 3 are not read by the K = 32 GEMMs that follow
             PHASE_SYNC(); stamp(2);                                        // also publishes the U rows (shared memory) to the CTA
             w = w_wait();                                        // fused = mask(c + A0 feat0 + stride-2 scatter of U)
-            if (warp == 0) issue_layer(elected, tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0, D0, 1);
+            if (warp == 0) issue_layer<D0, 1>(tmem, xa_addr + 16, XA_LBO, XA_PLANE, w, D0);
             gemm_done(true);
             tm_load<8>(trow + (uint32_t)c8, fz);
             float fc[8];
@@ -692,8 +725,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
         float pred[3];
         {
             uint32_t w = w_wait();                               // conv1 of the three predictors -> columns 0 | 32 | 64
-            if (warp == 0)
-                for (int i = 0; i < 3; ++i) issue_layer(elected, tmem + 32 * i, xa_addr, XA_LBO, XA_PLANE, w + (uint32_t)i * 12288u, D0, D0, 3);
+            if (warp == 0) issue_layer_x3(tmem, xa_addr, 0u, XA_LBO, XA_PLANE, w, 12288u, D0, D0, 3);
             gemm_done(true);
             // next utterance's embedding row: in flight during the predictor and variance stages
             if (ui + 1 < my_utts) gather_x0(b + (int)gridDim.x, x0n);
@@ -718,9 +750,7 @@ umma_phoneme_kernel(const __grid_constant__ PhonemeParams p) {
             }
             PHASE_SYNC(); stamp(2);
             w = w_wait();                                        // conv2 + ReLU, scalar head on the pre-LN2 values
-            if (warp == 0)
-                for (int i = 0; i < 3; ++i)
-                    issue_layer(elected, tmem + 32 * i, op_addr + (uint32_t)i * Y1_TILE, XA_LBO, Y1_PLANE, w + (uint32_t)i * 12288u, D0, D0, 3);
+            if (warp == 0) issue_layer_x3(tmem, op_addr, Y1_TILE, XA_LBO, Y1_PLANE, w, 12288u, D0, D0, 3);
             gemm_done(true);
             float y2[3][8], dot[3];
 #pragma unroll
@@ -833,7 +863,8 @@ int launch_umma_phoneme(const es_config_t& cfg, const es_weights_t& w, int B, in
     }
     static bool attr_set = false;
     if (!attr_set) {
-        ES_CUDA(cudaFuncSetAttribute(umma_phoneme_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
+        ES_CUDA(cudaFuncSetAttribute(umma_phoneme_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
+        ES_CUDA(cudaFuncSetAttribute(umma_phoneme_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
         attr_set = true;
     }
     PhonemeParams p;
@@ -850,7 +881,7 @@ int launch_umma_phoneme(const es_config_t& cfg, const es_weights_t& w, int B, in
     p.err = err_flag;
     p.trace = g_ph_trace;
     const int grid = B < n_sm ? B : n_sm;
-    ES_CUDA(launch_pdl(umma_phoneme_kernel, grid, NTHR, PH_SMEM, s, p));
+    ES_CUDA(launch_pdl(p.trace ? umma_phoneme_kernel<true> : umma_phoneme_kernel<false>, grid, NTHR, PH_SMEM, s, p));
     ES_LAUNCH_OK();
     return 0;
 }
