@@ -390,7 +390,7 @@ int es_encoder_forward(es_model_t* m, void* stream, int B, int N,
         int rc;
         { ProfRange r(ES_K_PHONEME, s);
           rc = launch_umma_phoneme(m->cfg, m->w, B, N, n1, pool, phoneme, phoneme_mask, pitch_tgt, energy_tgt, dur_tgt,
-                                   pitch_pred, energy_pred, dur_pred, fused4, dur_int, dur_cum, mel_len, e.xm1, e.qkv, s); }
+                                   pitch_pred, energy_pred, dur_pred, fused4, dur_int, dur_cum, mel_len, e.xm1, s); }
         if (rc > 0) return 1;
         if (rc == 0) return 0;
     }

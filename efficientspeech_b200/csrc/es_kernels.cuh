@@ -64,7 +64,7 @@ void umma_phoneme_set_trace(long long* buf);   // debug: [2][128] (clock64, even
 int launch_umma_phoneme(const es_config_t& cfg, const es_weights_t& w, int B, int N, int n1, int pool,
                         const int32_t* ids, const uint8_t* mask, const float* pitch_tgt, const float* energy_tgt,
                         const int32_t* dur_tgt, float* pitch_pred, float* energy_pred, float* dur_pred, float* fused4,
-                        int32_t* dur_int, int32_t* dur_cum, int32_t* mel_len, float* sc_xm1, float* sc_u, cudaStream_t s);
+                        int32_t* dur_int, int32_t* dur_cum, int32_t* mel_len, float* sc_xm1, cudaStream_t s);
 // tcgen05 attention (es_umma_attn.cu); -1: outside its envelope (n > 128 or C not in {32, 64})
 int launch_umma_attention(const float* qkv, float* out, int B, int n, int C, int H, float scale, cudaStream_t s);
 

@@ -20,9 +20,9 @@
 // one zero halo row on each side (es_umma_enc.cu); attention is S = Q K^T, softmax out of TMEM, O = P V
 // (es_umma_attn.cu).  Weights are the packed split-fp16 images of the per-layer kernels, streamed through two
 // 48 KB shared-memory buffers by bulk copies issued two layers ahead.  Level-1 rows (n1 = ceil(N/2) <= 64)
-// live in rows 0..n1-1; the M = 128 GEMMs simply carry zero rows.  Two small per-utterance scratch arrays in
-// global memory (L2) hand rows between threads where the row -> thread map changes (stride-2 merge conv, the
-// stride-2 transposed-conv scatter of Fuse).
+// live in rows 0..n1-1; the M = 128 GEMMs simply carry zero rows.  Where the row -> thread map changes, rows are
+// handed over through a small per-utterance scratch array in global memory (L2; stride-2 merge conv -> residual of
+// block 1) or through shared memory (the U rows of Fuse's stride-2 transposed-conv scatter).
 //
 // Layer list per utterance (reference lines in es_api.cu next to the per-layer launches):
 //   embed+merge0 (3 table gathers) | qkv0, attention0, proj0+res+LN1+mask, conv3(ffn1)+GELU, ffn2+res+LN2+mask |
@@ -79,7 +79,6 @@ struct PhonemeParams {
     float* pitch_pred; float* energy_pred; float* dur_pred; float* fused4;
     int32_t* dur_int; int32_t* dur_cum; int32_t* mel_len;
     float* sc_xm1;                               // [B][n1][64]  block-1 input rows (residual of proj1)
-    float* sc_u;                                 // [B][n1][96]  Fuse: U rows of the half-rate positions
     float scale_log2e;                           // (C // H)^-0.5 * log2(e): 32^-0.5 at both levels
     int* err;
     long long* trace;                            // debug: clock64 stamps of CTA 0 / thread 0, [2 utterances][128 events], or null
@@ -847,11 +846,11 @@ bool umma_phoneme_supported(const es_config_t& cfg, const es_weights_t& w, int N
     return w.pitch.bins && w.pitch.table && w.energy.bins && w.energy.table;
 }
 
-// sc_xm1: B*n1*64 floats, sc_u: B*n1*96 floats of scratch.  -1: outside the kernel's envelope.
+// sc_xm1: B*n1*64 floats of scratch.  -1: outside the kernel's envelope.
 int launch_umma_phoneme(const es_config_t& cfg, const es_weights_t& w, int B, int N, int n1, int pool,
                         const int32_t* ids, const uint8_t* mask, const float* pitch_tgt, const float* energy_tgt,
                         const int32_t* dur_tgt, float* pitch_pred, float* energy_pred, float* dur_pred, float* fused4,
-                        int32_t* dur_int, int32_t* dur_cum, int32_t* mel_len, float* sc_xm1, float* sc_u, cudaStream_t s) {
+                        int32_t* dur_int, int32_t* dur_cum, int32_t* mel_len, float* sc_xm1, cudaStream_t s) {
     if (!umma_phoneme_supported(cfg, w, N) || n1 > 64 || n1 < 1) return -1;
     int* err_flag = umma_err_flag();
     ES_CHECK(err_flag, "cannot allocate the device error flag");
@@ -876,7 +875,7 @@ int launch_umma_phoneme(const es_config_t& cfg, const es_weights_t& w, int B, in
     p.pred[0] = w.pitch; p.pred[1] = w.energy; p.pred[2] = w.duration;
     p.pitch_pred = pitch_pred; p.energy_pred = energy_pred; p.dur_pred = dur_pred; p.fused4 = fused4;
     p.dur_int = dur_int; p.dur_cum = dur_cum; p.mel_len = mel_len;
-    p.sc_xm1 = sc_xm1; p.sc_u = sc_u;
+    p.sc_xm1 = sc_xm1;
     p.scale_log2e = 1.4426950408889634f / sqrtf(32.f);
     p.err = err_flag;
     p.trace = g_ph_trace;

@@ -107,3 +107,35 @@ def test_compute_entry_fails_cleanly_without_device():
     lib.es_model_destroy(h)
     bad = _cabi.es_config_t(128, 48, 3, 1, 1, 2, 2, 5, 80, 153)
     assert lib.es_model_create(ctypes.byref(bad), ctypes.byref(w), ctypes.byref(h)) != 0
+
+
+def test_path_switches_and_workspace_planning_on_the_host():
+    """Host logic of the C ABI that needs no device: the A/B switches validate their argument, and the workspace
+    plan is monotone and covers the gathered decoder entry (projection table + frame -> row map)."""
+    lib = _cabi.load()
+    cfg = _cabi.es_config_t(128, 32, 3, 1, 1, 2, 2, 5, 80, 153)
+    w = _cabi.es_weights_t()
+    h = ctypes.c_void_p(None)
+    assert lib.es_model_create(ctypes.byref(cfg), ctypes.byref(w), ctypes.byref(h)) == 0
+    try:
+        for mode in (_cabi.ES_GATHER_PER_FRAME, _cabi.ES_GATHER_MATERIALIZE, _cabi.ES_GATHER_FUSED):
+            assert lib.es_model_set_decoder_gather(h, mode) == 0
+        assert lib.es_model_set_decoder_gather(h, 7) != 0
+        assert b"gather mode" in lib.es_last_error()
+        assert lib.es_model_set_fused_phoneme(h, 0) == 0 and lib.es_model_set_fused_phoneme(h, 1) == 0
+        assert lib.es_model_set_tensor_core(h, 0) == 0 and lib.es_model_set_tensor_core(h, 1) == 0
+        B, N, T, dx2 = 8, 128, 768, 128
+        enc = lib.es_workspace_bytes(h, B, N, 0)
+        dec = lib.es_workspace_bytes(h, B, 0, T)
+        both = lib.es_workspace_bytes(h, B, N, T)
+        assert enc > 0 and dec >= 3 * B * T * dx2 * 4                  # three rotating [B,T,dx2] fp32 buffers
+        assert both >= enc + dec                                       # one plan after the other
+        assert both - enc - dec >= (B * N + 1) * dx2 * 4 + B * T * 4 - 1024   # + projection table + int32 row map
+        assert lib.es_workspace_bytes(h, 2 * B, N, T) > both
+        assert lib.es_workspace_bytes(None, B, N, T) == 0
+        # argument checks come before any device work
+        assert lib.es_frame_rows(h, None, B, N, T, None, None, None) != 0
+        assert b"es_frame_rows" in lib.es_last_error()
+        assert lib.es_decoder_forward_gathered(h, None, B, N, T, None, None, None, 1, None, None, 0) != 0
+    finally:
+        lib.es_model_destroy(h)
