@@ -9,7 +9,7 @@ from typing import Optional
 from . import build as _build
 
 ES_ABI_VERSION = 10
-ES_GATHER_PER_FRAME, ES_GATHER_MATERIALIZE, ES_GATHER_FUSED = 0, 1, 2
+ES_GATHER_MATERIALIZE, ES_GATHER_FUSED = 1, 2
 ES_MAX_ENC_BLOCKS = 2
 ES_MAX_DEC_LAYERS = 24
 ES_MAX_DEC_BLOCKS = 8

@@ -40,16 +40,42 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB_PATH) -> str:
-    """`defines` / `out`: experiment builds (e.g. -DES_MBAR_SUSPEND_NS=0 into a second .so selected with
-    $ES_B200_LIB); the default build takes neither."""
+    """One object per .cu (compiled in parallel, rebuilt only when the source or a header changed), then one link.
+    `defines` / `out`: experiment builds (e.g. -DES_MBAR_SUSPEND_NS=0 into a second .so selected with $ES_B200_LIB);
+    their objects live in their own directory.  The default build takes neither."""
     if not force and not defines and out == LIB_PATH and not needs_build():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + sources() + ["-o", out, "-lcudart"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    with open(os.path.join(PKG_DIR, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = find_nvcc()
+    tag = "default" if not defines else "exp_" + "_".join(d.replace("=", "-") for d in defines)
+    objdir = os.path.join(PKG_DIR, "build", tag)
+    os.makedirs(objdir, exist_ok=True)
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        [os.path.join(os.path.dirname(PKG_DIR), "include", "es_b200.h"), os.path.abspath(__file__)]
+    hdr_t = max(os.path.getmtime(h) for h in headers)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + [f"-D{d}" for d in defines]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.isfile(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj, 0, ""
+        cmd = [nvcc] + cflags + ["-c", src, "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, res.returncode, " ".join(cmd) + "\n" + res.stdout + res.stderr
+
+    with ThreadPoolExecutor(max(1, min(8, os.cpu_count() or 1))) as ex:
+        results = list(ex.map(compile_one, sources()))
+    log = "".join(r[2] for r in results)
+    ok = all(r[1] == 0 for r in results)
+    if ok:
+        cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC"] + [r[0] for r in results] + ["-o", out, "-lcudart"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + res.stdout + res.stderr
+        ok = res.returncode == 0
+    if not defines:
+        with open(os.path.join(PKG_DIR, "build.log"), "a" if not force else "w") as f:
+            f.write(log)
+    if not ok:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libes_b200.so")
     if verbose:

@@ -355,7 +355,7 @@ int es_model_set_fused_phoneme(es_model_t* m, int enable) {
 
 int es_model_set_decoder_gather(es_model_t* m, int mode) {
     ES_CHECK(m, "null model");
-    ES_CHECK(mode == ES_GATHER_PER_FRAME || mode == ES_GATHER_MATERIALIZE || mode == ES_GATHER_FUSED, "unknown gather mode");
+    ES_CHECK(mode == ES_GATHER_MATERIALIZE || mode == ES_GATHER_FUSED, "unknown gather mode");
     m->gather_mode = mode;
     return 0;
 }
@@ -485,14 +485,14 @@ int es_decoder_forward(es_model_t* m, void* stream, int B, int T, const float* f
     if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx4 == 128 &&
         umma_dec_supported(m->dx2, m->cfg.decoder_kernel_size, m->dx2)) {
         { ProfRange r(ES_K_DEC_PROJ, s);
-          if (launch_umma_dec(2, B, T, m->dx2, 0, features, nullptr, nullptr, nullptr, nullptr, m->w.dproj_w_h16,
+          if (launch_umma_dec(2, B, T, m->dx2, features, nullptr, nullptr, m->w.dproj_w_h16,
                               m->w.dproj_b, 1, m->w.dproj_ln_g, m->w.dproj_ln_b, nullptr, nullptr, nullptr,
                               nullptr, db.buf[0], s)) return 1; }
         return decoder_layers(m, B, T, db, 0, nullptr, mel, s);
     }
     if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx2 == 256 && umma_dec256_supported(m->dx4, 5, 256, 2)) {
         { ProfRange r(ES_K_DEC_PROJ, s);
-          if (launch_umma_dec256(2, B, T, m->dx4, m->dx2, 0, features, nullptr, nullptr, nullptr, nullptr, m->w.dproj_w_h16,
+          if (launch_umma_dec256(2, B, T, m->dx4, m->dx2, features, nullptr, nullptr, m->w.dproj_w_h16,
                                  m->w.dproj_b, 1, m->w.dproj_ln_g, m->w.dproj_ln_b, nullptr, nullptr, nullptr,
                                  nullptr, db.buf[0], s)) return 1; }
         return decoder_layers(m, B, T, db, 0, nullptr, mel, s);
@@ -509,45 +509,21 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
     ES_CHECK(m, "null model");
     ES_CHECK(B >= 1 && B <= 65535 && N >= 1 && T >= 1, "need 1 <= B <= 65535, N >= 1 and T >= 1 frames");
     ES_CHECK(fused4 && dur_cum && mel_len && mel, "null tensor");
-    const bool commute = m->gather_mode != ES_GATHER_PER_FRAME;
-    ES_CHECK(workspace && workspace_bytes >= decoder_workspace_bytes(m, B, commute ? N : 0, T), "workspace too small");
+    ES_CHECK(workspace && workspace_bytes >= decoder_workspace_bytes(m, B, N, T), "workspace too small");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Arena a(reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256)));
-    DecBufs db = plan_decoder(m, a, B, commute ? N : 0, T);
-    if (commute) {
-        // The projection is row-wise and the length regulator is a row gather: project once per PHONEME
-        // (B*N rows), expand through the frame -> row map (es_gather.cu).  networks.py:228-258, :292
-        const int R = B * N;
-        { ProfRange r(ES_K_DEC_PROJ, s); if (project_rows(m, R, fused4, db.P, s)) return 1; }
-        { ProfRange r(ES_K_LENREG, s);
-          if (launch_frame_source(dur_cum, mel_len, db.src, B, N, T, m->w.dproj_b, m->w.dproj_ln_g, m->w.dproj_ln_b,
-                                  m->dx2, db.P + (size_t)R * m->dx2, s)) return 1; }
-        if (m->gather_mode == ES_GATHER_FUSED && decoder_all_umma128(m))
-            // the first block reads its input and skip rows straight from the table: [B,T,dx2] is never materialised
-            return decoder_layers(m, B, T, db, -1, zero_padded_frames ? mel_len : nullptr, mel, s);
-        { ProfRange r(ES_K_LENREG, s); if (launch_gather_rows(db.P, db.src, db.buf[0], (long long)B * T, m->dx2, s)) return 1; }
-        return decoder_layers(m, B, T, db, 0, zero_padded_frames ? mel_len : nullptr, mel, s);
-    }
-    // legacy form: length-regulator gather fused into the projection's operand load, one GEMM row per FRAME
-    if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx4 == 128 &&
-        umma_dec_supported(m->dx2, m->cfg.decoder_kernel_size, m->dx2)) {
-        { ProfRange r(ES_K_DEC_PROJ, s);
-          if (launch_umma_dec(1, B, T, m->dx2, N, fused4, dur_cum, mel_len, nullptr, nullptr, m->w.dproj_w_h16,
-                              m->w.dproj_b, 1, m->w.dproj_ln_g, m->w.dproj_ln_b, nullptr, nullptr, nullptr,
-                              nullptr, db.buf[0], s)) return 1; }
-        return decoder_layers(m, B, T, db, 0, zero_padded_frames ? mel_len : nullptr, mel, s);
-    }
-    if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx2 == 256 && umma_dec256_supported(m->dx4, 5, 256, 1)) {
-        { ProfRange r(ES_K_DEC_PROJ, s);
-          if (launch_umma_dec256(1, B, T, m->dx4, m->dx2, N, fused4, dur_cum, mel_len, nullptr, nullptr, m->w.dproj_w_h16,
-                                 m->w.dproj_b, 1, m->w.dproj_ln_g, m->w.dproj_ln_b, nullptr, nullptr, nullptr,
-                                 nullptr, db.buf[0], s)) return 1; }
-        return decoder_layers(m, B, T, db, 0, zero_padded_frames ? mel_len : nullptr, mel, s);
-    }
-    RowGemmParams p = base_params(B, N, T, m->dx4, m->dx2, fused4, m->dx4, m->w.dproj_w, db.buf[0], m->dx2);
-    p.mode = ROW_GATHER; p.cum = dur_cum; p.valid_len = mel_len;
-    p.bias = m->w.dproj_b; p.act1 = ACT_TANH; p.ln_g = m->w.dproj_ln_g; p.ln_b = m->w.dproj_ln_b;
-    { ProfRange r(ES_K_DEC_PROJ, s); if (launch_rowgemm(p, s)) return 1; }
+    DecBufs db = plan_decoder(m, a, B, N, T);
+    // The projection is row-wise and the length regulator is a row gather: project once per PHONEME
+    // (B*N rows), expand through the frame -> row map (es_gather.cu).  networks.py:228-258, :292
+    const int R = B * N;
+    { ProfRange r(ES_K_DEC_PROJ, s); if (project_rows(m, R, fused4, db.P, s)) return 1; }
+    { ProfRange r(ES_K_LENREG, s);
+      if (launch_frame_source(dur_cum, mel_len, db.src, B, N, T, m->w.dproj_b, m->w.dproj_ln_g, m->w.dproj_ln_b,
+                              m->dx2, db.P + (size_t)R * m->dx2, s)) return 1; }
+    if (m->gather_mode == ES_GATHER_FUSED && decoder_all_umma128(m))
+        // the first block reads its input and skip rows straight from the table: [B,T,dx2] is never materialised
+        return decoder_layers(m, B, T, db, -1, zero_padded_frames ? mel_len : nullptr, mel, s);
+    { ProfRange r(ES_K_LENREG, s); if (launch_gather_rows(db.P, db.src, db.buf[0], (long long)B * T, m->dx2, s)) return 1; }
     return decoder_layers(m, B, T, db, 0, zero_padded_frames ? mel_len : nullptr, mel, s);
 }
 
@@ -566,11 +542,11 @@ bool decoder_all_umma128(const es_model* m) {
 int project_rows(const es_model* m, int rows, const float* in, float* out, cudaStream_t s) {
     if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx4 == 128 &&
         umma_dec_supported(m->dx2, m->cfg.decoder_kernel_size, m->dx2))
-        return launch_umma_dec(2, 1, rows, m->dx2, 0, in, nullptr, nullptr, nullptr, nullptr, m->w.dproj_w_h16,
+        return launch_umma_dec(2, 1, rows, m->dx2, in, nullptr, nullptr, m->w.dproj_w_h16,
                                m->w.dproj_b, 1, m->w.dproj_ln_g, m->w.dproj_ln_b, nullptr, nullptr, nullptr,
                                nullptr, out, s);
     if (m->use_tensor_core && m->w.dproj_w_h16 && m->dx2 == 256 && umma_dec256_supported(m->dx4, 5, 256, 2))
-        return launch_umma_dec256(2, 1, rows, m->dx4, m->dx2, 0, in, nullptr, nullptr, nullptr, nullptr, m->w.dproj_w_h16,
+        return launch_umma_dec256(2, 1, rows, m->dx4, m->dx2, in, nullptr, nullptr, m->w.dproj_w_h16,
                                   m->w.dproj_b, 1, m->w.dproj_ln_g, m->w.dproj_ln_b, nullptr, nullptr, nullptr,
                                   nullptr, out, s);
     RowGemmParams p = base_params(1, rows, rows, m->dx4, m->dx2, in, m->dx4, m->w.dproj_w, out, m->dx2);
@@ -605,7 +581,7 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
             }
             if (m->use_tensor_core && w.pw_w_h16 && umma_dec_supported(C, m->cfg.decoder_kernel_size, C)) {
                 ProfRange r(ES_K_DEC_LAYER, s);
-                if (launch_umma_dec(0, B, T, C, 0, db.buf[in_idx], nullptr, nullptr, w.dw_w, w.dw_b, w.pw_w_h16,
+                if (launch_umma_dec(0, B, T, C, db.buf[in_idx], w.dw_w, w.dw_b, w.pw_w_h16,
                                     w.pw_b, 1, w.ln_g, w.ln_b, last ? db.buf[s_idx] : nullptr,
                                     last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
                                     nullptr, db.buf[out_idx], s)) return 1;
@@ -614,7 +590,7 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
             }
             if (m->use_tensor_core && w.pw_w_h16 && C == 256 && umma_dec256_supported(C, m->cfg.decoder_kernel_size, C, 0)) {
                 ProfRange r(ES_K_DEC_LAYER, s);
-                if (launch_umma_dec256(0, B, T, C, C, 0, db.buf[in_idx], nullptr, nullptr, w.dw_w, w.dw_b, w.pw_w_h16,
+                if (launch_umma_dec256(0, B, T, C, C, db.buf[in_idx], w.dw_w, w.dw_b, w.pw_w_h16,
                                        w.pw_b, 1, w.ln_g, w.ln_b, last ? db.buf[s_idx] : nullptr,
                                        last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
                                        nullptr, db.buf[out_idx], s)) return 1;
@@ -636,14 +612,14 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
     if (m->use_tensor_core && m->w.mel_w_h16 && m->cfg.n_mel == 80 &&
         umma_dec_supported(C, m->cfg.decoder_kernel_size, m->cfg.n_mel)) {
         ProfRange r(ES_K_MEL, s);
-        return launch_umma_dec(2, B, T, m->cfg.n_mel, 0, db.buf[s_idx], nullptr, nullptr, nullptr, nullptr,
+        return launch_umma_dec(2, B, T, m->cfg.n_mel, db.buf[s_idx], nullptr, nullptr,
                                m->w.mel_w_h16, m->w.mel_b, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
                                zero_from, mel, s);
     }
     if (m->use_tensor_core && m->w.mel_w_h16 && C == 256 && m->cfg.n_mel == 80 &&
         umma_dec256_supported(C, m->cfg.decoder_kernel_size, 80, 2)) {
         ProfRange r(ES_K_MEL, s);
-        return launch_umma_dec256(2, B, T, C, m->cfg.n_mel, 0, db.buf[s_idx], nullptr, nullptr, nullptr, nullptr,
+        return launch_umma_dec256(2, B, T, C, m->cfg.n_mel, db.buf[s_idx], nullptr, nullptr,
                                   m->w.mel_w_h16, m->w.mel_b, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
                                   zero_from, mel, s);
     }

@@ -42,6 +42,20 @@ extern std::atomic<uint64_t> g_launches;
         ES_CUDA(cudaGetLastError());                                          \
     } while (0)
 
+// ---- per-device caches -------------------------------------------------------------------------------
+// cudaFuncSetAttribute, the SM count and device allocations belong to ONE device; a process may drive several
+// (the Python API accepts any device), so everything cached across calls is keyed by cudaGetDevice().
+constexpr int kMaxDevices = 64;
+template <typename T>
+struct PerDeviceSlot {
+    T v[kMaxDevices] = {};
+    T& get() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return v[d & (kMaxDevices - 1)];
+    }
+};
+
 // ---- launch with programmatic stream serialization (PDL); the kernel must call griddepcontrol.wait --
 template <typename Param>
 inline cudaError_t launch_pdl(void (*kernel)(Param), dim3 grid, int block, size_t smem, cudaStream_t s, const Param& p) {
@@ -95,7 +109,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---- generic fused row-GEMM (es_rowgemm.cu) ----------------------------------------------
-enum RowMode : int { ROW_PLAIN = 0, ROW_GATHER = 1, ROW_DWCONV = 2 };
+enum RowMode : int { ROW_PLAIN = 0, ROW_DWCONV = 2 };
 
 struct RowGemmParams {
     // geometry: output rows are (b, t), t in [0, n_out); input rows (b, t_in), t_in in [0, n_in)
@@ -105,9 +119,6 @@ struct RowGemmParams {
     int mode;
     const float* A;            // [B*n_in][lda]
     int lda;
-    // GATHER: A row of frame t is row upper_bound(cum[b,:], t) of utterance b, zero for t >= valid_len[b]
-    const int* cum;            // [B][n_in] inclusive prefix sums
-    const int* valid_len;      // [B]
     // DWCONV: A'[t][c] = dw_b[c] + sum_tau dw_w[tau][c] * A[t + tau - dw_k/2][c]
     const float* dw_w;
     const float* dw_b;

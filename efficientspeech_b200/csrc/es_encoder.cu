@@ -189,7 +189,7 @@ int launch_attention(const float* qkv, float* out, int B, int n, int C, int H, f
     ES_CHECK(C % 32 == 0 && C <= 256, "attention width must be a multiple of 32 and <= 256");
     const size_t smem = ((size_t)(ATT_Q + ATT_KT) * (C + 4) + (size_t)ATT_Q * (n + 1)) * sizeof(float);
     ES_CHECK(smem <= 200 * 1024, "phoneme sequence too long for the attention score tile");
-    static bool attr_set = false;
+    static PerDeviceSlot<bool> attr_once; bool& attr_set = attr_once.get();   // function attributes are per device
     if (!attr_set) {
         ES_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
@@ -327,7 +327,7 @@ int launch_fuse(const float* f0, const float* f1, const float* a0, const float* 
     const long long rows = (long long)B * N;
     const size_t smem = ((size_t)d * d + (size_t)k * 2 * d * d + (size_t)k * d + d) * sizeof(float);
     if ((d == 32 || d == 64) && smem <= 200 * 1024) {
-        static bool attr_set = false;
+        static PerDeviceSlot<bool> attr_once; bool& attr_set = attr_once.get();   // function attributes are per device
         if (!attr_set) {
             ES_CUDA(cudaFuncSetAttribute(fuse_narrow_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             ES_CUDA(cudaFuncSetAttribute(fuse_narrow_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

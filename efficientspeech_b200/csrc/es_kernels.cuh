@@ -28,8 +28,7 @@ int launch_gather_rows(const float* P, const int32_t* src, float* Y, long long r
 
 // tcgen05 decoder kernel (es_umma_dec.cu)
 bool umma_dec_supported(int C, int dw_k, int N);
-int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, const int* cum,
-                    const int* valid_len, const float* dw_w, const float* dw_b, const void* w_h16,
+int launch_umma_dec(int mode, int B, int T, int N, const float* X, const float* dw_w, const float* dw_b, const void* w_h16,
                     const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
                     const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
                     float* Y, cudaStream_t s);
@@ -43,8 +42,7 @@ int launch_umma_dec_gathered(int B, int T, int N, const float* X, const float* d
 int umma_dec_check_errors(cudaStream_t s);
 // wide decoders (dx2 = 256): K-streamed tcgen05 kernel (es_umma_dec256.cu)
 bool umma_dec256_supported(int K, int dw_k, int N, int mode);
-int launch_umma_dec256(int mode, int B, int T, int K, int N, int n_src, const float* X, const int* cum,
-                       const int* valid_len, const float* dw_w, const float* dw_b, const void* w_chunks,
+int launch_umma_dec256(int mode, int B, int T, int K, int N, const float* X, const float* dw_w, const float* dw_b, const void* w_chunks,
                        const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
                        const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
                        float* Y, cudaStream_t s);

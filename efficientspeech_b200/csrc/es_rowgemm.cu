@@ -10,7 +10,6 @@
 // reductions, so each layer touches HBM exactly once for its input and once for its output.
 //
 // Prologues:  PLAIN   dense conv taps over time (Conv1d k in {1,3,5}, stride 1|2, zero padding)
-//             GATHER  the length regulator: row t <- fused4[b, upper_bound(cum[b], t)]   (networks.py:228-258)
 //             DWCONV  depthwise conv k (groups=C) + bias computed in smem before the GEMM (networks.py:281-282)
 //
 // This is the reference-precision path for every dense contraction; the tcgen05 kernel in
@@ -36,7 +35,7 @@ rowgemm_kernel(const RowGemmParams p) {
     const int col_base = blockIdx.y * (32 * NJ);
     const int K = p.K;
     // PLAIN mode streams K in chunks of KC (one chunk for every layer but the widest projections);
-    // GATHER / DWCONV stage the whole K at once (their K is the decoder width, <= 512).
+    // DWCONV stages the whole K at once (their K is the decoder width, <= 512).
     const int KC = (p.mode == ROW_PLAIN && K > kMaxKChunk) ? kMaxKChunk : K;
     const int K4 = KC >> 2;
     const int lds = KC + 4;
@@ -45,32 +44,6 @@ rowgemm_kernel(const RowGemmParams p) {
     // ------------------------------------------------------------------ prologue
     if (p.mode == ROW_PLAIN) {
         // staged per K chunk inside the main loop
-    } else if (p.mode == ROW_GATHER) {
-        int* srcs = reinterpret_cast<int*>(smem + BM * lds);
-        if (tid < BM) {
-            const int t = t0 + tid;
-            int s = -1;
-            if (t < p.n_out && t < p.valid_len[b]) {
-                // upper_bound: first n with cum[b,n] > t   (FeatureUpsampler == repeat_interleave)
-                const int* c = p.cum + (size_t)b * p.n_in;
-                int lo = 0, hi = p.n_in;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (__ldg(c + mid) > t) hi = mid; else lo = mid + 1;
-                }
-                s = lo < p.n_in ? lo : -1;
-            }
-            srcs[tid] = s;
-        }
-        __syncthreads();
-        const float* Ab = p.A + (size_t)b * p.n_in * p.lda;
-        for (int idx = tid; idx < BM * K4; idx += NTHREADS) {
-            const int r = idx / K4, c4 = idx - r * K4;
-            const int s = srcs[r];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s >= 0) v = __ldg(reinterpret_cast<const float4*>(Ab + (size_t)s * p.lda) + c4);
-            *reinterpret_cast<float4*>(As + r * lds + c4 * 4) = v;
-        }
     } else {  // ROW_DWCONV
         float* Xs = smem + BM * lds;
         const int half = p.dw_k >> 1;
@@ -244,7 +217,7 @@ rowgemm_kernel(const RowGemmParams p) {
 
 template <int NJ>
 int launch_nj(const RowGemmParams& p, size_t smem, dim3 grid, cudaStream_t stream) {
-    static bool attr_set = false;   // per-instantiation; idempotent, so a benign race at worst
+    static PerDeviceSlot<bool> attr_once; bool& attr_set = attr_once.get();   // function attributes are per device
     if (!attr_set) {
         ES_CUDA(cudaFuncSetAttribute(rowgemm_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
@@ -277,9 +250,6 @@ int launch_rowgemm(const RowGemmParams& p, cudaStream_t stream) {
     if (p.mode == ROW_PLAIN) {
         ES_CHECK(p.taps >= 1 && p.taps <= ES_MAX_TAPS && (p.stride == 1 || p.stride == 2), "bad taps/stride");
         smem = (size_t)((BM - 1) * p.stride + p.taps) * lds * sizeof(float);
-    } else if (p.mode == ROW_GATHER) {
-        ES_CHECK(p.cum && p.valid_len, "gather needs cum and valid_len");
-        smem = (size_t)BM * lds * sizeof(float) + BM * sizeof(int);
     } else {
         ES_CHECK(p.dw_w && p.dw_b && p.dw_k >= 1 && p.dw_k <= ES_MAX_TAPS && (p.dw_k & 1), "bad depthwise kernel");
         ES_CHECK(p.n_in == p.n_out, "depthwise prologue keeps the length");
@@ -483,7 +453,7 @@ rowgemm_narrow_kernel(const RowGemmBatch batch) {
 
 template <int NT>
 int launch_narrow_nt(const RowGemmBatch& batch, size_t smem, dim3 grid, cudaStream_t stream) {
-    static bool attr_set = false;
+    static PerDeviceSlot<bool> attr_once; bool& attr_set = attr_once.get();   // function attributes are per device
     if (!attr_set) {
         ES_CUDA(cudaFuncSetAttribute(rowgemm_narrow_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;

@@ -250,13 +250,13 @@ int launch_umma_attention(const float* qkv, float* out, int B, int n, int C, int
     if (n > AT_M || n < 1 || (C != 32 && C != 64)) return -1;
     int* err_flag = umma_err_flag();
     ES_CHECK(err_flag, "cannot allocate the device error flag");
-    static int n_sm = 0;
+    static PerDeviceSlot<int> n_sm_once; int& n_sm = n_sm_once.get();
     if (!n_sm) {
         int dev = 0;
         ES_CUDA(cudaGetDevice(&dev));
         ES_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    static bool attr_set = false;
+    static PerDeviceSlot<bool> attr_once; bool& attr_set = attr_once.get();   // function attributes are per device
     if (!attr_set) {
         ES_CUDA(cudaFuncSetAttribute(umma_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         attr_set = true;

@@ -10,7 +10,6 @@
 //               complete_tx) into a 3-deep ring, so two tiles (70 KB) are always in flight per
 //               SM; depthwise conv k=5 + bias in registers (sliding window)
 //       PLAIN   same ring without halo / conv (mel head, stand-alone projection)
-//       GATHER  the length regulator: row t <- fused4[b, upper_bound(cum[b], t)] (L2-resident)
 //       The results are held in registers while the previous tile's GEMM still reads the A
 //       operand, then split into fp16 hi/lo and stored straight into the UMMA canonical K-major
 //       no-swizzle operand layout (bank-conflict free); the issue warp then launches 24 x
@@ -63,21 +62,17 @@ constexpr uint32_t OFF_W = OFF_A + 2 * A_PLANE;               // W hi [K/8][N][8
 constexpr uint32_t W_PLANE_MAX = 128 * CK * 2;                // 32768
 constexpr uint32_t OFF_PAR = OFF_W + 2 * W_PLANE_MAX;         // bias, ln g/b, ln2 g/b: 5 x 128 floats
 constexpr uint32_t OFF_DW = OFF_PAR + 5 * 128 * 4;            // depthwise taps + bias: 6 x 128 floats
-constexpr uint32_t OFF_SRC = OFF_DW + 6 * 128 * 4;            // gather sources: 64 ints
 constexpr int MAP_LD = 72;                                    // row-map stride per ring slot (68 tile rows)
-constexpr uint32_t OFF_MAP = OFF_SRC + TM * 4;                // gathered x tiles: tile row -> staged row, per ring slot
+constexpr uint32_t OFF_MAP = OFF_DW + 6 * 128 * 4;            // gathered x tiles: tile row -> staged row, per ring slot
 constexpr uint32_t OFF_BAR = OFF_MAP + NSTAGE * MAP_LD * 4;   // 12 mbarriers + tmem base
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
-enum { MODE_DWCONV = 0, MODE_GATHER = 1, MODE_PLAIN = 2 };
+enum { MODE_DWCONV = 0, MODE_PLAIN = 2 };
 
 struct UmmaDecParams {
     int B, T, N;                 // N = output channels (128, or 80 for the mel head)
-    int n_src;                   // GATHER: source rows per utterance
-    const float* X;              // DWCONV/PLAIN: [B,T,128]; GATHER: fused4 [B,n_src,128]
-    const int* cum;              // GATHER
-    const int* valid_len;        // GATHER
+    const float* X;              // [B,T,128] (GX: the projection table)
     const float* dw_w;           // [5][128]
     const float* dw_b;           // [128]
     const void* w_h16;           // canonical split-fp16 weights: [2][16][N][8] halves
@@ -155,9 +150,14 @@ __device__ __forceinline__ void epilogue_math(uint32_t (&r)[64], const float* pa
             const f32x2 bb = *reinterpret_cast<const f32x2*>(par + 8 * j + 2 * t4);
 #pragma unroll
             for (int row = 0; row < 2; ++row) {
+#ifdef ES_EXP_NOTANH      // timing experiment (tools/gpu_exp.sh): never defined in the product build
+                v[2 * j + row] = fma2(pk2u(r[4 * j + 2 * row], r[4 * j + 2 * row + 1]), cs, bb);
+                (void)one2; (void)mtwo2;
+#else
                 const float2 a = up2(fma2(pk2u(r[4 * j + 2 * row], r[4 * j + 2 * row + 1]), cs, bb));
                 const float2 d = up2(add2(pk2(ex2_approx(a.x), ex2_approx(a.y)), one2));
                 v[2 * j + row] = fma2(mtwo2, pk2(rcp_approx(d.x), rcp_approx(d.y)), one2);
+#endif
             }
         }
     } else {
@@ -205,6 +205,15 @@ __device__ __forceinline__ void epilogue_math(uint32_t (&r)[64], const float* pa
     // store covers 8 rows x 64 B: half the wavefronts per byte.
     float* y0 = yrow0 + qcol;
     float* y1 = y0 + 8 * N;
+#ifdef ES_EXP_NOSTORE     // timing experiment: keep the math alive, store (practically) nothing
+    {
+        f32x2 acc = 0ull;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc ^= v[j];
+        if (acc == 0x7fc123457fc12345ull && ok0) *reinterpret_cast<f32x2*>(y0) = acc;
+        return;
+    }
+#endif
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if (2 * k < nj) {                                // nj is even (N % 16 == 0)
@@ -243,7 +252,6 @@ umma_dec_kernel(const UmmaDecParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t* a_hi = smem + OFF_A;
     float* par = reinterpret_cast<float*>(smem + OFF_PAR);
-    int* srcs = reinterpret_cast<int*>(smem + OFF_SRC);
     int* xmap = reinterpret_cast<int*>(smem + OFF_MAP);
     const uint32_t bar_x = smem_u32(smem + OFF_BAR);          // [3] x tile landed
     const uint32_t bar_w = bar_x + 24;                        //     weights landed
@@ -369,13 +377,11 @@ umma_dec_kernel(const UmmaDecParams p) {
                     if (sx[k] >= 0) bulk_g2s(dst + (uint32_t)(head + lane + 32 * k) * CK * 4u, p.X + (size_t)sx[k] * CK, CK * 4u, bar_x + 8 * slot);
             }
         };
-        if (MODE != MODE_GATHER) {
-            for (int k = 0; k < NSTAGE; ++k) {
-                const int tile = blockIdx.x + k * gridDim.x;
-                if (tile < n_tiles) {
-                    if (gx) { load_src(tile); issue_rows(tile, k); }
-                    else if (elected) issue_x(tile, k);
-                }
+        for (int k = 0; k < NSTAGE; ++k) {
+            const int tile = blockIdx.x + k * gridDim.x;
+            if (tile < n_tiles) {
+                if (gx) { load_src(tile); issue_rows(tile, k); }
+                else if (elected) issue_x(tile, k);
             }
         }
         if (!mbar_wait(bar_w, 0)) failed = true;
@@ -406,7 +412,7 @@ umma_dec_kernel(const UmmaDecParams p) {
             if (elected) { mma_commit(bar_mma + 8 * g); ES_TRACE(0, i, 3); }
             // ring slot of tile i was released by the producers before they signalled bar_aready:
             // the tile three steps ahead starts streaming into it
-            if (MODE != MODE_GATHER && next < n_tiles) {
+            if (next < n_tiles) {
                 if (!mbar_wait(bar_xfree + 8 * slot, (i / NSTAGE) & 1)) failed = true;
                 if (gx) issue_rows(next, slot);
                 else if (elected) issue_x(next, slot);
@@ -430,7 +436,7 @@ umma_dec_kernel(const UmmaDecParams p) {
             if (GX) {
                 if (!mbar_wait(bar_x + 8 * slot, (i / NSTAGE) & 1)) failed = true;   // staged rows + row map
                 if (tr_on) ES_TRACE(1, i, 1);
-            } else if (MODE != MODE_GATHER) {
+            } else {
                 // zero the halo / tail rows the bulk copy does not cover (utterance boundaries only)
                 const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
                 const int head = lo - (t0 - HALO), tail0 = hi - (t0 - HALO);
@@ -446,49 +452,12 @@ umma_dec_kernel(const UmmaDecParams p) {
                 if (!mbar_wait(bar_x + 8 * slot, (i / NSTAGE) & 1)) failed = true;
                 if (edge) named_bar_sync(1, NPROD);          // zero fill visible to every producer warp
                 if (tr_on) ES_TRACE(1, i, 1);
-            } else {
-                // length regulator: stage this utterance's duration prefix sums in shared memory (the x
-                // ring is unused in this mode), then every frame of the tile finds its source phoneme
-                // by an upper_bound in shared memory instead of ~8 dependent L2 round trips
-                int* scum = reinterpret_cast<int*>(smem + OFF_XS);
-                const bool cum_in_smem = p.n_src <= 8192;
-                if (cum_in_smem) {
-                    for (int k = ptid; k < p.n_src; k += NPROD) scum[k] = __ldg(p.cum + (size_t)b * p.n_src + k);
-                    named_bar_sync(1, NPROD);
-                }
-                if (ptid < TM) {
-                    const int t = t0 + ptid;
-                    int sidx = -1;
-                    if (t < p.T && t < p.valid_len[b]) {
-                        const int* c = p.cum + (size_t)b * p.n_src;
-                        int lo = 0, hi = p.n_src;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            const int cv = cum_in_smem ? scum[mid] : __ldg(c + mid);
-                            if (cv > t) hi = mid; else lo = mid + 1;
-                        }
-                        sidx = lo < p.n_src ? lo : -1;
-                    }
-                    srcs[ptid] = sidx;
-                }
-                named_bar_sync(1, NPROD);
             }
             // warp pw -> tile rows 16pw..16pw+15 (two 8-row core-matrix groups).  Both groups are computed
             // into registers BEFORE waiting for the A operand to be released, so that after the previous
             // GEMM completes only the 32 shared-memory stores remain on the critical path.
             uint2 ahi[16], alo[16];                          // this lane's share: 16 rows x 4 channels, split fp16
-            if (MODE == MODE_GATHER) {
-                // all 16 source rows of this warp are requested at once (one L2 round trip, not two)
-                ulonglong2 rowv[16];
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const int sidx = srcs[pw * 16 + r];
-                    rowv[r] = sidx >= 0 ? __ldg(reinterpret_cast<const ulonglong2*>(p.X + ((size_t)b * p.n_src + sidx) * CK) + lane)
-                                        : make_ulonglong2(0ull, 0ull);
-                }
-#pragma unroll
-                for (int r = 0; r < 16; ++r) split4(rowv[r], ahi[r], alo[r]);
-            } else {
+            {
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
                     const int r0 = pw * 16 + pass * 8;
@@ -516,7 +485,11 @@ umma_dec_kernel(const UmmaDecParams p) {
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
                         ulonglong2 o;
+#ifdef ES_EXP_NODW         // timing experiment: no depthwise FMAs
+                        if (false) {
+#else
                         if (MODE == MODE_DWCONV) {
+#endif
                             o = bdw;
 #pragma unroll
                             for (int t = 0; t < DWK; ++t) {
@@ -524,9 +497,14 @@ umma_dec_kernel(const UmmaDecParams p) {
                                 o.y = fma2(wdw[t].y, win[r + t].y, o.y);
                             }
                         } else {
-                            o = win[r];
+                            o = win[r + HALO];
                         }
+#ifdef ES_EXP_NOSPLIT      // timing experiment: no fp16 split (raw bits stored)
+                        ahi[pass * 8 + r] = make_uint2((uint32_t)o.x, (uint32_t)o.y);
+                        alo[pass * 8 + r] = make_uint2((uint32_t)(o.x >> 32), (uint32_t)(o.y >> 32));
+#else
                         split4(o, ahi[pass * 8 + r], alo[pass * 8 + r]);
+#endif
                     }
                 }
             }
@@ -549,7 +527,6 @@ umma_dec_kernel(const UmmaDecParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_aready);
             if (tr_on) ES_TRACE(1, i, 5);
-            if (MODE == MODE_GATHER) named_bar_sync(1, NPROD);   // srcs reusable
         }
     } else {
         // =========================================================================== epilogue
@@ -600,6 +577,15 @@ umma_dec_kernel(const UmmaDecParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tfree + 8 * g);     // accumulator drained: the GEMM of tile i+2 may start
             if (tr_on) ES_TRACE(2 + g, u, 2);
+#ifdef ES_EXP_NOEPI       // timing experiment: the epilogue only drains the accumulator
+            {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) acc ^= r[j];
+                if (acc == 0x7fc12345u && ok0) p.Y[g0 * N] = __uint_as_float(acc);
+                continue;
+            }
+#endif
             epilogue_math<RES2>(r, par, N, nj, inv_n, p.act_tanh != 0, p.ln_g != nullptr,
                                 res0, res1, p.Y + g0 * N, ok0, ok1,
                                 p.zero_from ? p.zero_from[b] - (t0 + row0) : 0x7fffffff, t4,
@@ -614,13 +600,13 @@ umma_dec_kernel(const UmmaDecParams p) {
     if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-int* g_err_flag = nullptr;
+PerDeviceSlot<int*> g_err_flags;       // one flag per device (the kernels of device d write device d's flag)
 long long* g_trace = nullptr;
 int g_trace_pick = 0, g_trace_count = 0;   // which launch after es_debug_set_trace is stamped (env ES_TRACE_LAUNCH)
 
 template <int MODE, bool RES2, bool GX = false, bool GS = false>
 int launch_mode(const UmmaDecParams& p, int grid, cudaStream_t s) {
-    static bool attr_set = false;
+    static PerDeviceSlot<bool> attr_once; bool& attr_set = attr_once.get();   // function attributes are per device
     if (!attr_set) {
         ES_CUDA(cudaFuncSetAttribute(umma_dec_kernel<MODE, RES2, GX, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
@@ -636,27 +622,24 @@ bool umma_dec_supported(int C, int dw_k, int N) {
     return C == CK && dw_k == DWK && (N == 128 || N == 80);
 }
 
-// mode: 0 depthwise layer, 1 gather + projection, 2 plain (mel head)
-int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, const int* cum,
-                    const int* valid_len, const float* dw_w, const float* dw_b, const void* w_h16,
+// mode: 0 depthwise layer, 2 plain (mel head, per-phoneme projection)
+int launch_umma_dec(int mode, int B, int T, int N, const float* X, const float* dw_w, const float* dw_b, const void* w_h16,
                     const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
                     const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
                     float* Y, cudaStream_t s) {
     ES_CHECK(w_h16 && X && Y && bias, "null tensor");
     ES_CHECK(N % 16 == 0 && N >= 32 && N <= 128, "N must be a multiple of 16 in [32,128]");
     ES_CHECK(!(ln_g || res2) || N == 128, "LayerNorm epilogue needs N == 128");
-    if (!g_err_flag) {
-        ES_CUDA(cudaMalloc(&g_err_flag, sizeof(int)));
-        ES_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
-    }
-    static int n_sm = 0;
+    int* const g_err_flag = umma_err_flag();
+    ES_CHECK(g_err_flag, "cannot allocate the device error flag");
+    static PerDeviceSlot<int> n_sm_once; int& n_sm = n_sm_once.get();
     if (!n_sm) {
         int dev = 0;
         ES_CUDA(cudaGetDevice(&dev));
         ES_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
     UmmaDecParams p;
-    p.B = B; p.T = T; p.N = N; p.n_src = n_src; p.X = X; p.cum = cum; p.valid_len = valid_len;
+    p.B = B; p.T = T; p.N = N; p.X = X;
     p.dw_w = dw_w; p.dw_b = dw_b; p.w_h16 = w_h16; p.bias = bias; p.act_tanh = act_tanh;
     p.ln_g = ln_g; p.ln_b = ln_b; p.res2 = res2; p.ln2_g = ln2_g; p.ln2_b = ln2_b;
     p.zero_from = zero_from; p.src = nullptr; p.pad_id = 0;
@@ -665,8 +648,8 @@ int launch_umma_dec(int mode, int B, int T, int N, int n_src, const float* X, co
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
     switch (mode) {
         case MODE_DWCONV: return res2 ? launch_mode<MODE_DWCONV, true>(p, grid, s) : launch_mode<MODE_DWCONV, false>(p, grid, s);
-        case MODE_GATHER: ES_CHECK(!res2, "gather mode has no skip input"); return launch_mode<MODE_GATHER, false>(p, grid, s);
-        default: ES_CHECK(!res2, "plain mode has no skip input"); return launch_mode<MODE_PLAIN, false>(p, grid, s);
+        case MODE_PLAIN: ES_CHECK(!res2, "plain mode has no skip input"); return launch_mode<MODE_PLAIN, false>(p, grid, s);
+        default: ES_CHECK(false, "unknown mode"); return 1;
     }
 }
 
@@ -680,15 +663,13 @@ int launch_umma_dec_gathered(int B, int T, int N, const float* X, const float* d
     ES_CHECK(gather_x || gather_res2, "nothing to gather");
     ES_CHECK(!gather_res2 || res2, "gathered skip without a table");
     ES_CHECK(!(gather_x && res2) || gather_res2, "a layer that gathers its input also gathers its skip (first block)");
-    if (!g_err_flag) {
-        ES_CUDA(cudaMalloc(&g_err_flag, sizeof(int)));
-        ES_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
-    }
+    int* const g_err_flag = umma_err_flag();
+    ES_CHECK(g_err_flag, "cannot allocate the device error flag");
     int dev = 0, n_sm = 0;
     ES_CUDA(cudaGetDevice(&dev));
     ES_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     UmmaDecParams p;
-    p.B = B; p.T = T; p.N = N; p.n_src = 0; p.X = X; p.cum = nullptr; p.valid_len = nullptr;
+    p.B = B; p.T = T; p.N = N; p.X = X;
     p.dw_w = dw_w; p.dw_b = dw_b; p.w_h16 = w_h16; p.bias = bias; p.act_tanh = act_tanh;
     p.ln_g = ln_g; p.ln_b = ln_b; p.res2 = res2; p.ln2_g = ln2_g; p.ln2_b = ln2_b;
     p.zero_from = nullptr; p.src = src; p.pad_id = pad_id;
@@ -701,11 +682,12 @@ int launch_umma_dec_gathered(int B, int T, int N, const float* X, const float* d
 
 // device flag raised by any tcgen05 kernel whose bounded mbarrier wait timed out (shared with es_umma_enc.cu)
 int* umma_err_flag() {
-    if (!g_err_flag) {
-        if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) return nullptr;
-        cudaMemset(g_err_flag, 0, sizeof(int));
+    int*& flag = g_err_flags.get();
+    if (!flag) {
+        if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) { flag = nullptr; return nullptr; }
+        cudaMemset(flag, 0, sizeof(int));
     }
-    return g_err_flag;
+    return flag;
 }
 
 // debug: subsequent tcgen05 decoder launches stamp clock64() per role/tile/event into buf (CTA 0)
@@ -718,6 +700,7 @@ void umma_dec_set_trace(long long* buf) {
 
 // Reads (and clears) the device-side mbarrier-timeout flag; synchronises the stream.
 int umma_dec_check_errors(cudaStream_t s) {
+    int* const g_err_flag = g_err_flags.get();
     if (!g_err_flag) return 0;
     int h = 0;
     ES_CUDA(cudaMemcpyAsync(&h, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -5,8 +5,7 @@
 // a 128-frame tile is processed in chunks of 32 input channels, and three rings run in lock step
 //
 //   x ring   (4 stages)  [132 rows][32 ch] fp32, filled by the producers with 16-byte cp.async
-//                        (zero-fill outside the utterance / for padded frames; in GATHER mode the
-//                        rows come from the length-regulator source indices), 3 chunks in flight.
+//                        (zero-fill outside the utterance / for padded frames), 3 chunks in flight.
 //                        Every producer thread owns one 16-byte column piece and rows r, r+16, ...:
 //                        the per-chunk address work is one pointer plus compile-time offsets.
 //   A ring   (3 stages)  the producers' depthwise conv (k=5, sliding window in registers) of the
@@ -27,8 +26,8 @@
 // normalised (+ skip, second statistics, written back again on block-end layers) and finally
 // stored with 8-byte accesses (8 rows x 32 contiguous bytes per warp instruction).
 //
-// Same modes as es_umma_dec.cu: DWCONV (decoder layer), GATHER (length regulator + projection,
-// K = 4d up to 512), PLAIN (mel head, N = 80).
+// Same modes as es_umma_dec.cu: DWCONV (decoder layer), PLAIN (per-phoneme projection with K = 4d up to 512;
+// mel head, N = 80).
 #include <stdlib.h>
 
 #include "es_common.cuh"
@@ -66,14 +65,11 @@ constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;
 static_assert(OFF_W % 128 == 0 && OFF_A % 128 == 0, "operand alignment");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
-enum { MODE_DWCONV = 0, MODE_GATHER = 1, MODE_PLAIN = 2 };
+enum { MODE_DWCONV = 0, MODE_PLAIN = 2 };
 
 struct Dec256Params {
     int B, T, K;                 // K input channels (multiple of 32, <= 512)
-    int n_src;
-    const float* X;              // DWCONV/PLAIN: [B,T,K]; GATHER: fused4 [B,n_src,K]
-    const int* cum;
-    const int* valid_len;
+    const float* X;              // [B,T,K]
     const float* dw_w;           // [5][K]
     const float* dw_b;           // [K]
     const void* w_chunks;        // [K/32][2 (hi,lo)][4][N][8] halves
@@ -137,8 +133,6 @@ umma_dec256_kernel(const Dec256Params p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float* par = reinterpret_cast<float*>(smem + OFF_PAR);
     float* dws = reinterpret_cast<float*>(smem + OFF_DW);
-    int* srcs = reinterpret_cast<int*>(smem + OFF_SRC);
-    int* scum = reinterpret_cast<int*>(smem + OFF_CUM);
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
     const uint32_t bar_wfull = bar0;            // [3] W chunk landed
     const uint32_t bar_cfree = bar0 + 24;       // [3] chunk stage (A and W) consumed by its MMAs
@@ -259,9 +253,7 @@ umma_dec256_kernel(const Dec256Params p) {
         auto tile_setup = [&](int i) {
             const int tile = blockIdx.x + i * gridDim.x;
             const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM2;
-            if (MODE == MODE_GATHER) {
-                ld_base = p.X + (size_t)b * p.n_src * K + q * 4;
-            } else {
+            {
                 const int tf = t0 - HALO + xrow;
                 ld_base = p.X + ((long long)b * p.T + tf) * K + q * 4;
                 ld_mask = 0;
@@ -279,14 +271,8 @@ umma_dec256_kernel(const Dec256Params p) {
                 if (XROWS % 16 == 0 || it < XITER - 1 || xrow + 16 * it < XROWS) {
                     const float* src;
                     bool ok;
-                    if (MODE == MODE_GATHER) {
-                        const int sidx = srcs[(ld_i & 1) * TM2 + xrow + 16 * it];
-                        ok = sidx >= 0;
-                        src = ld_base + (size_t)(ok ? sidx : 0) * K + ld_c * KC;
-                    } else {
-                        ok = (ld_mask >> it) & 1u;
-                        src = ok ? ld_base + (size_t)(16 * it) * K + ld_c * KC : p.X;
-                    }
+                    ok = (ld_mask >> it) & 1u;
+                    src = ok ? ld_base + (size_t)(16 * it) * K + ld_c * KC : p.X;
                     cp_async16(dst + (uint32_t)it * (16u * KC * 4u), src, ok ? 16u : 0u);
                 }
             }
@@ -296,32 +282,6 @@ umma_dec256_kernel(const Dec256Params p) {
                 if (++ld_i < my_tiles) tile_setup(ld_i);
             }
         };
-        // length regulator: source phoneme of every frame of tile i (GATHER mode)
-        auto compute_srcs = [&](int i) {
-            if (i >= my_tiles) return;
-            const int tile = blockIdx.x + i * gridDim.x;
-            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM2;
-            const bool in_smem = p.n_src <= 1024;
-            if (in_smem) {
-                for (int k = ptid; k < p.n_src; k += NPROD) scum[k] = __ldg(p.cum + (size_t)b * p.n_src + k);
-                named_bar_sync(1, NPROD);
-            }
-            const int t = t0 + ptid;
-            int sidx = -1;
-            if (t < p.T && t < p.valid_len[b]) {
-                const int* cg = p.cum + (size_t)b * p.n_src;
-                int lo = 0, hi = p.n_src;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    const int cv = in_smem ? scum[mid] : __ldg(cg + mid);
-                    if (cv > t) hi = mid; else lo = mid + 1;
-                }
-                sidx = lo < p.n_src ? lo : -1;
-            }
-            srcs[(i & 1) * TM2 + ptid] = sidx;
-            named_bar_sync(1, NPROD);
-        };
-        if (MODE == MODE_GATHER) { compute_srcs(0); compute_srcs(1); }
         if (my_tiles > 0) tile_setup(0);
         for (int g = 0; g < 3; ++g) {                         // three chunks in flight
             if (g < total_chunks) load_next();
@@ -331,7 +291,6 @@ umma_dec256_kernel(const Dec256Params p) {
         for (int g = 0; g < total_chunks; ++g) {
             cp_async_wait<2>();                               // this thread's share of chunk g has landed
             named_bar_sync(2, NPROD);                         // ... everybody's; chunk g-1's stage is free
-            if (MODE == MODE_GATHER && c == 0 && i >= 1) compute_srcs(i + 1);   // sources one tile ahead
             if (g + 3 < total_chunks) load_next();
             cp_async_commit();
 
@@ -540,7 +499,7 @@ umma_dec256_kernel(const Dec256Params p) {
 
 template <int MODE, int N>
 int launch_mode256(const Dec256Params& p, int grid, cudaStream_t s) {
-    static bool attr_set = false;
+    static PerDeviceSlot<bool> attr_once; bool& attr_set = attr_once.get();   // function attributes are per device
     if (!attr_set) {
         ES_CUDA(cudaFuncSetAttribute(umma_dec256_kernel<MODE, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
@@ -556,13 +515,12 @@ bool umma_dec256_supported(int K, int dw_k, int N, int mode) {
     if (N != 256 && N != 80) return false;
     if (K % KC || K < KC || K > 512) return false;
     if (mode == MODE_DWCONV && (K != 256 || dw_k != DWK || N != 256)) return false;
-    if (mode == MODE_GATHER && N != 256) return false;
+    if (mode != MODE_DWCONV && mode != MODE_PLAIN) return false;
     return true;
 }
 
-// mode: 0 depthwise layer, 1 gather + projection, 2 plain (mel head / stand-alone projection)
-int launch_umma_dec256(int mode, int B, int T, int K, int N, int n_src, const float* X, const int* cum,
-                       const int* valid_len, const float* dw_w, const float* dw_b, const void* w_chunks,
+// mode: 0 depthwise layer, 2 plain (mel head / stand-alone projection)
+int launch_umma_dec256(int mode, int B, int T, int K, int N, const float* X, const float* dw_w, const float* dw_b, const void* w_chunks,
                        const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
                        const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
                        float* Y, cudaStream_t s) {
@@ -572,14 +530,14 @@ int launch_umma_dec256(int mode, int B, int T, int K, int N, int n_src, const fl
     ES_CHECK(!res2 || ln_g, "the skip path needs the first LayerNorm");
     int* err_flag = umma_err_flag();
     ES_CHECK(err_flag, "cannot allocate the device error flag");
-    static int n_sm = 0;
+    static PerDeviceSlot<int> n_sm_once; int& n_sm = n_sm_once.get();
     if (!n_sm) {
         int dev = 0;
         ES_CUDA(cudaGetDevice(&dev));
         ES_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
     Dec256Params p;
-    p.B = B; p.T = T; p.K = K; p.n_src = n_src; p.X = X; p.cum = cum; p.valid_len = valid_len;
+    p.B = B; p.T = T; p.K = K; p.X = X;
     p.dw_w = dw_w; p.dw_b = dw_b; p.w_chunks = w_chunks; p.bias = bias; p.act_tanh = act_tanh;
     p.ln_g = ln_g; p.ln_b = ln_b; p.res2 = res2; p.ln2_g = ln2_g; p.ln2_b = ln2_b;
     p.zero_from = zero_from; p.Y = Y; p.err = err_flag;
@@ -587,7 +545,6 @@ int launch_umma_dec256(int mode, int B, int T, int K, int N, int n_src, const fl
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
     switch (mode) {
         case MODE_DWCONV: return launch_mode256<MODE_DWCONV, 256>(p, grid, s);
-        case MODE_GATHER: return launch_mode256<MODE_GATHER, 256>(p, grid, s);
         default:
             if (N == 256) return launch_mode256<MODE_PLAIN, 256>(p, grid, s);
             return launch_mode256<MODE_PLAIN, 80>(p, grid, s);

@@ -393,7 +393,7 @@ int launch_umma_rowgemm_batch(const RowGemmParams* ps, const void* const* w_h16,
     if (p.stride == 1 && p.n_in != p.n_out) return -1;       // 'same' convs only (pad = taps / 2)
     int* err_flag = umma_err_flag();
     ES_CHECK(err_flag, "cannot allocate the device error flag");
-    static int n_sm = 0;
+    static PerDeviceSlot<int> n_sm_once; int& n_sm = n_sm_once.get();
     if (!n_sm) {
         int dev = 0;
         ES_CUDA(cudaGetDevice(&dev));
@@ -401,7 +401,7 @@ int launch_umma_rowgemm_batch(const RowGemmParams* ps, const void* const* w_h16,
     }
     const int nj = p.Nout > 128 ? 16 : p.Nout / 8;
     if (nj != 4 && nj != 8 && nj != 12 && nj != 16) return -1;
-    static bool attr_set = false;
+    static PerDeviceSlot<bool> attr_once; bool& attr_set = attr_once.get();   // function attributes are per device
     if (!attr_set) {
         ES_CUDA(cudaFuncSetAttribute(umma_rowgemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         ES_CUDA(cudaFuncSetAttribute(umma_rowgemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

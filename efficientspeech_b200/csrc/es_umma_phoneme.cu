@@ -854,13 +854,13 @@ int launch_umma_phoneme(const es_config_t& cfg, const es_weights_t& w, int B, in
     if (!umma_phoneme_supported(cfg, w, N) || n1 > 64 || n1 < 1) return -1;
     int* err_flag = umma_err_flag();
     ES_CHECK(err_flag, "cannot allocate the device error flag");
-    static int n_sm = 0;
+    static PerDeviceSlot<int> n_sm_once; int& n_sm = n_sm_once.get();
     if (!n_sm) {
         int dev = 0;
         ES_CUDA(cudaGetDevice(&dev));
         ES_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    static bool attr_set = false;
+    static PerDeviceSlot<bool> attr_once; bool& attr_set = attr_once.get();   // function attributes are per device
     if (!attr_set) {
         ES_CUDA(cudaFuncSetAttribute(umma_phoneme_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
         ES_CUDA(cudaFuncSetAttribute(umma_phoneme_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));

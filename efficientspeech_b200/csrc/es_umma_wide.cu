@@ -448,7 +448,7 @@ umma_wide_kernel(const WideParams wp) {
 
 template <int NT, int TAPS>
 int launch_wide(const WideParams& wp, dim3 grid, cudaStream_t s) {
-    static bool attr_set = false;
+    static PerDeviceSlot<bool> attr_once; bool& attr_set = attr_once.get();   // function attributes are per device
     if (!attr_set) {
         ES_CUDA(cudaFuncSetAttribute(umma_wide_kernel<NT, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
@@ -503,7 +503,7 @@ int launch_umma_wide(const RowGemmParams& p_in, const void* w_units, cudaStream_
     }
     int* err_flag = umma_err_flag();
     ES_CHECK(err_flag, "cannot allocate the device error flag");
-    static int n_sm = 0;
+    static PerDeviceSlot<int> n_sm_once; int& n_sm = n_sm_once.get();
     if (!n_sm) {
         int dev = 0;
         ES_CUDA(cudaGetDevice(&dev));

@@ -151,7 +151,7 @@ class _Backend:
         self.handle = C.c_void_p(None)
         self.workspace: Optional[torch.Tensor] = None
         self.tensor_core = True
-        # ES_DEC_GATHER_MODE (0/1/2) overrides the default for A/B runs of the same command line
+        # ES_DEC_GATHER_MODE (1/2) overrides the default for A/B runs of the same command line
         self.gather_mode = int(os.environ.get("ES_DEC_GATHER_MODE", _cabi.ES_GATHER_FUSED))
         self.fused_phoneme = os.environ.get("ES_FUSED_PHONEME", "1") != "0"
 
@@ -317,10 +317,10 @@ class MelDecoder(nn.Module):
 
     def set_gather_mode(self, mode: int) -> None:
         """How ``Phoneme2Mel`` joins the length regulator and this decoder (include/es_b200.h, ES_GATHER_*):
-        0 projection per frame with the gather in its operand load; 1 projection per phoneme + row-gather
-        kernel; 2 (default) projection per phoneme, the first block gathers the rows itself."""
-        if mode not in (0, 1, 2):
-            raise ValueError("gather mode must be 0, 1 or 2")
+        1 projection per phoneme + row-gather kernel; 2 (default) projection per phoneme, the first block gathers the
+        rows itself.  Bit-identical results."""
+        if mode not in (1, 2):
+            raise ValueError("gather mode must be 1 or 2")
         self._backend.gather_mode = int(mode)
 
     def forward(self, features):
@@ -395,7 +395,11 @@ class PhonemeEncoder(nn.Module):
         B, N = phoneme.shape
         d = self._cfg.dim
         ids = phoneme.to(torch.int32).contiguous()
-        mask = x["phoneme_mask"] if B > 1 else None                     # networks.py:338
+        # networks.py:338 drops the mask when the batch holds ONE utterance.  A shard of a larger batch
+        # (sharding.shard_batch) can have one row too: it carries x["global_batch_size"], and the mask decision
+        # follows the GLOBAL batch so that shards stay bit-comparable with the unsharded run.
+        gB = int(x.get("global_batch_size", B))
+        mask = x["phoneme_mask"] if gB > 1 else None
         mask_u8 = None
         if mask is not None:
             mask_u8 = mask.to(device=dev, dtype=torch.bool).contiguous().view(torch.uint8)
@@ -429,9 +433,13 @@ class PhonemeEncoder(nn.Module):
             T = int(T)
         else:
             T = int(mel_len.max().item())                               # networks.py:246 (one sync, not B)
+            # the stream is idle here anyway: poll the device-side mbarrier-timeout flag (covers this call's
+            # phoneme-side kernels and the previous call's decoder), so a pipeline fault cannot pass silently
+            with torch.cuda.device(dev):
+                _cabi.check(_cabi.load().es_check_async_errors(_stream(dev)))
         return {"pitch": pitch, "energy": energy, "duration": dur, "mel_len": mel_len,
                 "_fused4": fused4, "_dur_cum": dur_cum, "_dur_int": dur_int, "_T": T,
-                "_mask_u8": mask_u8}
+                "_mask_u8": mask_u8, "_global_B": gB}
 
     def _expand(self, y):
         """FeatureUpsampler.forward (networks.py:228-258): materialise features / masks."""
@@ -446,6 +454,7 @@ class PhonemeEncoder(nn.Module):
                 _ptr(y["_mask_u8"]), feats.data_ptr(), fmask.data_ptr(), None))
         y["features"] = feats
         # the reference returns a [B,T,4d] bool tensor; this is the same values as a broadcast view
+        # (None for a single-utterance batch, networks.py:391-392)
         y["masks"] = None if y["_mask_u8"] is None else fmask.view(torch.bool).unsqueeze(-1).expand(B, T, C4)
         return y
 
@@ -501,11 +510,10 @@ class Phoneme2Mel(nn.Module):
         if T <= 0:
             raise RuntimeError("all durations are zero: the utterances have no frames "
                                "(the reference raises inside its decoder convolution here)")
-        B = pred["mel_len"].shape[0]
         # decoder with the length-regulator gather fused into its first kernel; padded frames are
-        # zeroed only when B > 1, like the reference (networks.py:424-427)
+        # zeroed only when the (global) batch has more than one utterance, like the reference (networks.py:424-427)
         mel = self.decoder._forward_gathered(pred["_fused4"], pred["_dur_cum"], pred["mel_len"], T,
-                                             zero_padded=B > 1)
+                                             zero_padded=pred["_global_B"] > 1)
         pred["mel"] = mel
         if train:
             if self.return_features:
@@ -533,11 +541,28 @@ class GraphedForward:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.static_out = model(self.static_in, train=train)
+        # the graph holds raw pointers into the backends' workspaces and packed weight images: keep them alive here
+        # and remember which weight version / switches they belong to
+        self._pinned = [(b, b.key, b.workspace, b.flat) for b in (model.encoder._backend, model.decoder._backend)]
+
+    def _check_current(self):
+        for b, key, ws, flat in self._pinned:
+            params = list(b.owner.parameters())
+            now = key[:4] + tuple((p.data_ptr(), p._version) for p in params)
+            if now != key:
+                raise RuntimeError("GraphedForward: the model's weights, device or kernel switches changed after capture; "
+                                   "capture again (the graph replays the packed image it was captured with)")
 
     def __call__(self, x=None):
+        self._check_current()
         if x is not None:
+            T = x.get("max_mel_len")
+            if T is not None and int(T) != int(self.static_in["max_mel_len"]):
+                raise ValueError(f"GraphedForward was captured with max_mel_len={self.static_in['max_mel_len']}, got {T}")
             for k, v in x.items():
                 if torch.is_tensor(v):
+                    if tuple(v.shape) != tuple(self.static_in[k].shape):
+                        raise ValueError(f"GraphedForward: x[{k!r}] has shape {tuple(v.shape)}, captured {tuple(self.static_in[k].shape)}")
                     self.static_in[k].copy_(v, non_blocking=True)
         self.graph.replay()
         return self.static_out

@@ -37,10 +37,18 @@ def shard_batch(batch: Dict[str, object], rank: int, world: int) -> Dict[str, ob
     """Slice every per-utterance tensor along dim 0.  The phoneme dimension is NOT re-padded:
     the unmasked attention makes each utterance depend on its own padding to the GLOBAL N_max
     (SURVEY.md H3), so shards keep the full batch's phoneme length to stay bit-comparable with
-    the unsharded run; T_max may differ per shard (padded frames are position independent)."""
+    the unsharded run, and teacher-forced shards keep the global frame count (``max_mel_len``) for the same reason
+    (SURVEY.md H4).  Free-running shards derive T from their own predicted durations, as the reference would.
+    The shard carries ``global_batch_size``: the reference drops the phoneme mask for a one-utterance batch
+    (networks.py:338), and a shard of size 1 must keep following the GLOBAL batch's policy."""
     B = batch["phoneme"].shape[0]
     lo, hi = shard_bounds(B, rank, world)
     out = {}
     for k, v in batch.items():
         out[k] = v[lo:hi] if hasattr(v, "shape") and len(v.shape) > 0 and v.shape[0] == B else v
+    out["global_batch_size"] = int(batch.get("global_batch_size", B))
+    if "mel_len" in batch and "max_mel_len" not in batch:
+        # teacher-forced: padded frames flow through the decoder (SURVEY H4), so the frames next to an utterance's end
+        # depend on whether pad-row frames or the convolution's zero padding follow them -- shards keep the global T
+        out["max_mel_len"] = int(max(batch["mel_len"]))
     return out

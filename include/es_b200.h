@@ -158,13 +158,11 @@ int  es_model_set_tensor_core(es_model_t* m, int enable);
 int  es_model_set_fused_phoneme(es_model_t* m, int enable);
 
 /* How es_decoder_forward_gathered joins the length regulator and the decoder (default ES_GATHER_FUSED):
- *   ES_GATHER_PER_FRAME    projection GEMM per frame with the gather in its operand load (first version)
  *   ES_GATHER_MATERIALIZE  projection per phoneme, then a row-gather kernel writes skip [B,T,dx2]
  *   ES_GATHER_FUSED        projection per phoneme; the first decoder block gathers rows of the table itself
  *                          ([B,T,dx2] is never written); decoders without that kernel variant (dx2 = 256, SIMT
  *                          mode) fall back to ES_GATHER_MATERIALIZE.
- * All three compute the same function; results agree to fp32 rounding of one 4d-long dot product. */
-#define ES_GATHER_PER_FRAME   0
+ * Both compute the same function (bit-identical).  (Value 0, a projection GEMM per frame, was removed.) */
 #define ES_GATHER_MATERIALIZE 1
 #define ES_GATHER_FUSED       2
 int  es_model_set_decoder_gather(es_model_t* m, int mode);

@@ -1,14 +1,28 @@
-"""Import the UNMODIFIED reference ``layers`` package from /root/reference (build container only).
+"""Import the UNMODIFIED reference ``layers`` package.
 
-TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box; nothing that runs
-there imports this module.  The two stubbed modules are text-front-end dependencies the
+TEST / BASELINE INFRASTRUCTURE.  Two locations, in this order: ``oracle/_ref/`` (the staged copy made by
+``oracle/build_ref.py``; git-ignored, travels to the GPU box like the built ``.so``) and ``/root/reference``
+(build container only -- it does not exist on the GPU box).  Only ``tests/``, ``bench.py``'s CPU legs and the
+scripts under ``oracle/`` import this module.  The two stubbed modules are text-front-end dependencies the
 acoustic path never calls.
 """
 import os
 import sys
 import types
 
-REF_DIR = os.environ.get("ES_REFERENCE_DIR", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(_HERE, "_ref")
+_MOUNTED = os.environ.get("ES_REFERENCE_DIR", "/root/reference")
+
+
+def _pick() -> str:
+    for d in (_STAGED, _MOUNTED):
+        if os.path.isfile(os.path.join(d, "layers", "networks.py")):
+            return d
+    return _MOUNTED
+
+
+REF_DIR = _pick()
 
 
 def reference_available() -> bool:

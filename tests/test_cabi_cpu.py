@@ -118,9 +118,9 @@ def test_path_switches_and_workspace_planning_on_the_host():
     h = ctypes.c_void_p(None)
     assert lib.es_model_create(ctypes.byref(cfg), ctypes.byref(w), ctypes.byref(h)) == 0
     try:
-        for mode in (_cabi.ES_GATHER_PER_FRAME, _cabi.ES_GATHER_MATERIALIZE, _cabi.ES_GATHER_FUSED):
+        for mode in (_cabi.ES_GATHER_MATERIALIZE, _cabi.ES_GATHER_FUSED):
             assert lib.es_model_set_decoder_gather(h, mode) == 0
-        assert lib.es_model_set_decoder_gather(h, 7) != 0
+        assert lib.es_model_set_decoder_gather(h, 7) != 0 and lib.es_model_set_decoder_gather(h, 0) != 0
         assert b"gather mode" in lib.es_last_error()
         assert lib.es_model_set_fused_phoneme(h, 0) == 0 and lib.es_model_set_fused_phoneme(h, 1) == 0
         assert lib.es_model_set_tensor_core(h, 0) == 0 and lib.es_model_set_tensor_core(h, 1) == 0
