@@ -1,6 +1,7 @@
 // C ABI (include/es_b200.h): model handle, workspace planning and the kernel sequence of the
 // acoustic forward path.  Host code only; every kernel lives in the sibling .cu files.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -567,24 +568,26 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
             while (out_idx == s_idx || out_idx == in_idx) ++out_idx;
             const es_dec_layer_w_t& w = m->w.dec[layer];
             const bool last = (l == m->cfg.block_depth - 1);
-            if (in_idx < 0 || (last && s_idx < 0)) {
-                // first block of the gathered entry: input and / or skip rows come from the projection table
+            const bool gx = in_idx < 0, gs = last && s_idx < 0;
+            if (gx || gs)
                 ES_CHECK(db.P && db.src && w.pw_w_h16 && umma_dec_supported(C, m->cfg.decoder_kernel_size, C),
                          "virtual skip needs the 128-channel tcgen05 layer kernel");
-                ProfRange r(ES_K_DEC_LAYER, s);
-                if (launch_umma_dec_gathered(B, T, C, in_idx < 0 ? db.P : db.buf[in_idx], w.dw_w, w.dw_b, w.pw_w_h16, w.pw_b, 1,
-                                             w.ln_g, w.ln_b, last ? (s_idx < 0 ? db.P : db.buf[s_idx]) : nullptr,
-                                             last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
-                                             db.src, db.pad_id, in_idx < 0, last && s_idx < 0, db.buf[out_idx], s)) return 1;
-                in_idx = out_idx;
-                continue;
-            }
             if (m->use_tensor_core && w.pw_w_h16 && umma_dec_supported(C, m->cfg.decoder_kernel_size, C)) {
+                // 128-channel decoders: one fused tcgen05 kernel per layer; in the first block of the gathered entry the
+                // input and / or skip rows come from the projection table through the frame -> row map
                 ProfRange r(ES_K_DEC_LAYER, s);
-                if (launch_umma_dec(0, B, T, C, db.buf[in_idx], w.dw_w, w.dw_b, w.pw_w_h16,
-                                    w.pw_b, 1, w.ln_g, w.ln_b, last ? db.buf[s_idx] : nullptr,
-                                    last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
-                                    nullptr, db.buf[out_idx], s)) return 1;
+                const float* xin = gx ? db.P : db.buf[in_idx];
+                const float* skip = last ? (s_idx < 0 ? db.P : db.buf[s_idx]) : nullptr;
+                int rc;
+                if (gx || gs)
+                    rc = launch_umma_dec_gathered(B, T, C, xin, w.dw_w, w.dw_b, w.pw_w_h16, w.pw_b, 1, w.ln_g, w.ln_b, skip,
+                                                  last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
+                                                  db.src, db.pad_id, gx, gs, db.buf[out_idx], s);
+                else
+                    rc = launch_umma_dec(0, B, T, C, xin, w.dw_w, w.dw_b, w.pw_w_h16, w.pw_b, 1, w.ln_g, w.ln_b, skip,
+                                         last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
+                                         nullptr, db.buf[out_idx], s);
+                if (rc) return 1;
                 in_idx = out_idx;
                 continue;
             }

@@ -276,9 +276,9 @@ def test_frame_rows_exact_random():
 @pytest.mark.parametrize("vname,B,N,max_dur", [("tiny", 5, 40, 9), ("tiny", 3, 129, 4), ("tiny", 1, 33, 7),
                                                ("tiny", 4, 64, 40), ("small", 4, 33, 6), ("base", 2, 31, 6)])
 def test_gather_modes_agree(vname, B, N, max_dur):
-    """The three ways of joining the length regulator and the decoder (ES_GATHER_*): projection per frame,
-    projection per phoneme + row-gather kernel, projection per phoneme + gathered loads in the first block.
-    All within the mel bar of the oracle; the two per-phoneme forms are bit-identical."""
+    """The two ways of joining the length regulator and the decoder (ES_GATHER_*): projection per phoneme + row-gather
+    kernel, projection per phoneme + gathered loads in the first block.  Both within the mel bar of the oracle and
+    bit-identical to each other."""
     cfg = VARIANTS[vname]
     sd = init_state_dict(cfg, seed=31 + N)
     batch = make_batch(cfg, B, N, seed=N + B, ragged=B > 1, fixed_duration=None, max_dur=max_dur)
@@ -287,7 +287,7 @@ def test_gather_modes_agree(vname, B, N, max_dur):
     o = es_oracle.phoneme2mel(batch, sd, train=True)
     got = {}
     try:
-        for mode in (0, 1, 2):
+        for mode in (1, 2):
             model.decoder.set_gather_mode(mode)
             with torch.no_grad():
                 got[mode] = npy(model(x, train=True)["mel"])
@@ -296,7 +296,6 @@ def test_gather_modes_agree(vname, B, N, max_dur):
     finally:
         model.decoder.set_gather_mode(2)
     assert np.array_equal(got[1], got[2])
-    assert np.abs(got[0] - got[1]).max() <= 5e-5
 
 
 def test_gather_fused_zero_duration_run():
