@@ -9,9 +9,11 @@ The compute lives in ``libes_b200.so`` (hand-written CUDA behind the C ABI of
 """
 from .config import ESConfig, VARIANTS, variant, LJSPEECH_PITCH_STATS, LJSPEECH_ENERGY_STATS  # noqa: F401
 from .modules import (AcousticDecoder, Encoder, FeatureUpsampler, Fuse, MelDecoder, MixFFN,  # noqa: F401
-                      Phoneme2Mel, PhonemeEncoder, SelfAttention)
+                      Phoneme2Mel, PhonemeEncoder, SelfAttention, mel_to_half)
 
-__version__ = "0.1.0"
+from .collate import collate, collate_flat  # noqa: F401
+
+__version__ = "0.2.0"
 
 
 def build_model(cfg_or_name="tiny") -> "Phoneme2Mel":

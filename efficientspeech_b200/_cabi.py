@@ -8,7 +8,7 @@ from typing import Optional
 
 from . import build as _build
 
-ES_ABI_VERSION = 10
+ES_ABI_VERSION = 11
 ES_GATHER_MATERIALIZE, ES_GATHER_FUSED = 1, 2
 ES_MAX_ENC_BLOCKS = 2
 ES_MAX_DEC_LAYERS = 24
@@ -64,10 +64,13 @@ PROTOTYPES = {
     "es_model_set_tensor_core": (_i, [_vp, _i]),
     "es_model_set_decoder_gather": (_i, [_vp, _i]),
     "es_model_set_fused_phoneme": (_i, [_vp, _i]),
+    "es_model_set_ragged_schedule": (_i, [_vp, _i]),
     "es_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "es_encoder_forward": (_i, [_vp, _vp, _i, _i] + [_vp] * 12 + [_vp, _sz]),
     "es_length_regulate": (_i, [_vp, _vp, _i, _i, _i] + [_vp] * 6),
     "es_frame_rows": (_i, [_vp, _vp, _i, _i, _i] + [_vp] * 3),
+    "es_collate": (_i, [_vp, _i, _i] + [_vp] * 13),
+    "es_mel_to_half": (_i, [_vp, _vp, _vp, _sz]),
     "es_decoder_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _sz]),
     "es_decoder_forward_gathered": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _sz]),
     "es_dense_layout": (_i, [_i, _i, _i, _i]),

@@ -49,6 +49,7 @@ struct es_model {
     int use_tensor_core;
     int gather_mode;        // es_model_set_decoder_gather: ES_GATHER_* (how the length regulator meets the decoder)
     int fused_phoneme;      // es_model_set_fused_phoneme: whole phoneme side in one kernel where supported
+    int ragged_schedule;    // es_model_set_ragged_schedule: the decoder skips tiles that cannot reach a valid frame
     // derived geometry
     int d, C[2], H[2], k[2], hC[2], dx4, dx2, n_layers;
 };
@@ -108,15 +109,19 @@ struct DecBufs {
     float* P;            // gathered entry (N > 0): per-phoneme projection table [B*N + 1][dx2], last row = padded frames
     int* src;            //                         frame -> table row map [B*T]
     int pad_id;          //                         = B*N, the table row of the zero-padded frames
+    int2* tiles;         // ragged schedule (es_gather.cu): (b, t0) of the tiles that can reach a valid frame, [B * ceil(T/64)]
+    int* tile_count;     //                                 their number
 };
 
 DecBufs plan_decoder(const es_model* m, Arena& a, int B, int N, int T) {
     DecBufs d;
     for (int i = 0; i < 3; ++i) d.buf[i] = a.take<float>((size_t)B * T * m->dx2);
-    d.P = nullptr; d.src = nullptr; d.pad_id = B * N;
+    d.P = nullptr; d.src = nullptr; d.pad_id = B * N; d.tiles = nullptr; d.tile_count = nullptr;
     if (N > 0) {
         d.P = a.take<float>(((size_t)B * N + 1) * m->dx2);
         d.src = a.take<int>((size_t)B * T);
+        d.tiles = a.take<int2>((size_t)B * ((T + 63) / 64));
+        d.tile_count = a.take<int>(1);
     }
     return d;
 }
@@ -257,7 +262,8 @@ int predictors(const es_model* m, int B, int N, const float* fused, float* const
 }
 
 int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, const int* zero_from,
-                   float* mel, cudaStream_t s);
+                   float* mel, cudaStream_t s, bool ragged = false);
+bool decoder_all_umma256(const es_model* m);
 int project_rows(const es_model* m, int rows, const float* in, float* out, cudaStream_t s);
 bool decoder_all_umma128(const es_model* m);
 
@@ -328,6 +334,7 @@ int es_model_create(const es_config_t* cfg, const es_weights_t* w, es_model_t** 
     m->use_tensor_core = 1;
     m->gather_mode = ES_GATHER_FUSED;
     m->fused_phoneme = 1;
+    m->ragged_schedule = 1;
     m->d = cfg->dim;
     m->C[0] = cfg->dim; m->C[1] = 2 * cfg->dim;
     m->H[0] = cfg->head; m->H[1] = 2 * cfg->head;
@@ -351,6 +358,12 @@ int es_model_set_tensor_core(es_model_t* m, int enable) {
 int es_model_set_fused_phoneme(es_model_t* m, int enable) {
     ES_CHECK(m, "null model");
     m->fused_phoneme = enable ? 1 : 0;
+    return 0;
+}
+
+int es_model_set_ragged_schedule(es_model_t* m, int enable) {
+    ES_CHECK(m, "null model");
+    m->ragged_schedule = enable ? 1 : 0;
     return 0;
 }
 
@@ -473,6 +486,18 @@ int es_frame_rows(es_model_t* m, void* stream, int B, int N, int T,
                                static_cast<cudaStream_t>(stream));
 }
 
+int es_collate(void* stream, int B, int N, const int32_t* offsets, const int32_t* phoneme_flat, const float* pitch_flat,
+               const float* energy_flat, const int32_t* duration_flat, int32_t* perm, int32_t* phoneme,
+               uint8_t* phoneme_mask, int32_t* phoneme_len, float* pitch, float* energy, int32_t* duration,
+               int32_t* mel_len) {
+    return launch_collate(B, N, offsets, phoneme_flat, pitch_flat, energy_flat, duration_flat, perm, phoneme, phoneme_mask,
+                          phoneme_len, pitch, energy, duration, mel_len, static_cast<cudaStream_t>(stream));
+}
+
+int es_mel_to_half(void* stream, const float* mel, void* mel_f16, size_t n) {
+    return launch_cast_f32_f16(mel, mel_f16, n, static_cast<cudaStream_t>(stream));
+}
+
 int es_decoder_forward(es_model_t* m, void* stream, int B, int T, const float* features, float* mel,
                        void* workspace, size_t workspace_bytes) {
     ES_CHECK(m, "null model");
@@ -521,11 +546,29 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
     { ProfRange r(ES_K_LENREG, s);
       if (launch_frame_source(dur_cum, mel_len, db.src, B, N, T, m->w.dproj_b, m->w.dproj_ln_g, m->w.dproj_ln_b,
                               m->dx2, db.P + (size_t)R * m->dx2, s)) return 1; }
-    if (m->gather_mode == ES_GATHER_FUSED && decoder_all_umma128(m))
+    // Ragged schedule: with padded frames zeroed at the end (networks.py:424-427, B > 1) a tile that starts at or beyond
+    // mel_len[b] + 2 L cannot reach a frame anyone reads (a layer looks 2 frames each way): the tcgen05 layer kernels
+    // walk the compacted list of the other tiles, and the frames nobody computed are zero-filled in the mel.
+    const bool ragged = zero_padded_frames && m->ragged_schedule && (decoder_all_umma128(m) || decoder_all_umma256(m));
+    const int tile_frames = m->dx2 == 128 ? 64 : 128, halo = (m->cfg.decoder_kernel_size / 2) * m->n_layers;
+    if (ragged) {
+        ProfRange r(ES_K_LENREG, s);
+        if (launch_tile_list(mel_len, B, T, tile_frames, halo, db.tiles, db.tile_count, s)) return 1;
+    }
+    int rc;
+    if (m->gather_mode == ES_GATHER_FUSED && decoder_all_umma128(m)) {
         // the first block reads its input and skip rows straight from the table: [B,T,dx2] is never materialised
-        return decoder_layers(m, B, T, db, -1, zero_padded_frames ? mel_len : nullptr, mel, s);
-    { ProfRange r(ES_K_LENREG, s); if (launch_gather_rows(db.P, db.src, db.buf[0], (long long)B * T, m->dx2, s)) return 1; }
-    return decoder_layers(m, B, T, db, 0, zero_padded_frames ? mel_len : nullptr, mel, s);
+        rc = decoder_layers(m, B, T, db, -1, zero_padded_frames ? mel_len : nullptr, mel, s, ragged);
+    } else {
+        { ProfRange r(ES_K_LENREG, s); if (launch_gather_rows(db.P, db.src, db.buf[0], (long long)B * T, m->dx2, s)) return 1; }
+        rc = decoder_layers(m, B, T, db, 0, zero_padded_frames ? mel_len : nullptr, mel, s, ragged);
+    }
+    if (rc) return 1;
+    if (ragged) {
+        ProfRange r(ES_K_LENREG, s);
+        if (launch_zero_tail(mel, mel_len, B, T, m->cfg.n_mel, tile_frames, halo, s)) return 1;
+    }
+    return 0;
 }
 
 }  // extern "C"
@@ -535,6 +578,14 @@ namespace {
 // every depthwise layer runs on the 128-channel tcgen05 kernel (which has the gathered-row variant)
 bool decoder_all_umma128(const es_model* m) {
     if (!m->use_tensor_core || !umma_dec_supported(m->dx2, m->cfg.decoder_kernel_size, m->dx2)) return false;
+    for (int l = 0; l < m->n_layers; ++l) if (!m->w.dec[l].pw_w_h16) return false;
+    return true;
+}
+
+// every depthwise layer and the mel head run on the 256-channel tcgen05 kernel
+bool decoder_all_umma256(const es_model* m) {
+    if (!m->use_tensor_core || m->dx2 != 256 || !umma_dec256_supported(256, m->cfg.decoder_kernel_size, 256, 0)) return false;
+    if (!m->w.mel_w_h16 || m->cfg.n_mel != 80) return false;
     for (int l = 0; l < m->n_layers; ++l) if (!m->w.dec[l].pw_w_h16) return false;
     return true;
 }
@@ -558,8 +609,10 @@ int project_rows(const es_model* m, int rows, const float* in, float* out, cudaS
 // Decoder blocks + mel head (networks.py:293-302, :424-427).  db.buf[s_idx] holds `skip`; s_idx < 0: `skip` is
 // virtual -- row db.src[b*T + t] of the table db.P -- and the first block gathers it (decoder_all_umma128 only).
 int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, const int* zero_from,
-                   float* mel, cudaStream_t s) {
+                   float* mel, cudaStream_t s, bool ragged) {
     const int C = m->dx2;
+    const int2* tl = ragged ? db.tiles : nullptr;             // ragged schedule (tcgen05 kernels only)
+    const int* tc = ragged ? db.tile_count : nullptr;
     int layer = 0;
     for (int blk = 0; blk < m->cfg.n_blocks; ++blk) {
         int in_idx = s_idx;
@@ -582,11 +635,11 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
                 if (gx || gs)
                     rc = launch_umma_dec_gathered(B, T, C, xin, w.dw_w, w.dw_b, w.pw_w_h16, w.pw_b, 1, w.ln_g, w.ln_b, skip,
                                                   last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
-                                                  db.src, db.pad_id, gx, gs, db.buf[out_idx], s);
+                                                  db.src, db.pad_id, gx, gs, db.buf[out_idx], s, tl, tc);
                 else
                     rc = launch_umma_dec(0, B, T, C, xin, w.dw_w, w.dw_b, w.pw_w_h16, w.pw_b, 1, w.ln_g, w.ln_b, skip,
                                          last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
-                                         nullptr, db.buf[out_idx], s);
+                                         nullptr, db.buf[out_idx], s, tl, tc);
                 if (rc) return 1;
                 in_idx = out_idx;
                 continue;
@@ -596,7 +649,7 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
                 if (launch_umma_dec256(0, B, T, C, C, db.buf[in_idx], w.dw_w, w.dw_b, w.pw_w_h16,
                                        w.pw_b, 1, w.ln_g, w.ln_b, last ? db.buf[s_idx] : nullptr,
                                        last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
-                                       nullptr, db.buf[out_idx], s)) return 1;
+                                       nullptr, db.buf[out_idx], s, tl, tc)) return 1;
                 in_idx = out_idx;
                 continue;
             }
@@ -617,14 +670,14 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
         ProfRange r(ES_K_MEL, s);
         return launch_umma_dec(2, B, T, m->cfg.n_mel, db.buf[s_idx], nullptr, nullptr,
                                m->w.mel_w_h16, m->w.mel_b, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
-                               zero_from, mel, s);
+                               zero_from, mel, s, tl, tc);
     }
     if (m->use_tensor_core && m->w.mel_w_h16 && C == 256 && m->cfg.n_mel == 80 &&
         umma_dec256_supported(C, m->cfg.decoder_kernel_size, 80, 2)) {
         ProfRange r(ES_K_MEL, s);
         return launch_umma_dec256(2, B, T, C, m->cfg.n_mel, db.buf[s_idx], nullptr, nullptr,
                                   m->w.mel_w_h16, m->w.mel_b, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                  zero_from, mel, s);
+                                  zero_from, mel, s, tl, tc);
     }
     RowGemmParams p = base_params(B, T, T, C, m->cfg.n_mel, db.buf[s_idx], C, m->w.mel_w, mel, m->cfg.n_mel);
     p.bias = m->w.mel_b; p.zero_from = zero_from;

@@ -14,6 +14,8 @@
 //                        (es_umma_dec.cu) or by gather_rows_kernel.
 //   gather_rows_kernel   Y[r, :] = P[src[r], :], 128-bit accesses (decoders whose layer kernel has no
 //                        gathered-load variant: dx2 = 256, fp32 SIMT mode).
+#include <cuda_fp16.h>
+
 #include "es_common.cuh"
 #include "es_kernels.cuh"
 
@@ -111,6 +113,111 @@ int launch_gather_rows(const float* P, const int32_t* src, float* Y, long long r
     long long blocks = (rows + 7) / 8;
     if (blocks > 148LL * 32) blocks = 148LL * 32;
     gather_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(P, src, Y, rows, C / 4);
+    ES_LAUNCH_OK();
+    return 0;
+}
+
+// ---- ragged scheduling -------------------------------------------------------------------------------------------------
+// A decoder layer is a 5-tap convolution along time: through L layers a frame depends on frames within 2 L of it.  The
+// reference runs the decoder over every padded frame and then zeroes the frames past mel_len (networks.py:424-427), so
+// tiles that start at or beyond mel_len[b] + halo (halo = 2 L) cannot reach a frame anyone reads.  tile_list_kernel
+// lists the others -- utterance by utterance, so consecutive CTAs still stream consecutive memory -- and the decoder
+// kernels walk that list instead of the dense B x ceil(T / TM) grid; zero_tail_kernel writes the zeros of the mel
+// frames no listed tile covers.
+namespace {
+constexpr int TL_THREADS = 1024;
+__device__ __forceinline__ int tiles_of(int valid, int T, int TM, int halo) {
+    const int ext = min(T, valid + halo);
+    return valid > 0 ? (ext + TM - 1) / TM : 0;                 // an utterance without frames needs no tile at all
+}
+__global__ void __launch_bounds__(TL_THREADS)
+tile_list_kernel(const int32_t* __restrict__ valid_len, int B, int T, int TM, int halo, int2* __restrict__ tiles,
+                 int* __restrict__ count) {
+    __shared__ int warp_sums[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < B; b0 += TL_THREADS) {
+        const int b = b0 + threadIdx.x;
+        const int n = b < B ? tiles_of(__ldg(valid_len + b), T, TM, halo) : 0;
+        int incl = n;                                              // block-wide inclusive scan: shuffles, then warp sums
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += v;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const int start = base + (warp ? warp_sums[warp - 1] : 0) + incl - n;
+        for (int k = 0; k < n; ++k) tiles[start + k] = make_int2(b, k * TM);
+        __syncthreads();
+        if (threadIdx.x == 0) base += warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
+__global__ void __launch_bounds__(256)
+zero_tail_kernel(float* __restrict__ Y, const int32_t* __restrict__ valid_len, int T, int C, int TM, int halo) {
+    const int b = blockIdx.y;
+    const int first = tiles_of(__ldg(valid_len + b), T, TM, halo) * TM;       // frames [first, T) are not covered
+    const long long n4 = (long long)(T - first) * C / 4;                      // C % 4 == 0
+    float4* y = reinterpret_cast<float4*>(Y + ((size_t)b * T + first) * C);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256)
+        y[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+}  // namespace
+
+int launch_tile_list(const int32_t* valid_len, int B, int T, int TM, int halo, int2* tiles, int* count, cudaStream_t s) {
+    ES_CHECK(valid_len && tiles && count && B >= 1 && T >= 1 && TM >= 1 && halo >= 0, "bad arguments");
+    tile_list_kernel<<<1, TL_THREADS, 0, s>>>(valid_len, B, T, TM, halo, tiles, count);
+    ES_LAUNCH_OK();
+    return 0;
+}
+
+int launch_zero_tail(float* Y, const int32_t* valid_len, int B, int T, int C, int TM, int halo, cudaStream_t s) {
+    ES_CHECK(Y && valid_len && C % 4 == 0, "bad arguments");
+    const int per_utt = (int)(((long long)T * C / 4 + 255) / 256);
+    dim3 grid(per_utt < 64 ? (per_utt > 0 ? per_utt : 1) : 64, B);
+    zero_tail_kernel<<<grid, 256, 0, s>>>(Y, valid_len, T, C, TM, halo);
+    ES_LAUNCH_OK();
+    return 0;
+}
+
+// fp32 -> fp16 (round to nearest even), 8 elements per thread: the opt-in half-precision copy of the mel that halves the
+// device -> host bytes of a PCIe-bound consumer (bench.py e2e); the fp32 mel stays the API's output.
+namespace {
+__global__ void __launch_bounds__(256)
+cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+    const size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * 8;
+    if (i + 8 <= n) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src + i) + 1);
+        __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
+        *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(h);
+    } else {
+        for (size_t k = i; k < n; ++k) dst[k] = __float2half_rn(src[k]);
+    }
+}
+}  // namespace
+
+int launch_cast_f32_f16(const float* src, void* dst, size_t n, cudaStream_t s) {
+    ES_CHECK(src && dst, "null tensor");
+    ES_CHECK((reinterpret_cast<size_t>(src) & 15) == 0 && (reinterpret_cast<size_t>(dst) & 15) == 0, "buffers must be 16-byte aligned");
+    if (n == 0) return 0;
+    const size_t blocks = (n + 2047) / 2048;
+    cast_f32_f16_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, static_cast<__half*>(dst), n);
     ES_LAUNCH_OK();
     return 0;
 }

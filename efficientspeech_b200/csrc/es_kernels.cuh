@@ -24,6 +24,15 @@ int launch_length_regulate(const float* fused4, const int32_t* cum, const uint8_
 int launch_frame_source(const int32_t* cum, const int32_t* valid_len, int32_t* src, int B, int N, int T,
                         const float* bias, const float* ln_g, const float* ln_b, int C, float* pad_row,
                         cudaStream_t s);
+// batch collation on the device (es_collate.cu)
+int launch_collate(int B, int N, const int32_t* offsets, const int32_t* ph_flat, const float* pitch_flat,
+                   const float* energy_flat, const int32_t* dur_flat, int32_t* perm, int32_t* phoneme, uint8_t* mask,
+                   int32_t* phoneme_len, float* pitch, float* energy, int32_t* duration, int32_t* mel_len, cudaStream_t s);
+int launch_cast_f32_f16(const float* src, void* dst, size_t n, cudaStream_t s);
+// ragged scheduling: the tiles of TM frames that can reach a valid frame (t0 < min(T, valid_len[b] + halo)), compacted, and
+// the zero fill of the mel frames no listed tile covers
+int launch_tile_list(const int32_t* valid_len, int B, int T, int TM, int halo, int2* tiles, int* count, cudaStream_t s);
+int launch_zero_tail(float* Y, const int32_t* valid_len, int B, int T, int C, int TM, int halo, cudaStream_t s);
 int launch_gather_rows(const float* P, const int32_t* src, float* Y, long long rows, int C, cudaStream_t s);
 
 // tcgen05 decoder kernel (es_umma_dec.cu)
@@ -31,21 +40,22 @@ bool umma_dec_supported(int C, int dw_k, int N);
 int launch_umma_dec(int mode, int B, int T, int N, const float* X, const float* dw_w, const float* dw_b, const void* w_h16,
                     const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
                     const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
-                    float* Y, cudaStream_t s);
+                    float* Y, cudaStream_t s, const int2* tile_list = nullptr, const int* tile_count = nullptr);
 // depthwise layer whose input rows (gather_x) and / or skip rows (gather_res2) are rows of a table addressed
 // through the frame -> row map `src` [B*T] (launch_frame_source): X / res2 then point at the table, whose row
 // `pad_id` (the largest index) serves the zero-padded frames
 int launch_umma_dec_gathered(int B, int T, int N, const float* X, const float* dw_w, const float* dw_b,
                              const void* w_h16, const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
                              const float* res2, const float* ln2_g, const float* ln2_b, const int* src, int pad_id,
-                             int gather_x, int gather_res2, float* Y, cudaStream_t s);
+                             int gather_x, int gather_res2, float* Y, cudaStream_t s, const int2* tile_list = nullptr,
+                             const int* tile_count = nullptr);
 int umma_dec_check_errors(cudaStream_t s);
 // wide decoders (dx2 = 256): K-streamed tcgen05 kernel (es_umma_dec256.cu)
 bool umma_dec256_supported(int K, int dw_k, int N, int mode);
 int launch_umma_dec256(int mode, int B, int T, int K, int N, const float* X, const float* dw_w, const float* dw_b, const void* w_chunks,
                        const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
                        const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
-                       float* Y, cudaStream_t s);
+                       float* Y, cudaStream_t s, const int2* tile_list = nullptr, const int* tile_count = nullptr);
 void umma_dec_set_trace(long long* buf);
 int* umma_err_flag();
 

@@ -83,6 +83,8 @@ struct UmmaDecParams {
     const int* zero_from;        // [B] rows t >= zero_from[b] zeroed, or null
     const int* src;              // GX / GS kernels: frame -> table row map [B*T] (es_gather.cu); X / res2 is the table
     int pad_id;                  // GX: table row of the zero-padded frames (the largest row index)
+    const int2* tile_list;       // ragged scheduling: the (b, t0) of the tiles that can reach a valid frame, or null = all tiles
+    const int* tile_count;       //                    their number (device memory, written by tile_list_kernel)
     float* Y;                    // [B,T,N]
     int* err;                    // device error flag (mbarrier timeout)
     long long* trace;            // debug: per-role clock64 stamps of CTA 0 ([4 roles][32 tiles][8 events]) or null
@@ -263,7 +265,16 @@ umma_dec_kernel(const UmmaDecParams p) {
 
     const int N = p.N;
     const int tiles_per_utt = (p.T + TM - 1) / TM;
-    const int n_tiles = p.B * tiles_per_utt;
+    int n_tiles = p.B * tiles_per_utt;
+    // tile index -> (utterance, first frame): dense order, or the compacted list of the ragged schedule (es_gather.cu)
+    auto tile_bt = [&](int tile, int& b, int& t0) {
+        if (p.tile_list) {
+            const int2 v = __ldg(p.tile_list + tile);
+            b = v.x; t0 = v.y;
+        } else {
+            b = tile / tiles_per_utt; t0 = (tile - b * tiles_per_utt) * TM;
+        }
+    };
     const uint32_t w_plane = (uint32_t)N * CK * 2u;
 
     // ---- one-time setup ---------------------------------------------------------------------
@@ -301,12 +312,13 @@ umma_dec_kernel(const UmmaDecParams p) {
     bool failed = false;
     pdl_launch_dependents();      // the next kernel may start its prologue
     pdl_wait();                   // the previous kernel's output is complete and visible from here on
+    if (p.tile_count) n_tiles = *reinterpret_cast<const volatile int*>(p.tile_count);
 
     if (warp == 12) {
         // =========================================================================== issue warp
         // rows [t0-HALO, t0+TM+HALO) clipped to the utterance -> ring slot, one bulk copy
         auto issue_x = [&](int tile, int slot) {
-            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
+            int b, t0; tile_bt(tile, b, t0);
             const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
             const uint32_t bytes = (uint32_t)(hi - lo) * CK * 4u;
             mbar_arrive_expect_tx(bar_x + 8 * slot, bytes);
@@ -328,7 +340,7 @@ umma_dec_kernel(const UmmaDecParams p) {
         constexpr bool gx = GX;
         int sx[3] = {-1, -1, -1};
         auto load_src = [&](int tile) {
-            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
+            int b, t0; tile_bt(tile, b, t0);
             const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
             const int* sp = p.src + (size_t)b * p.T;
 #pragma unroll
@@ -338,7 +350,7 @@ umma_dec_kernel(const UmmaDecParams p) {
             }
         };
         auto issue_rows = [&](int tile, int slot) {
-            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
+            int b, t0; tile_bt(tile, b, t0);
             const int lo = max(t0 - HALO, 0), hi = min(t0 + TM + HALO, p.T);
             const int head = lo - (t0 - HALO), nfr = hi - lo;   // tile rows [head, head + nfr) are frames lo..hi-1
             const int first = __shfl_sync(0xffffffffu, sx[0], 0);
@@ -427,7 +439,7 @@ umma_dec_kernel(const UmmaDecParams p) {
 
         int i = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
-            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
+            int b, t0; tile_bt(tile, b, t0);
             const int slot = i % NSTAGE;
             float* Xs = reinterpret_cast<float*>(smem + OFF_XS + (uint32_t)slot * X_STAGE);
             const bool tr_on = (pw == 0 && lane == 0);
@@ -538,7 +550,7 @@ umma_dec_kernel(const UmmaDecParams p) {
 
         int i = g;
         for (int tile = blockIdx.x + g * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, i += 2) {
-            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM;
+            int b, t0; tile_bt(tile, b, t0);
             const int rows_valid = min(TM, p.T - t0);
             const int u = i >> 1;
             const int row0 = rbase + tr, row1 = row0 + 8;
@@ -626,7 +638,7 @@ bool umma_dec_supported(int C, int dw_k, int N) {
 int launch_umma_dec(int mode, int B, int T, int N, const float* X, const float* dw_w, const float* dw_b, const void* w_h16,
                     const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
                     const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
-                    float* Y, cudaStream_t s) {
+                    float* Y, cudaStream_t s, const int2* tile_list, const int* tile_count) {
     ES_CHECK(w_h16 && X && Y && bias, "null tensor");
     ES_CHECK(N % 16 == 0 && N >= 32 && N <= 128, "N must be a multiple of 16 in [32,128]");
     ES_CHECK(!(ln_g || res2) || N == 128, "LayerNorm epilogue needs N == 128");
@@ -642,7 +654,7 @@ int launch_umma_dec(int mode, int B, int T, int N, const float* X, const float* 
     p.B = B; p.T = T; p.N = N; p.X = X;
     p.dw_w = dw_w; p.dw_b = dw_b; p.w_h16 = w_h16; p.bias = bias; p.act_tanh = act_tanh;
     p.ln_g = ln_g; p.ln_b = ln_b; p.res2 = res2; p.ln2_g = ln2_g; p.ln2_b = ln2_b;
-    p.zero_from = zero_from; p.src = nullptr; p.pad_id = 0;
+    p.zero_from = zero_from; p.src = nullptr; p.pad_id = 0; p.tile_list = tile_list; p.tile_count = tile_count;
     p.Y = Y; p.err = g_err_flag; p.trace = (g_trace && g_trace_count++ == g_trace_pick) ? g_trace : nullptr;
     const int n_tiles = B * ((T + TM - 1) / TM);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
@@ -657,7 +669,8 @@ int launch_umma_dec(int mode, int B, int T, int N, const float* X, const float* 
 int launch_umma_dec_gathered(int B, int T, int N, const float* X, const float* dw_w, const float* dw_b,
                              const void* w_h16, const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
                              const float* res2, const float* ln2_g, const float* ln2_b, const int* src, int pad_id,
-                             int gather_x, int gather_res2, float* Y, cudaStream_t s) {
+                             int gather_x, int gather_res2, float* Y, cudaStream_t s, const int2* tile_list,
+                             const int* tile_count) {
     ES_CHECK(w_h16 && X && Y && bias && dw_w && dw_b && src, "null tensor");
     ES_CHECK(N == 128, "gathered layers are full-width (N == 128)");
     ES_CHECK(gather_x || gather_res2, "nothing to gather");
@@ -672,7 +685,7 @@ int launch_umma_dec_gathered(int B, int T, int N, const float* X, const float* d
     p.B = B; p.T = T; p.N = N; p.X = X;
     p.dw_w = dw_w; p.dw_b = dw_b; p.w_h16 = w_h16; p.bias = bias; p.act_tanh = act_tanh;
     p.ln_g = ln_g; p.ln_b = ln_b; p.res2 = res2; p.ln2_g = ln2_g; p.ln2_b = ln2_b;
-    p.zero_from = nullptr; p.src = src; p.pad_id = pad_id;
+    p.zero_from = nullptr; p.src = src; p.pad_id = pad_id; p.tile_list = tile_list; p.tile_count = tile_count;
     p.Y = Y; p.err = g_err_flag; p.trace = (g_trace && g_trace_count++ == g_trace_pick) ? g_trace : nullptr;
     const int n_tiles = B * ((T + TM - 1) / TM);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;

@@ -80,6 +80,8 @@ struct Dec256Params {
     const int* zero_from;
     float* Y;
     int* err;
+    const int2* tile_list;       // ragged scheduling (es_gather.cu): (b, t0) of the tiles that can reach a valid frame, or null
+    const int* tile_count;
 };
 
 constexpr float kTanhScale2 = 2.8853900817779268f;
@@ -144,9 +146,15 @@ umma_dec256_kernel(const Dec256Params p) {
     const int K = (MODE == MODE_DWCONV) ? 256 : p.K;
     const int nchunks = K / KC;
     const int tiles_per_utt = (p.T + TM2 - 1) / TM2;
-    const int n_tiles = p.B * tiles_per_utt;
-    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total_chunks = my_tiles * nchunks;
+    // tile index -> (utterance, first frame): dense order, or the compacted list of the ragged schedule (es_gather.cu)
+    auto tile_bt = [&](int tile, int& b, int& t0) {
+        if (p.tile_list) {
+            const int2 v = __ldg(p.tile_list + tile);
+            b = v.x; t0 = v.y;
+        } else {
+            b = tile / tiles_per_utt; t0 = (tile - b * tiles_per_utt) * TM2;
+        }
+    };
     constexpr uint32_t w_plane = (uint32_t)(KC / 8) * N * 16u;   // bytes of one fp16 plane of one chunk
     constexpr uint32_t w_chunk_bytes = 2 * w_plane;
 
@@ -184,6 +192,9 @@ umma_dec256_kernel(const Dec256Params p) {
     bool failed = false;
     pdl_launch_dependents();
     pdl_wait();
+    const int n_tiles = p.tile_count ? *reinterpret_cast<const volatile int*>(p.tile_count) : p.B * tiles_per_utt;
+    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total_chunks = my_tiles * nchunks;
 
     if (warp == 12) {
         // =========================================================================== issue warp
@@ -252,7 +263,7 @@ umma_dec256_kernel(const Dec256Params p) {
         uint32_t ld_mask = 0;                                 // bit it: row xrow + 16*it exists
         auto tile_setup = [&](int i) {
             const int tile = blockIdx.x + i * gridDim.x;
-            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM2;
+            int b, t0; tile_bt(tile, b, t0);
             {
                 const int tf = t0 - HALO + xrow;
                 ld_base = p.X + ((long long)b * p.T + tf) * K + q * 4;
@@ -353,7 +364,7 @@ umma_dec256_kernel(const Dec256Params p) {
 
         for (int i = 0; i < my_tiles; ++i) {
             const int tile = blockIdx.x + i * gridDim.x;
-            const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * TM2;
+            int b, t0; tile_bt(tile, b, t0);
             const int rows_valid = min(TM2, p.T - t0);
             const int acc = i & 1;
             const int row0 = rbase + tr, row1 = row0 + 8;
@@ -523,7 +534,7 @@ bool umma_dec256_supported(int K, int dw_k, int N, int mode) {
 int launch_umma_dec256(int mode, int B, int T, int K, int N, const float* X, const float* dw_w, const float* dw_b, const void* w_chunks,
                        const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
                        const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
-                       float* Y, cudaStream_t s) {
+                       float* Y, cudaStream_t s, const int2* tile_list, const int* tile_count) {
     ES_CHECK(w_chunks && X && Y && bias, "null tensor");
     ES_CHECK(umma_dec256_supported(K, DWK, N, mode), "shape outside the wide decoder kernel's envelope");
     ES_CHECK(!(ln_g || res2) || N == 256, "LayerNorm epilogue needs N == 256");
@@ -540,7 +551,7 @@ int launch_umma_dec256(int mode, int B, int T, int K, int N, const float* X, con
     p.B = B; p.T = T; p.K = K; p.X = X;
     p.dw_w = dw_w; p.dw_b = dw_b; p.w_chunks = w_chunks; p.bias = bias; p.act_tanh = act_tanh;
     p.ln_g = ln_g; p.ln_b = ln_b; p.res2 = res2; p.ln2_g = ln2_g; p.ln2_b = ln2_b;
-    p.zero_from = zero_from; p.Y = Y; p.err = err_flag;
+    p.zero_from = zero_from; p.Y = Y; p.err = err_flag; p.tile_list = tile_list; p.tile_count = tile_count;
     const int n_tiles = B * ((T + TM2 - 1) / TM2);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
     switch (mode) {

@@ -23,7 +23,7 @@ from . import _cabi, packing
 from .config import ESConfig, N_SYMBOLS
 
 __all__ = ["PhonemeEncoder", "MelDecoder", "Phoneme2Mel", "GraphedForward", "Encoder", "Fuse", "AcousticDecoder",
-           "FeatureUpsampler", "SelfAttention", "MixFFN"]
+           "FeatureUpsampler", "SelfAttention", "MixFFN", "mel_to_half"]
 
 
 # ------------------------------------------------------------------------------------------
@@ -154,6 +154,7 @@ class _Backend:
         # ES_DEC_GATHER_MODE (1/2) overrides the default for A/B runs of the same command line
         self.gather_mode = int(os.environ.get("ES_DEC_GATHER_MODE", _cabi.ES_GATHER_FUSED))
         self.fused_phoneme = os.environ.get("ES_FUSED_PHONEME", "1") != "0"
+        self.ragged_schedule = os.environ.get("ES_RAGGED_SCHEDULE", "1") != "0"
 
     def __del__(self):
         try:
@@ -169,7 +170,7 @@ class _Backend:
 
     def ensure(self, device: torch.device) -> C.c_void_p:
         params = list(self.owner.parameters())
-        key = (str(device), self.tensor_core, self.gather_mode, self.fused_phoneme) + \
+        key = (str(device), self.tensor_core, self.gather_mode, (self.fused_phoneme, self.ragged_schedule)) + \
             tuple((p.data_ptr(), p._version) for p in params)
         if key == self.key:
             return self.handle
@@ -261,6 +262,7 @@ class _Backend:
         _cabi.check(lib.es_model_set_tensor_core(h, 1 if self.tensor_core else 0))
         _cabi.check(lib.es_model_set_decoder_gather(h, int(self.gather_mode)))
         _cabi.check(lib.es_model_set_fused_phoneme(h, 1 if self.fused_phoneme else 0))
+        _cabi.check(lib.es_model_set_ragged_schedule(h, 1 if self.ragged_schedule else 0))
         self.handle = h
         self.key = key
         return h
@@ -274,6 +276,20 @@ class _Backend:
 
 def _stream(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def mel_to_half(mel: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Opt-in fp16 copy of a mel tensor (es_mel_to_half): halves the device -> host bytes of a consumer that pulls the
+    mel over PCIe.  Not part of the reference path -- ``Phoneme2Mel`` keeps returning fp32."""
+    _require_cuda(mel, "mel")
+    mel = mel.contiguous()
+    if mel.dtype != torch.float32:
+        raise RuntimeError("mel_to_half expects the fp32 mel")
+    if out is None:
+        out = torch.empty(mel.shape, dtype=torch.float16, device=mel.device)
+    with torch.cuda.device(mel.device):
+        _cabi.check(_cabi.load().es_mel_to_half(_stream(mel.device), mel.data_ptr(), out.data_ptr(), mel.numel()))
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -314,6 +330,11 @@ class MelDecoder(nn.Module):
     def set_tensor_core(self, enable: bool) -> None:
         """True (default): tcgen05 split-fp16 decoder layers; False: fp32 SIMT kernels."""
         self._backend.tensor_core = bool(enable)
+
+    def set_ragged_schedule(self, enable: bool) -> None:
+        """True (default): with padded frames zeroed (B > 1) the decoder only schedules tiles that can reach a valid frame
+        (include/es_b200.h: es_model_set_ragged_schedule); False: every padded frame is computed, as the reference does."""
+        self._backend.ragged_schedule = bool(enable)
 
     def set_gather_mode(self, mode: int) -> None:
         """How ``Phoneme2Mel`` joins the length regulator and this decoder (include/es_b200.h, ES_GATHER_*):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ES_ABI_VERSION 10
+#define ES_ABI_VERSION 11
 #define ES_MAX_ENC_BLOCKS 2
 #define ES_MAX_DEC_LAYERS 24
 #define ES_MAX_DEC_BLOCKS 8
@@ -157,6 +157,12 @@ int  es_model_set_tensor_core(es_model_t* m, int enable);
  * 0: one launch per layer, as for every other geometry.  Same function, same parity bars. */
 int  es_model_set_fused_phoneme(es_model_t* m, int enable);
 
+/* 1 (default): es_decoder_forward_gathered with zero_padded_frames = 1 schedules only the decoder tiles that can reach a
+ * valid frame (t0 < mel_len[b] + 2 L, L decoder layers) -- the ragged scheduling the reference's padding makes possible:
+ * it computes every padded frame and then zeroes it (networks.py:424-427).  0: every tile, as the reference does.
+ * Same results on every frame below mel_len, zeros above (tests compare the two bit for bit). */
+int  es_model_set_ragged_schedule(es_model_t* m, int enable);
+
 /* How es_decoder_forward_gathered joins the length regulator and the decoder (default ES_GATHER_FUSED):
  *   ES_GATHER_MATERIALIZE  projection per phoneme, then a row-gather kernel writes skip [B,T,dx2]
  *   ES_GATHER_FUSED        projection per phoneme; the first decoder block gathers rows of the table itself
@@ -212,6 +218,26 @@ int es_length_regulate(es_model_t* m, void* stream, int B, int N, int T,
  */
 int es_frame_rows(es_model_t* m, void* stream, int B, int N, int T,
                   const int32_t* dur_cum, const int32_t* mel_len, int32_t* rows);
+
+/*
+ * Replaces LJSpeechDataModule.collate_fn (datamodule.py:29-76) and get_mask_from_lengths (utils/tools.py:43-51) for the
+ * acoustic model's inputs -- the step BEFORE the path, on the device.  The B utterances arrive concatenated:
+ * utterance u owns elements [offsets[u], offsets[u+1]) of the *_flat arrays (offsets [B+1] int32).  Outputs, all
+ * device buffers: perm [B] (row r holds utterance perm[r]: STABLE argsort of decreasing length -- the reference's
+ * np.argsort(-len) leaves the order of equal lengths unspecified), phoneme [B,N] int32 zero-padded, phoneme_mask [B,N]
+ * (1 = padding), phoneme_len [B]; and, when the matching *_flat input is given (training batches), pitch / energy [B,N]
+ * fp32, duration [B,N] int32 and mel_len [B] = sum of durations.  N >= the longest utterance (the caller knows the
+ * lengths: it built the offsets).  B <= 12000.
+ */
+int es_collate(void* stream, int B, int N, const int32_t* offsets, const int32_t* phoneme_flat, const float* pitch_flat,
+               const float* energy_flat, const int32_t* duration_flat, int32_t* perm, int32_t* phoneme,
+               uint8_t* phoneme_mask, int32_t* phoneme_len, float* pitch, float* energy, int32_t* duration,
+               int32_t* mel_len);
+
+/* Opt-in, NOT part of the reference path: an fp16 copy (round to nearest even) of n fp32 values, for consumers that pull
+ * the mel over PCIe (the fp32 mel [B,T,80] of configs[1] is 62.9 MB per step; the e2e of bench.py is bound by that
+ * copy).  The fp32 mel remains the output of es_decoder_forward*; both buffers 16-byte aligned. */
+int es_mel_to_half(void* stream, const float* mel, void* mel_f16, size_t n);
 
 /* Replaces MelDecoder.forward (networks.py:291-304): features [B,T,4d] -> mel [B,T,n_mel]. */
 int es_decoder_forward(es_model_t* m, void* stream, int B, int T,

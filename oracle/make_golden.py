@@ -67,5 +67,31 @@ def main():
             print(path, os.path.getsize(path) // 1024, "KB  T_tf", tf["mel"].shape[1], "T_fr", fr["mel"].shape[1])
 
 
+def make_collate_fixture():
+    """tests/golden/collate_b7.npz: outputs of the reference's own collate_fn source (datamodule.py:29-76, extracted with
+    oracle.ref_shim.reference_functions -- the module itself needs lightning) on seeded ragged items of distinct lengths."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_collate_cpu as t
+    from oracle import es_oracle
+    items = t.ragged_items(123, 7)
+    for k, it in enumerate(items):
+        for key in it:
+            it[key] = np.resize(it[key], 4 + 5 * k)
+    ref = t.reference_collate(items)
+    o = es_oracle.collate(items)
+    out = {"B": 7}
+    for i, it in enumerate(items):
+        for k, v in it.items():
+            out[f"{k}_{i}"] = v
+    for k in ("phoneme", "phoneme_len", "phoneme_mask", "pitch", "energy", "duration", "mel_len"):
+        assert np.array_equal(np.asarray(ref[k]), o[k]), k
+        out["out_" + k] = np.asarray(ref[k])
+    out["out_perm"] = o["perm"]
+    path = os.path.join(ROOT, "tests", "golden", "collate_b7.npz")
+    np.savez_compressed(path, **out)
+    print(path)
+
+
 if __name__ == "__main__":
     main()
+    make_collate_fixture()

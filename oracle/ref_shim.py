@@ -68,3 +68,30 @@ def run_reference(model, batch, train):
         mel, mel_len, dur = out
         return {"mel": mel.numpy(), "mel_len": mel_len.numpy(), "duration": dur.numpy()}
     return {k: (v.numpy() if v is not None else None) for k, v in out.items()}
+
+
+def reference_functions(rel_path, names):
+    """The UNMODIFIED source of the named top-level functions / methods of a reference file, compiled into a fresh
+    namespace (numpy + torch only).  For files whose import needs packages this image lacks (datamodule.py imports
+    lightning, utils/tools.py matplotlib): their pure functions still run as written."""
+    import ast
+    import numpy as np
+    import torch
+    root = _MOUNTED if os.path.isfile(os.path.join(_MOUNTED, rel_path)) else REF_DIR
+    path = os.path.join(root, rel_path)
+    if not os.path.isfile(path):
+        raise RuntimeError(f"{rel_path} not found under the reference tree")
+    src = open(path).read()
+    tree = ast.parse(src)
+    ns = {"np": np, "torch": torch}
+    found = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in names and node.name not in found:
+            code = ast.get_source_segment(src, node)
+            import textwrap
+            exec(compile(textwrap.dedent(code), f"{rel_path}:{node.name}", "exec"), ns)
+            found[node.name] = ns[node.name]
+    missing = set(names) - set(found)
+    if missing:
+        raise RuntimeError(f"{rel_path}: no function(s) {sorted(missing)}")
+    return found, ns

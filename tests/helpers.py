@@ -16,7 +16,9 @@ TOL_PRED = 1e-4
 
 
 def golden_files():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Acoustic-path fixtures (<variant>_b<B>n<N>.npz); other rows keep their own fixtures (collate_*.npz, ...)."""
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if os.path.basename(p).split("_")[0] in VARIANTS)
 
 
 def load_golden(path):

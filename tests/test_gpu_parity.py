@@ -359,3 +359,69 @@ def test_fused_phoneme_kernel_matches_per_layer(B, N, ragged, train):
         with torch.no_grad():
             mel = model(x, train=True)["mel"] if train else model(x, train=False)[0]
         assert np.abs(npy(mel) - o["mel"]).max() <= TOL_MEL
+
+
+@pytest.mark.parametrize("B,train", [(1, True), (7, True), (64, False), (300, True), (2000, True)])
+def test_collate_on_device_exact(B, train):
+    """es_collate (datamodule.py:29-76 on the device) against the oracle: permutation (stable), padded arrays, mask,
+    lengths and mel_len bit-exact, including equal lengths and zero durations."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_collate_cpu import ragged_items
+    items = ragged_items(1000 + B, B, lo=1, hi=128 if B < 500 else 24, train=train)
+    got = es.collate(items, DEV)
+    o = es_oracle.collate(items)
+    keys = ["perm", "phoneme", "phoneme_len", "phoneme_mask"] + (["pitch", "energy", "duration", "mel_len"] if train else [])
+    assert set(k for k in got) == set(keys)
+    for k in keys:
+        g = npy(got[k])
+        assert g.dtype == o[k].dtype or k == "phoneme_mask", (k, g.dtype, o[k].dtype)
+        assert np.array_equal(g, o[k]), k
+    assert got["phoneme_mask"].dtype == torch.bool
+    if train and B > 1:
+        # the collated batch feeds the model directly
+        cfg = VARIANTS["tiny"]
+        model = cuda_model("tiny", init_state_dict(cfg, seed=3))
+        ids = torch.clamp(got["phoneme"], max=cfg.n_symbols - 1)
+        x = {"phoneme": ids[:8], "phoneme_mask": got["phoneme_mask"][:8], "pitch": got["pitch"][:8], "energy": got["energy"][:8],
+             "duration": got["duration"][:8], "mel_len": got["mel_len"][:8]}
+        if int(x["mel_len"].max()) > 0 and x["phoneme"].shape[1] >= 2:
+            with torch.no_grad():
+                out = model(x, train=True)
+            assert torch.isfinite(out["mel"]).all()
+
+
+@pytest.mark.parametrize("vname,B,N", [("tiny", 12, 128), ("small", 6, 96), ("base", 5, 64), ("tiny", 3, 20)])
+@pytest.mark.parametrize("train", [True, False])
+def test_ragged_schedule_is_bit_identical(vname, B, N, train):
+    """Ragged scheduling (the decoder walks only the tiles that can reach a valid frame, es_gather.cu: tile_list_kernel)
+    against the dense schedule the reference implies: the same bits on every frame, zeros past mel_len -- including an
+    utterance with NO frames and one that is a small fraction of the longest."""
+    cfg = VARIANTS[vname]
+    sd = dict(init_state_dict(cfg, seed=50 + N))
+    sd["encoder.duration_decoder.linear.bias"] = np.full_like(sd["encoder.duration_decoder.linear.bias"], 5.0)
+    batch = make_batch(cfg, B, N, seed=9 + B, ragged=True, fixed_duration=None, max_dur=9, min_len=4)
+    batch["duration"][-1] = 0                                       # an utterance without frames
+    batch["duration"][-2, 6:] = 0                                   # a very short one
+    batch["mel_len"] = batch["duration"].sum(1).astype(np.int32)
+    model = cuda_model(vname, sd)
+    x = to_dev(batch)
+    got = {}
+    try:
+        for on in (True, False):
+            model.decoder.set_ragged_schedule(on)
+            with torch.no_grad():
+                out = model(x, train=True) if train else model(x, train=False)
+            mel, mel_len = (out["mel"], out["mel_len"]) if train else (out[0], out[1])
+            got[on] = (npy(mel), npy(mel_len))
+            model.check_async_errors()
+    finally:
+        model.decoder.set_ragged_schedule(True)
+    assert np.array_equal(got[True][1], got[False][1])
+    assert np.array_equal(got[True][0], got[False][0])
+    ml = got[True][1]
+    for b in range(B):
+        assert (got[True][0][b, ml[b]:] == 0).all()
+    if train:
+        o = es_oracle.phoneme2mel(batch, sd, train=True)
+        assert np.abs(got[True][0] - o["mel"]).max() <= TOL_MEL
