@@ -543,18 +543,17 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
     // (B*N rows), expand through the frame -> row map (es_gather.cu).  networks.py:228-258, :292
     const int R = B * N;
     { ProfRange r(ES_K_DEC_PROJ, s); if (project_rows(m, R, fused4, db.P, s)) return 1; }
-    { ProfRange r(ES_K_LENREG, s);
-      if (launch_frame_source(dur_cum, mel_len, db.src, B, N, T, m->w.dproj_b, m->w.dproj_ln_g, m->w.dproj_ln_b,
-                              m->dx2, db.P + (size_t)R * m->dx2, s)) return 1; }
     // Ragged schedule: with padded frames zeroed at the end (networks.py:424-427, B > 1) a tile that starts at or beyond
     // mel_len[b] + 2 L cannot reach a frame anyone reads (a layer looks 2 frames each way): the tcgen05 layer kernels
-    // walk the compacted list of the other tiles, and the frames nobody computed are zero-filled in the mel.
-    const bool ragged = zero_padded_frames && m->ragged_schedule && (decoder_all_umma128(m) || decoder_all_umma256(m));
+    // walk the compacted list of the other tiles, and the frames nobody computes are zero-filled in the mel -- both by
+    // the index-map kernel, no extra launch.
+    const bool ragged = zero_padded_frames && m->ragged_schedule && m->cfg.n_mel % 4 == 0 &&
+                        (decoder_all_umma128(m) || decoder_all_umma256(m));
     const int tile_frames = m->dx2 == 128 ? 64 : 128, halo = (m->cfg.decoder_kernel_size / 2) * m->n_layers;
-    if (ragged) {
-        ProfRange r(ES_K_LENREG, s);
-        if (launch_tile_list(mel_len, B, T, tile_frames, halo, db.tiles, db.tile_count, s)) return 1;
-    }
+    { ProfRange r(ES_K_LENREG, s);
+      if (launch_frame_source(dur_cum, mel_len, db.src, B, N, T, m->w.dproj_b, m->w.dproj_ln_g, m->w.dproj_ln_b,
+                              m->dx2, db.P + (size_t)R * m->dx2, s, ragged ? db.tiles : nullptr, db.tile_count,
+                              tile_frames, halo, mel, m->cfg.n_mel)) return 1; }
     int rc;
     if (m->gather_mode == ES_GATHER_FUSED && decoder_all_umma128(m)) {
         // the first block reads its input and skip rows straight from the table: [B,T,dx2] is never materialised
@@ -563,12 +562,7 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
         { ProfRange r(ES_K_LENREG, s); if (launch_gather_rows(db.P, db.src, db.buf[0], (long long)B * T, m->dx2, s)) return 1; }
         rc = decoder_layers(m, B, T, db, 0, zero_padded_frames ? mel_len : nullptr, mel, s, ragged);
     }
-    if (rc) return 1;
-    if (ragged) {
-        ProfRange r(ES_K_LENREG, s);
-        if (launch_zero_tail(mel, mel_len, B, T, m->cfg.n_mel, tile_frames, halo, s)) return 1;
-    }
-    return 0;
+    return rc;
 }
 
 }  // extern "C"

@@ -25,11 +25,30 @@ namespace {
 constexpr int FS_THREADS = 256;
 constexpr int FS_MAX_SMEM_N = 8192;      // prefix sums staged in shared memory up to this many phonemes
 
+// ---- ragged scheduling -------------------------------------------------------------------------------------------------
+// A decoder layer is a 5-tap convolution along time: through L layers a frame depends on frames within 2 L of it.  The
+// reference runs the decoder over every padded frame and then zeroes the frames past mel_len (networks.py:424-427), so
+// tiles that start at or beyond mel_len[b] + halo (halo = 2 L) cannot reach a frame anyone reads.  frame_source_kernel
+// therefore also (a) lists the other tiles -- utterance by utterance, so consecutive CTAs of the decoder kernels still
+// stream consecutive memory -- for those kernels to walk instead of the dense B x ceil(T / TM) grid (CTA (0,0): one
+// block-wide scan per 256 utterances), and (b) zero-fills the mel frames no listed tile covers.  No extra launch.
+struct RaggedPlan {
+    int2* tiles;          // out: (b, t0) per scheduled tile, or null (ragged scheduling off)
+    int* count;           // out: number of scheduled tiles
+    int TM, halo;         // tile size in frames; reach of the decoder in frames (2 per layer)
+    float* mel;           // frames past the scheduled tiles are zero-filled here ...
+    int n_mel;            // ... n_mel (% 4 == 0) floats per frame
+};
+__device__ __forceinline__ int tiles_of(int valid, int T, int TM, int halo) {
+    const int ext = min(T, valid + halo);
+    return valid > 0 ? (ext + TM - 1) / TM : 0;                 // an utterance without frames needs no tile at all
+}
+
 __global__ void __launch_bounds__(FS_THREADS)
 frame_source_kernel(const int32_t* __restrict__ cum, const int32_t* __restrict__ valid_len,
                     int32_t* __restrict__ src, int B, int N, int T,
                     const float* __restrict__ bias, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                    int C, float* __restrict__ pad_row) {
+                    int C, float* __restrict__ pad_row, const RaggedPlan rp) {
     extern __shared__ int scum[];
     const int b = blockIdx.y, t = blockIdx.x * FS_THREADS + threadIdx.x;
     const int32_t* c = cum + (size_t)b * N;
@@ -50,6 +69,10 @@ frame_source_kernel(const int32_t* __restrict__ cum, const int32_t* __restrict__
             if (lo < N) s = b * N + lo;
         }
         src[(size_t)b * T + t] = s;
+        if (rp.tiles && t >= tiles_of(__ldg(valid_len + b), T, rp.TM, rp.halo) * rp.TM) {
+            float4* y = reinterpret_cast<float4*>(rp.mel + ((size_t)b * T + t) * rp.n_mel);
+            for (int k = 0; k < rp.n_mel / 4; ++k) y[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     // pad row = LN(tanh(0 * W + bias)): one warp, two-pass statistics
     if (pad_row && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 32) {
@@ -77,6 +100,34 @@ frame_source_kernel(const int32_t* __restrict__ cum, const int32_t* __restrict__
             if (ch < C) pad_row[ch] = (v[k] - mean) * rstd * __ldg(ln_g + ch) + __ldg(ln_b + ch);
         }
     }
+    // the tile list: exclusive scan of the per-utterance tile counts, 256 utterances per round
+    if (rp.tiles && blockIdx.x == 0 && blockIdx.y == 0) {
+        __shared__ int warp_sums[FS_THREADS / 32];
+        __shared__ int base;
+        if (threadIdx.x == 0) base = 0;
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int b0 = 0; b0 < B; b0 += FS_THREADS) {
+            const int u = b0 + threadIdx.x;
+            const int n = u < B ? tiles_of(__ldg(valid_len + u), T, rp.TM, rp.halo) : 0;
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) warp_sums[warp] = incl;
+            __syncthreads();
+            int before = base;
+            for (int w = 0; w < warp; ++w) before += warp_sums[w];
+            const int start = before + incl - n;
+            for (int k = 0; k < n; ++k) rp.tiles[start + k] = make_int2(u, k * rp.TM);
+            __syncthreads();
+            if (threadIdx.x == FS_THREADS - 1) base = before + incl;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) *rp.count = base;
+    }
 }
 
 // 8 rows per 256-thread CTA step, grid-stride; every lane moves 16 bytes per step
@@ -95,14 +146,17 @@ gather_rows_kernel(const float* __restrict__ P, const int32_t* __restrict__ src,
 
 int launch_frame_source(const int32_t* cum, const int32_t* valid_len, int32_t* src, int B, int N, int T,
                         const float* bias, const float* ln_g, const float* ln_b, int C, float* pad_row,
-                        cudaStream_t s) {
+                        cudaStream_t s, int2* tiles, int* tile_count, int tile_frames, int halo, float* mel, int n_mel) {
     ES_CHECK(cum && valid_len && src, "null tensor");
     ES_CHECK(B >= 1 && B <= 65535 && N >= 1 && T >= 1, "bad shape");
     ES_CHECK((long long)B * N < 0x7fffffffLL, "B * N overflows the row index");
     ES_CHECK(!pad_row || (bias && ln_g && ln_b && C >= 32 && C <= 256), "pad row needs bias / LayerNorm over <= 256 channels");
+    ES_CHECK(!tiles || (tile_count && mel && tile_frames >= 1 && halo >= 0 && n_mel % 4 == 0), "bad ragged plan");
     const dim3 grid((unsigned)((T + FS_THREADS - 1) / FS_THREADS), (unsigned)B);
     const size_t smem = N <= FS_MAX_SMEM_N ? (size_t)N * sizeof(int) : 0;
-    frame_source_kernel<<<grid, FS_THREADS, smem, s>>>(cum, valid_len, src, B, N, T, bias, ln_g, ln_b, C, pad_row);
+    RaggedPlan rp;
+    rp.tiles = tiles; rp.count = tile_count; rp.TM = tile_frames; rp.halo = halo; rp.mel = mel; rp.n_mel = n_mel;
+    frame_source_kernel<<<grid, FS_THREADS, smem, s>>>(cum, valid_len, src, B, N, T, bias, ln_g, ln_b, C, pad_row, rp);
     ES_LAUNCH_OK();
     return 0;
 }
@@ -113,84 +167,6 @@ int launch_gather_rows(const float* P, const int32_t* src, float* Y, long long r
     long long blocks = (rows + 7) / 8;
     if (blocks > 148LL * 32) blocks = 148LL * 32;
     gather_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(P, src, Y, rows, C / 4);
-    ES_LAUNCH_OK();
-    return 0;
-}
-
-// ---- ragged scheduling -------------------------------------------------------------------------------------------------
-// A decoder layer is a 5-tap convolution along time: through L layers a frame depends on frames within 2 L of it.  The
-// reference runs the decoder over every padded frame and then zeroes the frames past mel_len (networks.py:424-427), so
-// tiles that start at or beyond mel_len[b] + halo (halo = 2 L) cannot reach a frame anyone reads.  tile_list_kernel
-// lists the others -- utterance by utterance, so consecutive CTAs still stream consecutive memory -- and the decoder
-// kernels walk that list instead of the dense B x ceil(T / TM) grid; zero_tail_kernel writes the zeros of the mel
-// frames no listed tile covers.
-namespace {
-constexpr int TL_THREADS = 1024;
-__device__ __forceinline__ int tiles_of(int valid, int T, int TM, int halo) {
-    const int ext = min(T, valid + halo);
-    return valid > 0 ? (ext + TM - 1) / TM : 0;                 // an utterance without frames needs no tile at all
-}
-__global__ void __launch_bounds__(TL_THREADS)
-tile_list_kernel(const int32_t* __restrict__ valid_len, int B, int T, int TM, int halo, int2* __restrict__ tiles,
-                 int* __restrict__ count) {
-    __shared__ int warp_sums[32];
-    __shared__ int base;
-    if (threadIdx.x == 0) base = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int b0 = 0; b0 < B; b0 += TL_THREADS) {
-        const int b = b0 + threadIdx.x;
-        const int n = b < B ? tiles_of(__ldg(valid_len + b), T, TM, halo) : 0;
-        int incl = n;                                              // block-wide inclusive scan: shuffles, then warp sums
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int w = warp_sums[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += v;
-            }
-            warp_sums[lane] = w;
-        }
-        __syncthreads();
-        const int start = base + (warp ? warp_sums[warp - 1] : 0) + incl - n;
-        for (int k = 0; k < n; ++k) tiles[start + k] = make_int2(b, k * TM);
-        __syncthreads();
-        if (threadIdx.x == 0) base += warp_sums[31];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *count = base;
-}
-
-__global__ void __launch_bounds__(256)
-zero_tail_kernel(float* __restrict__ Y, const int32_t* __restrict__ valid_len, int T, int C, int TM, int halo) {
-    const int b = blockIdx.y;
-    const int first = tiles_of(__ldg(valid_len + b), T, TM, halo) * TM;       // frames [first, T) are not covered
-    const long long n4 = (long long)(T - first) * C / 4;                      // C % 4 == 0
-    float4* y = reinterpret_cast<float4*>(Y + ((size_t)b * T + first) * C);
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256)
-        y[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-}  // namespace
-
-int launch_tile_list(const int32_t* valid_len, int B, int T, int TM, int halo, int2* tiles, int* count, cudaStream_t s) {
-    ES_CHECK(valid_len && tiles && count && B >= 1 && T >= 1 && TM >= 1 && halo >= 0, "bad arguments");
-    tile_list_kernel<<<1, TL_THREADS, 0, s>>>(valid_len, B, T, TM, halo, tiles, count);
-    ES_LAUNCH_OK();
-    return 0;
-}
-
-int launch_zero_tail(float* Y, const int32_t* valid_len, int B, int T, int C, int TM, int halo, cudaStream_t s) {
-    ES_CHECK(Y && valid_len && C % 4 == 0, "bad arguments");
-    const int per_utt = (int)(((long long)T * C / 4 + 255) / 256);
-    dim3 grid(per_utt < 64 ? (per_utt > 0 ? per_utt : 1) : 64, B);
-    zero_tail_kernel<<<grid, 256, 0, s>>>(Y, valid_len, T, C, TM, halo);
     ES_LAUNCH_OK();
     return 0;
 }

@@ -23,16 +23,15 @@ int launch_length_regulate(const float* fused4, const int32_t* cum, const uint8_
 // length regulator as an index map + row gather (es_gather.cu)
 int launch_frame_source(const int32_t* cum, const int32_t* valid_len, int32_t* src, int B, int N, int T,
                         const float* bias, const float* ln_g, const float* ln_b, int C, float* pad_row,
-                        cudaStream_t s);
+                        cudaStream_t s, int2* tiles = nullptr, int* tile_count = nullptr, int tile_frames = 0, int halo = 0,
+                        float* mel = nullptr, int n_mel = 0);
 // batch collation on the device (es_collate.cu)
 int launch_collate(int B, int N, const int32_t* offsets, const int32_t* ph_flat, const float* pitch_flat,
                    const float* energy_flat, const int32_t* dur_flat, int32_t* perm, int32_t* phoneme, uint8_t* mask,
                    int32_t* phoneme_len, float* pitch, float* energy, int32_t* duration, int32_t* mel_len, cudaStream_t s);
 int launch_cast_f32_f16(const float* src, void* dst, size_t n, cudaStream_t s);
-// ragged scheduling: the tiles of TM frames that can reach a valid frame (t0 < min(T, valid_len[b] + halo)), compacted, and
-// the zero fill of the mel frames no listed tile covers
-int launch_tile_list(const int32_t* valid_len, int B, int T, int TM, int halo, int2* tiles, int* count, cudaStream_t s);
-int launch_zero_tail(float* Y, const int32_t* valid_len, int B, int T, int C, int TM, int halo, cudaStream_t s);
+// (ragged scheduling: with `tiles` given, launch_frame_source also lists the tiles of tile_frames frames that can reach a
+// valid frame -- t0 < min(T, valid_len[b] + halo) -- and zero-fills the mel frames no listed tile covers)
 int launch_gather_rows(const float* P, const int32_t* src, float* Y, long long rows, int C, cudaStream_t s);
 
 // tcgen05 decoder kernel (es_umma_dec.cu)

@@ -65,7 +65,9 @@ constexpr uint32_t OFF_DW = OFF_PAR + 5 * 128 * 4;            // depthwise taps 
 constexpr int MAP_LD = 72;                                    // row-map stride per ring slot (68 tile rows)
 constexpr uint32_t OFF_MAP = OFF_DW + 6 * 128 * 4;            // gathered x tiles: tile row -> staged row, per ring slot
 constexpr uint32_t OFF_BAR = OFF_MAP + NSTAGE * MAP_LD * 4;   // 12 mbarriers + tmem base
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;
+constexpr int TL_CACHE = 64;                                  // ragged schedule: this CTA's first 64 tile coordinates, staged once
+constexpr uint32_t OFF_TL = OFF_BAR + 128;
+constexpr uint32_t SMEM_BYTES = OFF_TL + TL_CACHE * 8;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 enum { MODE_DWCONV = 0, MODE_PLAIN = 2 };
@@ -267,9 +269,14 @@ umma_dec_kernel(const UmmaDecParams p) {
     const int tiles_per_utt = (p.T + TM - 1) / TM;
     int n_tiles = p.B * tiles_per_utt;
     // tile index -> (utterance, first frame): dense order, or the compacted list of the ragged schedule (es_gather.cu)
+    const int2* s_tiles = reinterpret_cast<const int2*>(smem + OFF_TL);
+    bool use_list = false;        // set after the dependency wait: a list that holds EVERY tile is the dense order itself
     auto tile_bt = [&](int tile, int& b, int& t0) {
-        if (p.tile_list) {
-            const int2 v = __ldg(p.tile_list + tile);
+        if (use_list) {
+            // (a dependent global load per tile and role costs more than skipping the tiles saves: the CTA's own
+            // entries are staged in shared memory right after the dependency wait)
+            const int k = (tile - (int)blockIdx.x) / (int)gridDim.x;
+            const int2 v = k < TL_CACHE ? s_tiles[k] : __ldg(p.tile_list + tile);
             b = v.x; t0 = v.y;
         } else {
             b = tile / tiles_per_utt; t0 = (tile - b * tiles_per_utt) * TM;
@@ -312,7 +319,15 @@ umma_dec_kernel(const UmmaDecParams p) {
     bool failed = false;
     pdl_launch_dependents();      // the next kernel may start its prologue
     pdl_wait();                   // the previous kernel's output is complete and visible from here on
-    if (p.tile_count) n_tiles = *reinterpret_cast<const volatile int*>(p.tile_count);
+    if (p.tile_count) {
+        n_tiles = *reinterpret_cast<const volatile int*>(p.tile_count);
+        use_list = n_tiles != p.B * tiles_per_utt;
+        if (use_list && tid < TL_CACHE) {
+            const int tile = blockIdx.x + tid * gridDim.x;
+            if (tile < n_tiles) reinterpret_cast<int2*>(smem + OFF_TL)[tid] = __ldg(p.tile_list + tile);
+        }
+        __syncthreads();
+    }
 
     if (warp == 12) {
         // =========================================================================== issue warp

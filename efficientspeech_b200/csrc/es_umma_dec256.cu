@@ -61,7 +61,9 @@ constexpr uint32_t OFF_DW = OFF_PAR + 5 * NMAX * 4;         // depthwise taps + 
 constexpr uint32_t OFF_SRC = OFF_DW + 6 * NMAX * 4;         // gather sources, 2 x 128 ints
 constexpr uint32_t OFF_CUM = OFF_SRC + 2 * TM2 * 4;         // duration prefix sums of the utterance (<= 1024)
 constexpr uint32_t OFF_BAR = OFF_CUM + 1024 * 4;
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;
+constexpr int TL_CACHE = 64;                                // ragged schedule: this CTA's first 64 tile coordinates
+constexpr uint32_t OFF_TL = OFF_BAR + 128;
+constexpr uint32_t SMEM_BYTES = OFF_TL + TL_CACHE * 8;
 static_assert(OFF_W % 128 == 0 && OFF_A % 128 == 0, "operand alignment");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -147,9 +149,12 @@ umma_dec256_kernel(const Dec256Params p) {
     const int nchunks = K / KC;
     const int tiles_per_utt = (p.T + TM2 - 1) / TM2;
     // tile index -> (utterance, first frame): dense order, or the compacted list of the ragged schedule (es_gather.cu)
+    const int2* s_tiles = reinterpret_cast<const int2*>(smem + OFF_TL);
+    bool use_list = false;        // set after the dependency wait: a list that holds EVERY tile is the dense order itself
     auto tile_bt = [&](int tile, int& b, int& t0) {
-        if (p.tile_list) {
-            const int2 v = __ldg(p.tile_list + tile);
+        if (use_list) {
+            const int k = (tile - (int)blockIdx.x) / (int)gridDim.x;      // staged in shared memory after the dependency wait
+            const int2 v = k < TL_CACHE ? s_tiles[k] : __ldg(p.tile_list + tile);
             b = v.x; t0 = v.y;
         } else {
             b = tile / tiles_per_utt; t0 = (tile - b * tiles_per_utt) * TM2;
@@ -193,6 +198,14 @@ umma_dec256_kernel(const Dec256Params p) {
     pdl_launch_dependents();
     pdl_wait();
     const int n_tiles = p.tile_count ? *reinterpret_cast<const volatile int*>(p.tile_count) : p.B * tiles_per_utt;
+    if (p.tile_count) {
+        use_list = n_tiles != p.B * tiles_per_utt;
+        if (use_list && tid < TL_CACHE) {
+            const int tile = blockIdx.x + tid * gridDim.x;
+            if (tile < n_tiles) reinterpret_cast<int2*>(smem + OFF_TL)[tid] = __ldg(p.tile_list + tile);
+        }
+        __syncthreads();
+    }
     const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int total_chunks = my_tiles * nchunks;
 
