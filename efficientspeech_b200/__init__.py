@@ -12,6 +12,7 @@ from .modules import (AcousticDecoder, Encoder, FeatureUpsampler, Fuse, MelDecod
                       Phoneme2Mel, PhonemeEncoder, SelfAttention, mel_to_half)
 
 from .collate import collate, collate_flat  # noqa: F401
+from . import hifigan  # noqa: F401  (drop-in for the reference's hifigan package)
 
 __version__ = "0.2.0"
 

@@ -54,6 +54,29 @@ class es_weights_t(C.Structure):
     ]
 
 
+ES_HG_MAX_UPS = 6
+ES_HG_MAX_RES = 4
+
+
+class es_hifigan_config_t(C.Structure):
+    _fields_ = [("n_mel", C.c_int32), ("initial_channel", C.c_int32), ("n_up", C.c_int32),
+                ("up_rate", C.c_int32 * ES_HG_MAX_UPS), ("up_kernel", C.c_int32 * ES_HG_MAX_UPS), ("n_res", C.c_int32),
+                ("res_kernel", C.c_int32 * ES_HG_MAX_RES), ("res_dilation", (C.c_int32 * 3) * ES_HG_MAX_RES)]
+
+
+class es_hg_conv_w_t(C.Structure):
+    _fields_ = [("w", _fp), ("b", _fp)]
+
+
+class es_hg_resblock_w_t(C.Structure):
+    _fields_ = [("convs1", es_hg_conv_w_t * 3), ("convs2", es_hg_conv_w_t * 3)]
+
+
+class es_hifigan_weights_t(C.Structure):
+    _fields_ = [("conv_pre", es_hg_conv_w_t), ("ups", es_hg_conv_w_t * ES_HG_MAX_UPS),
+                ("res", (es_hg_resblock_w_t * ES_HG_MAX_RES) * ES_HG_MAX_UPS), ("conv_post", es_hg_conv_w_t)]
+
+
 # name -> (restype, argtypes); exactly the functions include/es_b200.h declares
 _i, _sz, _vp = C.c_int, C.c_size_t, C.c_void_p
 PROTOTYPES = {
@@ -81,6 +104,10 @@ PROTOTYPES = {
     "es_profile_begin": (_i, [_i]),
     "es_profile_end": (_i, []),
     "es_profile_collect": (_i, [_vp, _vp, _i, C.POINTER(_i)]),
+    "es_hifigan_create": (_i, [C.POINTER(es_hifigan_config_t), C.POINTER(es_hifigan_weights_t), C.POINTER(_vp)]),
+    "es_hifigan_destroy": (None, [_vp]),
+    "es_hifigan_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "es_hifigan_forward": (_i, [_vp, _vp, _i, _i, _vp, C.c_longlong, C.c_longlong, C.c_longlong, _vp, _vp, _sz]),
     "es_selftest_umma_gemm": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
 }
 

@@ -305,6 +305,47 @@ int es_profile_collect(int32_t* kinds_host, float* ms_host, int capacity, int* n
  * operands (3 MMAs), M multiple of 128, N in {128,256}, K multiple of 64.  fp32 in/out. */
 int es_selftest_umma_gemm(void* stream, int M, int N, int K, const float* A, const float* Bm, float* C);
 
+/* =====================================================================================================================
+ * HiFi-GAN generator -- the step AFTER the acoustic path.
+ * Replaces hifigan.Generator.forward (hifigan/models.py:111-127; ResBlock1 :18-57) as called at model.py:161-162:
+ *     wav = self.hifigan(mel.transpose(1, 2)).squeeze(1)
+ * Weights are the plain conv weights after remove_weight_norm() (model.py:44), fp32, device, reference layouts:
+ * Conv1d [Cout][Cin][K], ConvTranspose1d [Cin][Cout][K].  Only the ResBlock1 family ("resblock": "1", LJ_V2 and LJ_V1).
+ */
+#define ES_HG_MAX_UPS 6
+#define ES_HG_MAX_RES 4
+
+typedef struct es_hifigan_config {
+    int32_t n_mel;                                   /* 80 */
+    int32_t initial_channel;                         /* upsample_initial_channel (128 for V2) */
+    int32_t n_up;                                    /* len(upsample_rates) */
+    int32_t up_rate[ES_HG_MAX_UPS];                  /* [8, 8, 2, 2] */
+    int32_t up_kernel[ES_HG_MAX_UPS];                /* [16, 16, 4, 4] */
+    int32_t n_res;                                   /* len(resblock_kernel_sizes) */
+    int32_t res_kernel[ES_HG_MAX_RES];               /* [3, 7, 11] */
+    int32_t res_dilation[ES_HG_MAX_RES][3];          /* [[1, 3, 5]] * 3 */
+} es_hifigan_config_t;
+
+typedef struct es_hg_conv_w { const float* w; const float* b; } es_hg_conv_w_t;
+typedef struct es_hg_resblock_w { es_hg_conv_w_t convs1[3]; es_hg_conv_w_t convs2[3]; } es_hg_resblock_w_t;
+typedef struct es_hifigan_weights {
+    es_hg_conv_w_t conv_pre;                                         /* [C0][n_mel][7] */
+    es_hg_conv_w_t ups[ES_HG_MAX_UPS];                               /* [C_i][C_i / 2][k_i] */
+    es_hg_resblock_w_t res[ES_HG_MAX_UPS][ES_HG_MAX_RES];            /* resblocks[i * n_res + j] */
+    es_hg_conv_w_t conv_post;                                        /* [1][C_last][7] */
+} es_hifigan_weights_t;
+
+typedef struct es_hifigan es_hifigan_t;
+
+int    es_hifigan_create(const es_hifigan_config_t* cfg, const es_hifigan_weights_t* w, es_hifigan_t** out);
+void   es_hifigan_destroy(es_hifigan_t* h);
+size_t es_hifigan_workspace_bytes(const es_hifigan_t* h, int B, int T);
+/* mel: element (b, c, t) at mel[b * mel_sb + c * mel_sc + t * mel_st] -- [B,80,T] as the reference passes it
+ * (sb = 80 T, sc = T, st = 1) or the acoustic model's own [B,T,80] (sb = 80 T, sc = 1, st = 80), so the transpose of
+ * model.py:160 never materialises.  wav [B, T * prod(up_rate)] fp32 in (-1, 1). */
+int    es_hifigan_forward(es_hifigan_t* h, void* stream, int B, int T, const float* mel, long long mel_sb, long long mel_sc,
+                          long long mel_st, float* wav, void* workspace, size_t workspace_bytes);
+
 #ifdef __cplusplus
 }
 #endif

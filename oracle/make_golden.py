@@ -92,6 +92,68 @@ def make_collate_fixture():
     print(path)
 
 
+HIFIGAN_V2 = {"resblock": "1", "upsample_rates": [8, 8, 2, 2], "upsample_kernel_sizes": [16, 16, 4, 4],
+              "upsample_initial_channel": 128, "resblock_kernel_sizes": [3, 7, 11],
+              "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]]}
+
+
+def hifigan_seeded_state(cfg, seed):
+    """Plain (weight-norm removed) generator weights from a numpy seed: N(0, 1/sqrt(fan_in)) weights, small biases."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def conv(name, shape, fan_in):
+        sd[name + ".weight"] = (rng.standard_normal(shape) / np.sqrt(fan_in)).astype(np.float32)
+        sd[name + ".bias"] = (0.1 * rng.standard_normal(shape[1] if name.startswith("ups") else shape[0])).astype(np.float32)
+
+    c0 = cfg["upsample_initial_channel"]
+    conv("conv_pre", (c0, 80, 7), 80 * 7)
+    ch = c0
+    for i, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
+        conv(f"ups.{i}", (ch, ch // 2, k), ch * k // u)
+        ch //= 2
+        for j, rk in enumerate(cfg["resblock_kernel_sizes"]):
+            for d in range(3):
+                conv(f"resblocks.{i * len(cfg['resblock_kernel_sizes']) + j}.convs1.{d}", (ch, ch, rk), ch * rk)
+                conv(f"resblocks.{i * len(cfg['resblock_kernel_sizes']) + j}.convs2.{d}", (ch, ch, rk), ch * rk)
+    conv("conv_post", (1, ch, 7), ch * 7)
+    return sd
+
+
+def make_hifigan_fixture():
+    """tests/golden/hifigan_v2_t6.npz: output of the reference's hifigan.Generator (hifigan/models.py:84-127, V2 geometry)
+    for a seeded mel, once with seeded plain weights (self-contained fixture) and once with the checkpoint of the tree
+    (hifigan/LJ_V2/generator_v2; the test needs oracle/_ref for that half)."""
+    import warnings
+    import torch
+    from oracle import hifigan_oracle as ho
+    from oracle import ref_shim
+    warnings.filterwarnings("ignore")
+    sys.path.insert(0, ref_shim.REF_DIR)
+    import hifigan as ref_hg
+    rng = np.random.default_rng(5)
+    mel = (rng.standard_normal((2, 80, 6)) * 1.5 - 4).astype(np.float32)
+    out = {"mel": mel, "weight_seed": 11}
+    g = ref_hg.Generator(ref_hg.AttrDict(HIFIGAN_V2)).eval()
+    g.remove_weight_norm()
+    sd = hifigan_seeded_state(HIFIGAN_V2, 11)
+    g.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    with torch.no_grad():
+        out["wav_seeded"] = g(torch.from_numpy(mel)).numpy()
+    cfg, ck = ho.load_reference_checkpoint(ref_shim.REF_DIR)
+    g2 = ref_hg.Generator(ref_hg.AttrDict(cfg)).eval()
+    g2.load_state_dict({k: torch.from_numpy(v) for k, v in ck.items()}, strict=True)
+    g2.remove_weight_norm()
+    with torch.no_grad():
+        out["wav_checkpoint"] = g2(torch.from_numpy(mel)).numpy()
+    assert np.abs(ho.generator(mel, sd, HIFIGAN_V2) - out["wav_seeded"]).max() < 2e-5
+    assert np.abs(ho.generator(mel, ck, cfg) - out["wav_checkpoint"]).max() < 2e-5
+    path = os.path.join(ROOT, "tests", "golden", "hifigan_v2_t6.npz")
+    np.savez_compressed(path, **out)
+    print(path)
+
+
 if __name__ == "__main__":
     main()
     make_collate_fixture()
+    make_hifigan_fixture()

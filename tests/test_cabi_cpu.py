@@ -32,10 +32,13 @@ def _struct_fields(name):
 def test_ctypes_structs_match_header():
     for name, cls in [("es_config", _cabi.es_config_t), ("es_enc_block_w", _cabi.es_enc_block_w_t),
                       ("es_predictor_w", _cabi.es_predictor_w_t), ("es_dec_layer_w", _cabi.es_dec_layer_w_t),
-                      ("es_weights", _cabi.es_weights_t)]:
+                      ("es_weights", _cabi.es_weights_t), ("es_hifigan_config", _cabi.es_hifigan_config_t),
+                      ("es_hg_conv_w", _cabi.es_hg_conv_w_t), ("es_hg_resblock_w", _cabi.es_hg_resblock_w_t),
+                      ("es_hifigan_weights", _cabi.es_hifigan_weights_t)]:
         assert _struct_fields(name) == [f[0] for f in cls._fields_], name
     for macro, val in [("ES_ABI_VERSION", _cabi.ES_ABI_VERSION), ("ES_MAX_DEC_LAYERS", _cabi.ES_MAX_DEC_LAYERS),
-                       ("ES_MAX_DEC_BLOCKS", _cabi.ES_MAX_DEC_BLOCKS), ("ES_MAX_ENC_BLOCKS", _cabi.ES_MAX_ENC_BLOCKS)]:
+                       ("ES_MAX_DEC_BLOCKS", _cabi.ES_MAX_DEC_BLOCKS), ("ES_MAX_ENC_BLOCKS", _cabi.ES_MAX_ENC_BLOCKS),
+                       ("ES_HG_MAX_UPS", _cabi.ES_HG_MAX_UPS), ("ES_HG_MAX_RES", _cabi.ES_HG_MAX_RES)]:
         assert int(re.search(r"#define %s (\d+)" % macro, HEADER).group(1)) == val
 
 
