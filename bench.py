@@ -688,6 +688,44 @@ def measure_b1_latency(ctx, a, variant, N, duration, warm=10, timed=100):
     return rec
 
 
+def measure_hifigan(ctx, B, T, steps):
+    """The step after the path: HiFi-GAN V2 generator, mel [B,80,T] -> waveform, seeded weights."""
+    import importlib.util
+    torch = ctx.torch
+    import efficientspeech_b200 as es
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "oracle", "make_golden.py"))
+    cfgd = {"resblock": "1", "upsample_rates": [8, 8, 2, 2], "upsample_kernel_sizes": [16, 16, 4, 4],
+            "upsample_initial_channel": 128, "resblock_kernel_sizes": [3, 7, 11],
+            "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]]}
+    torch.manual_seed(1234)
+    G = es.hifigan.Generator(es.hifigan.AttrDict(cfgd)).eval()
+    G.remove_weight_norm()
+    G = G.to(ctx.dev)
+    mel = (torch.randn(B, 80, T, device=ctx.dev) * 1.5 - 4.0)
+    with torch.no_grad():
+        for _ in range(2):
+            wav = G(mel)
+        ms = ctx.timed(lambda: G(mel), steps)
+    # MACs per output-rate sample: resblocks C^2 * (3+7+11) * 6 per stage, transposed convs Cin*Cout*k/u, conv_pre / post
+    macs, C, L = 80 * 128 * 7 * T, 128, T
+    for u, k in zip(cfgd["upsample_rates"], cfgd["upsample_kernel_sizes"]):
+        L *= u
+        macs += C * (C // 2) * (k // u) * L
+        C //= 2
+        macs += C * C * (3 + 7 + 11) * 6 * L
+    macs += C * 7 * L
+    flops = 2.0 * macs * B * ctx.world
+    sec = ms * 1e-3 / steps
+    fp32_peak = 148 * 128 * 2 * 1.965e9
+    return {"value": B * ctx.world * wav.shape[-1] / sec, "unit": "samples/s", "ms_per_step": ms / steps, "batch_per_gpu": B,
+            "mel_frames_per_utt": T, "audio_rtf": B * ctx.world * wav.shape[-1] / SR / sec,
+            "gflop_per_utt": 2.0 * macs / 1e9, "achieved_tflops": flops / sec / 1e12,
+            "roofline": {"bound": "fp32 FMA (SIMT kernels)", "achieved": flops / sec / 1e12, "peak": fp32_peak / 1e12,
+                         "unit": "TFLOP/s", "frac": flops / sec / fp32_peak,
+                         "peak_source": "nominal 148 SMs x 128 FMA lanes x 1.965 GHz (no measured fp32 figure in MEASURED_PEAKS.json)"},
+            "workload": f"HiFi-GAN V2 generator (hifigan/models.py:84-127), B={B} utterances of {T} mel frames, fp32, seeded weights"}
+
+
 def run_b200_arm(a):
     ctx = Ctx(a)
     torch, world, rank = ctx.torch, ctx.world, ctx.rank
@@ -725,6 +763,8 @@ def run_b200_arm(a):
             torch.cuda.empty_cache()
         sub["tiny_b1_latency"] = measure_b1_latency(ctx, a, "tiny", a.phonemes, a.duration)
         sub["tiny_free_running_ragged"] = measure_free_running(ctx, a, "tiny", 256, a.phonemes, a.duration, max(5, a.steps // 2))
+        torch.cuda.empty_cache()
+        sub["hifigan_v2_b16"] = measure_hifigan(ctx, 16, a.phonemes * a.duration, 3)
 
     if rank != 0:
         if world > 1:

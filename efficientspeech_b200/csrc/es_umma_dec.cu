@@ -321,12 +321,14 @@ umma_dec_kernel(const UmmaDecParams p) {
     pdl_wait();                   // the previous kernel's output is complete and visible from here on
     if (p.tile_count) {
         n_tiles = *reinterpret_cast<const volatile int*>(p.tile_count);
-        use_list = n_tiles != p.B * tiles_per_utt;
-        if (use_list && tid < TL_CACHE) {
-            const int tile = blockIdx.x + tid * gridDim.x;
-            if (tile < n_tiles) reinterpret_cast<int2*>(smem + OFF_TL)[tid] = __ldg(p.tile_list + tile);
+        use_list = n_tiles != p.B * tiles_per_utt;           // CTA-uniform
+        if (use_list) {
+            if (tid < TL_CACHE) {
+                const int tile = blockIdx.x + tid * gridDim.x;
+                if (tile < n_tiles) reinterpret_cast<int2*>(smem + OFF_TL)[tid] = __ldg(p.tile_list + tile);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     if (warp == 12) {

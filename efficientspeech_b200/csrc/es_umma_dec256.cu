@@ -199,12 +199,14 @@ umma_dec256_kernel(const Dec256Params p) {
     pdl_wait();
     const int n_tiles = p.tile_count ? *reinterpret_cast<const volatile int*>(p.tile_count) : p.B * tiles_per_utt;
     if (p.tile_count) {
-        use_list = n_tiles != p.B * tiles_per_utt;
-        if (use_list && tid < TL_CACHE) {
-            const int tile = blockIdx.x + tid * gridDim.x;
-            if (tile < n_tiles) reinterpret_cast<int2*>(smem + OFF_TL)[tid] = __ldg(p.tile_list + tile);
+        use_list = n_tiles != p.B * tiles_per_utt;           // CTA-uniform
+        if (use_list) {
+            if (tid < TL_CACHE) {
+                const int tile = blockIdx.x + tid * gridDim.x;
+                if (tile < n_tiles) reinterpret_cast<int2*>(smem + OFF_TL)[tid] = __ldg(p.tile_list + tile);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int total_chunks = my_tiles * nchunks;
