@@ -108,6 +108,9 @@ PROTOTYPES = {
     "es_hifigan_destroy": (None, [_vp]),
     "es_hifigan_workspace_bytes": (_sz, [_vp, _i, _i]),
     "es_hifigan_forward": (_i, [_vp, _vp, _i, _i, _vp, C.c_longlong, C.c_longlong, C.c_longlong, _vp, _vp, _sz]),
+    "es_loss_workspace_bytes": (_sz, []),
+    "es_loss": (_i, [_vp, _i, _i, _i, _i] + [_vp] * 15 + [_vp, _sz]),
+    "es_adamw_step": (_i, [_vp, _sz, _vp, _vp, _vp, _vp] + [C.c_float] * 7),
     "es_selftest_umma_gemm": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
 }
 

@@ -346,6 +346,25 @@ size_t es_hifigan_workspace_bytes(const es_hifigan_t* h, int B, int T);
 int    es_hifigan_forward(es_hifigan_t* h, void* stream, int B, int T, const float* mel, long long mel_sb, long long mel_sc,
                           long long mel_st, float* wav, void* workspace, size_t workspace_bytes);
 
+/* =====================================================================================================================
+ * Training-step pieces around the network.  The network's backward is not built; these are
+ * the parts of EfficientSpeech.training_step that do not depend on it.
+ */
+/* Replaces EfficientSpeech.loss + the weighted total of training_step (model.py:167-217).  Predictions as the forward
+ * returns them (mel [B,T,n_mel], pitch / energy / duration [B,N]); targets mel [B,T,n_mel], pitch / energy [B,N] fp32,
+ * duration [B,N] int32; valid frames t < mel_len[b], valid phonemes phoneme_mask == 0 (null: all).  losses[5] (device) =
+ * total (10 mel + 2 pitch + 2 energy + duration), mel L1, pitch MSE, energy MSE, log-duration MSE.  d_* (each optional):
+ * gradient of the TOTAL with respect to the matching prediction.  Deterministic (fixed-order reductions). */
+size_t es_loss_workspace_bytes(void);
+int    es_loss(void* stream, int B, int N, int T, int n_mel, const float* mel_pred, const float* mel_tgt, const int32_t* mel_len,
+               const float* pitch_pred, const float* energy_pred, const float* dur_pred, const float* pitch, const float* energy,
+               const int32_t* duration, const uint8_t* phoneme_mask, float* losses, float* d_mel, float* d_pitch,
+               float* d_energy, float* d_dur, void* workspace, size_t workspace_bytes);
+/* Replaces one torch.optim.AdamW.step (model.py:279-283) over flat fp32 buffers of n elements.  The caller passes what
+ * torch computes on the host in double: step_size = lr / (1 - beta1^t), bias_correction2_sqrt = sqrt(1 - beta2^t). */
+int    es_adamw_step(void* stream, size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, float step_size, float bias_correction2_sqrt);
+
 #ifdef __cplusplus
 }
 #endif

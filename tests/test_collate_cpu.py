@@ -35,7 +35,8 @@ def reference_collate(items):
     return {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in bx.items()}
 
 
-@pytest.mark.skipif(not os.path.isfile("/root/reference/datamodule.py"), reason="reference tree not mounted")
+@pytest.mark.skipif(not (os.path.isfile(os.path.join(ref_shim._MOUNTED, "datamodule.py")) or
+                         os.path.isfile(os.path.join(ref_shim.REF_DIR, "datamodule.py"))), reason="reference sources not available")
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_oracle_collate_matches_reference_source(seed):
     items = ragged_items(seed, 9)

@@ -44,6 +44,25 @@ def test_weight_broadcast_gloo_world2():
     assert out[1][1]                     # versions bumped -> packed image rebuilt on next forward
 
 
+def _allreduce_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from efficientspeech_b200.training import allreduce_flat
+    g = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    allreduce_flat(g)                                      # the ONE collective of the training step: flat gradient, averaged
+    out[rank] = g.tolist()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo_world2():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_allreduce_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    want = (torch.arange(10, dtype=torch.float32) * 1.5).tolist()
+    assert out[0] == want and out[1] == want
+
+
 def test_shards_partition_the_batch():
     cfg = es.VARIANTS["tiny"]
     batch = make_batch(cfg, 13, 16, seed=0, ragged=True, fixed_duration=None)
