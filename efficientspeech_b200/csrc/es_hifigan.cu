@@ -22,9 +22,15 @@
 #include <new>
 
 #include "es_common.cuh"
+#include "es_umma.cuh"      // packed fp32x2 arithmetic (fma.rn.f32x2): two FMAs per issue slot
 
 namespace es {
 namespace {
+
+using umma::f32x2;
+using umma::fma2;
+using umma::pk2;
+using umma::up2;
 
 constexpr int HG_THREADS = 256;
 constexpr int PT = 4;            // consecutive samples per thread
@@ -49,65 +55,99 @@ struct ConvParams {
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
-// Conv1d, stride 1, zero padding.  grid (ceil(Lout / TL), B); thread (tx, ty): samples t0 + 4 tx .. +3, channels 8 ty .. +7
+// Conv1d, stride 1, zero padding.  grid (ceil(Lout / TL), B); thread (tx, ty): samples t0 + 4 tx .. +3, channels 8 ty .. +7.
+// KT: compile-time kernel size (3 / 7 / 11: the resblock kernels, taps fully unrolled) or 0 = run-time p.K;
+// DIL1: dilation 1 -- the 4 samples x K taps of a thread read K + 3 consecutive staged samples ONCE per input channel
+// (a register window) instead of 4 K.
+template <int KT, bool DIL1>
 __global__ void __launch_bounds__(HG_THREADS)
 hg_conv_kernel(const ConvParams p) {
     extern __shared__ __align__(16) float hsm[];
+    const int K = KT ? KT : p.K;
+    const int dil = DIL1 ? 1 : p.dil;
     const int n_cg = (p.Cout + CO - 1) / CO;
     const int TX = HG_THREADS / n_cg, TL = TX * PT;
-    const int span = (p.K - 1) * p.dil;
-    const int in_w = TL + span;                               // staged samples per input channel
-    float* xs = hsm;                                          // [CI_CHUNK][in_w]
-    float* ws = hsm + CI_CHUNK * ((in_w + 3) & ~3);           // [CI_CHUNK][K][n_cg * CO]
-    const int ldw = n_cg * CO;
+    const int in_w = TL + (K - 1) * dil;                      // staged samples per input channel
     const int in_ld = (in_w + 3) & ~3;
+    const int ldw = n_cg * CO;                                // 8 .. 128: a power of two, divides 256
+    float* xs = hsm;                                          // [CI_CHUNK][in_ld]
+    float* ws = hsm + CI_CHUNK * in_ld;                       // [CI_CHUNK][K][ldw]
     const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
     const int b = blockIdx.y, t0 = blockIdx.x * TL;
     const float* xb = p.x + (long long)b * p.sb;
+    const int wco = tid & (ldw - 1), wr0 = tid / ldw, wstep = HG_THREADS / ldw;   // weight staging: column, first row, row step
 
-    float acc[PT][CO];
+    // accumulators as packed channel pairs: acc2[i][c2] = (sample i, channels 2 c2 and 2 c2 + 1); one FFMA2 = two FMAs
+    f32x2 acc2[PT][CO / 2];
 #pragma unroll
     for (int i = 0; i < PT; ++i)
 #pragma unroll
-        for (int c = 0; c < CO; ++c) acc[i][c] = 0.f;
+        for (int c = 0; c < CO / 2; ++c) acc2[i][c] = 0ull;
 
     for (int c0 = 0; c0 < p.Cin; c0 += CI_CHUNK) {
-        // stage 8 input channels (leaky ReLU applied here, zeros outside the signal) and their weights
-        for (int idx = tid; idx < CI_CHUNK * in_w; idx += HG_THREADS) {
-            const int ci = idx / in_w, s = idx - ci * in_w;
-            const int t = t0 - p.pad + s;
-            float v = 0.f;
-            if (t >= 0 && t < p.Lin) v = lrelu(__ldg(xb + (long long)(c0 + ci) * p.sc + (long long)t * p.st), p.slope_in);
-            xs[ci * in_ld + s] = v;
+        // stage 8 input channels (leaky ReLU applied here, zeros outside the signal) and their weights [ci][tap][co]
+#pragma unroll 1
+        for (int ci = 0; ci < CI_CHUNK; ++ci) {
+            const float* xc = xb + (long long)(c0 + ci) * p.sc;
+            for (int s = tid; s < in_w; s += HG_THREADS) {
+                const int t = t0 - p.pad + s;
+                float v = 0.f;
+                if (t >= 0 && t < p.Lin) v = lrelu(__ldg(xc + (long long)t * p.st), p.slope_in);
+                xs[ci * in_ld + s] = v;
+            }
         }
-        for (int idx = tid; idx < CI_CHUNK * p.K * ldw; idx += HG_THREADS) {
-            const int co = idx % ldw, j = (idx / ldw) % p.K, ci = idx / (ldw * p.K);
-            ws[idx] = co < p.Cout ? __ldg(p.w + ((long long)co * p.Cin + c0 + ci) * p.K + j) : 0.f;
+        for (int r = wr0; r < CI_CHUNK * K; r += wstep) {
+            const int ci = r / K, j = r - ci * K;
+            ws[r * ldw + wco] = wco < p.Cout ? __ldg(p.w + ((long long)wco * p.Cin + c0 + ci) * K + j) : 0.f;
         }
         __syncthreads();
-        if (ty < n_cg) {
 #pragma unroll 1
-            for (int ci = 0; ci < CI_CHUNK; ++ci) {
-                const float* xr = xs + ci * in_ld + tx * PT;
-                const float* wr = ws + ci * p.K * ldw + ty * CO;
-#pragma unroll 1
-                for (int j = 0; j < p.K; ++j) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(wr + j * ldw);
-                    const float4 w1 = *reinterpret_cast<const float4*>(wr + j * ldw + 4);
-                    const float wv[CO] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                    float xv[PT];
+        for (int ci = 0; ci < CI_CHUNK; ++ci) {
+            const float* xr = xs + ci * in_ld + tx * PT;
+            const float* wr = ws + ci * K * ldw + ty * CO;
+            if (DIL1 && KT) {
+                f32x2 win[PT + (KT ? KT : 1) - 1];                     // (x, x): the sample broadcast over a channel pair
 #pragma unroll
-                    for (int i = 0; i < PT; ++i) xv[i] = xr[i + j * p.dil];
+                for (int k = 0; k < PT + KT - 1; ++k) { const float v = xr[k]; win[k] = pk2(v, v); }
+#pragma unroll
+                for (int j = 0; j < KT; ++j) {
+                    const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(wr + j * ldw);
+                    const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(wr + j * ldw + 4);
+                    const f32x2 wv[CO / 2] = {w0.x, w0.y, w1.x, w1.y};
 #pragma unroll
                     for (int i = 0; i < PT; ++i)
 #pragma unroll
-                        for (int c = 0; c < CO; ++c) acc[i][c] = fmaf(xv[i], wv[c], acc[i][c]);
+                        for (int c = 0; c < CO / 2; ++c) acc2[i][c] = fma2(win[i + j], wv[c], acc2[i][c]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < (KT ? KT : 1); ++j) {
+                    for (int jj = (KT ? j : 0); jj < (KT ? j + 1 : K); ++jj) {
+                        const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(wr + jj * ldw);
+                        const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(wr + jj * ldw + 4);
+                        const f32x2 wv[CO / 2] = {w0.x, w0.y, w1.x, w1.y};
+                        f32x2 xv[PT];
+#pragma unroll
+                        for (int i = 0; i < PT; ++i) { const float v = xr[i + jj * dil]; xv[i] = pk2(v, v); }
+#pragma unroll
+                        for (int i = 0; i < PT; ++i)
+#pragma unroll
+                            for (int c = 0; c < CO / 2; ++c) acc2[i][c] = fma2(xv[i], wv[c], acc2[i][c]);
+                    }
                 }
             }
         }
         __syncthreads();
     }
-    if (ty >= n_cg) return;
+    float acc[PT][CO];
+#pragma unroll
+    for (int i = 0; i < PT; ++i)
+#pragma unroll
+        for (int c = 0; c < CO / 2; ++c) {
+            const float2 v = up2(acc2[i][c]);
+            acc[i][2 * c] = v.x;
+            acc[i][2 * c + 1] = v.y;
+        }
     const int t = t0 + tx * PT;
 #pragma unroll
     for (int c = 0; c < CO; ++c) {
@@ -115,115 +155,155 @@ hg_conv_kernel(const ConvParams p) {
         if (co >= p.Cout_store) continue;
         const float bv = __ldg(p.bias + co);
         const long long o = ((long long)b * p.Cout_store + co) * p.Lout + t;
+        if (t + PT <= p.Lout && (o & 3) == 0) {
+            float4 v = make_float4(acc[0][c] + bv, acc[1][c] + bv, acc[2][c] + bv, acc[3][c] + bv);
+            if (p.res) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(p.res + o));
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
+            v.x *= p.out_scale; v.y *= p.out_scale; v.z *= p.out_scale; v.w *= p.out_scale;
+            if (p.tanh_out) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+            if (p.accumulate) {
+                const float4 y = *reinterpret_cast<const float4*>(p.y + o);
+                v.x += y.x; v.y += y.y; v.z += y.z; v.w += y.w;
+            }
+            *reinterpret_cast<float4*>(p.y + o) = v;
+        } else {
 #pragma unroll
-        for (int i = 0; i < PT; ++i) {
-            if (t + i >= p.Lout) break;
-            float v = acc[i][c] + bv;
-            if (p.res) v += __ldg(p.res + o + i);
-            v *= p.out_scale;
-            if (p.tanh_out) v = tanhf(v);
-            if (p.accumulate) v += p.y[o + i];
-            p.y[o + i] = v;
+            for (int i = 0; i < PT; ++i) {
+                if (t + i >= p.Lout) break;
+                float v = acc[i][c] + bv;
+                if (p.res) v += __ldg(p.res + o + i);
+                v *= p.out_scale;
+                if (p.tanh_out) v = tanhf(v);
+                if (p.accumulate) v += p.y[o + i];
+                p.y[o + i] = v;
+            }
         }
     }
 }
 
 // ConvTranspose1d in gather form: y[co, t] = b[co] + sum_ci sum_{j = (t + pad) mod u, += u, < K} lrelu(x[ci, (t + pad - j) / u]) w[ci, co, j]
-// thread (tx, ty): ONE output sample t0 + tx, channels 8 ty .. +7
+// thread (tx, ty): the u consecutive output samples t0 + u tx + r (r < u <= 8: one per tap PHASE), channels 8 ty .. +7.
+// All lanes of a warp then use the same taps at the same time (weights are broadcast loads, input samples consecutive
+// words) -- with one sample per lane the 8 phases of a warp read 8 different weight rows: an 8-way bank conflict per load.
+constexpr int UP_MAX = 8;
 __global__ void __launch_bounds__(HG_THREADS)
 hg_upsample_kernel(const ConvParams p) {
     extern __shared__ __align__(16) float hsm[];
     const int n_cg = (p.Cout + CO - 1) / CO;
     const int TX = HG_THREADS / n_cg;
-    const int u = p.stride;
-    const int in_w = TX / u + (p.K + u - 1) / u + 2;
+    const int u = p.stride, TP = TX * u;
+    // input offsets a tap can reach: off = (r + pad - j) / u (exact), r < u, j < K
+    const int off_lo = -((p.K - 1 - p.pad + u - 1) / u), off_hi = (u - 1 + p.pad) / u;
+    const int in_w = TX + off_hi - off_lo;
     const int in_ld = (in_w + 3) & ~3;
     const int ldw = n_cg * CO;
     float* xs = hsm;                                          // [CI_CHUNK][in_ld]
     float* ws = hsm + CI_CHUNK * in_ld;                       // [CI_CHUNK][K][ldw]
     const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
-    const int b = blockIdx.y, t0 = blockIdx.x * TX;
-    // first input sample any output of this tile can touch: s = (t + pad - j) / u >= (t0 + pad - (K - 1)) / u (floor)
-    const int s_lo_num = t0 + p.pad - (p.K - 1);
-    const int s_base = s_lo_num >= 0 ? s_lo_num / u : -((-s_lo_num + u - 1) / u);
+    const int b = blockIdx.y, t0 = blockIdx.x * TP;           // t0 is a multiple of u
+    const int s_base = t0 / u + off_lo;                       // input sample staged at index 0
     const float* xb = p.x + (long long)b * p.sb;
+    const int wco = tid & (ldw - 1), wr0 = tid / ldw, wstep = HG_THREADS / ldw;
 
-    float acc[CO];
+    float acc[UP_MAX][CO];
 #pragma unroll
-    for (int c = 0; c < CO; ++c) acc[c] = 0.f;
-    const int t = t0 + tx;
-    const int ph = (t + p.pad) % u;                           // tap phase of this output sample
+    for (int r = 0; r < UP_MAX; ++r)
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[r][c] = 0.f;
 
     for (int c0 = 0; c0 < p.Cin; c0 += CI_CHUNK) {
-        for (int idx = tid; idx < CI_CHUNK * in_w; idx += HG_THREADS) {
-            const int ci = idx / in_w, k = idx - ci * in_w;
-            const int s = s_base + k;
-            float v = 0.f;
-            if (s >= 0 && s < p.Lin) v = lrelu(__ldg(xb + (long long)(c0 + ci) * p.sc + (long long)s * p.st), p.slope_in);
-            xs[ci * in_ld + k] = v;
+#pragma unroll 1
+        for (int ci = 0; ci < CI_CHUNK; ++ci) {
+            const float* xc = xb + (long long)(c0 + ci) * p.sc;
+            for (int k = tid; k < in_w; k += HG_THREADS) {
+                const int sidx = s_base + k;
+                float v = 0.f;
+                if (sidx >= 0 && sidx < p.Lin) v = lrelu(__ldg(xc + (long long)sidx * p.st), p.slope_in);
+                xs[ci * in_ld + k] = v;
+            }
         }
-        for (int idx = tid; idx < CI_CHUNK * p.K * ldw; idx += HG_THREADS) {
-            const int co = idx % ldw, j = (idx / ldw) % p.K, ci = idx / (ldw * p.K);
-            ws[idx] = co < p.Cout ? __ldg(p.w + ((long long)(c0 + ci) * p.Cout + co) * p.K + j) : 0.f;
+        for (int r = wr0; r < CI_CHUNK * p.K; r += wstep) {
+            const int ci = r / p.K, j = r - ci * p.K;
+            ws[r * ldw + wco] = wco < p.Cout ? __ldg(p.w + ((long long)(c0 + ci) * p.Cout + wco) * p.K + j) : 0.f;
         }
         __syncthreads();
-        if (ty < n_cg && t < p.Lout) {
-            for (int j = ph; j < p.K; j += u) {
-                const int s = (t + p.pad - j) / u - s_base;   // exact division (phase), >= 0 by construction of s_base
-                if (s < 0 || s >= in_w) continue;
 #pragma unroll 1
-                for (int ci = 0; ci < CI_CHUNK; ++ci) {
-                    const float xv = xs[ci * in_ld + s];
-                    const float* wr = ws + (ci * p.K + j) * ldw + ty * CO;
-                    const float4 w0 = *reinterpret_cast<const float4*>(wr);
-                    const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
-                    acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
-                    acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-                    acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
-                    acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+        for (int ci = 0; ci < CI_CHUNK; ++ci) {
+            const float* xr = xs + ci * in_ld + tx - off_lo;
+            const float* wr = ws + ci * p.K * ldw + ty * CO;
+#pragma unroll
+            for (int r = 0; r < UP_MAX; ++r) {
+                if (r < u) {
+                    for (int j = (r + p.pad) % u; j < p.K; j += u) {          // warp-uniform
+                        const float xv = xr[(r + p.pad - j) / u];              // exact division; staged zeros outside the signal
+                        const float4 w0 = *reinterpret_cast<const float4*>(wr + j * ldw);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wr + j * ldw + 4);
+                        acc[r][0] = fmaf(xv, w0.x, acc[r][0]); acc[r][1] = fmaf(xv, w0.y, acc[r][1]);
+                        acc[r][2] = fmaf(xv, w0.z, acc[r][2]); acc[r][3] = fmaf(xv, w0.w, acc[r][3]);
+                        acc[r][4] = fmaf(xv, w1.x, acc[r][4]); acc[r][5] = fmaf(xv, w1.y, acc[r][5]);
+                        acc[r][6] = fmaf(xv, w1.z, acc[r][6]); acc[r][7] = fmaf(xv, w1.w, acc[r][7]);
+                    }
                 }
             }
         }
         __syncthreads();
     }
-    if (ty >= n_cg || t >= p.Lout) return;
 #pragma unroll
     for (int c = 0; c < CO; ++c) {
         const int co = ty * CO + c;
-        if (co < p.Cout_store) p.y[((long long)b * p.Cout_store + co) * p.Lout + t] = acc[c] + __ldg(p.bias + co);
+        if (co >= p.Cout_store) continue;
+        const float bv = __ldg(p.bias + co);
+        float* yr = p.y + ((long long)b * p.Cout_store + co) * p.Lout + t0 + u * tx;
+#pragma unroll
+        for (int r = 0; r < UP_MAX; ++r)
+            if (r < u && t0 + u * tx + r < p.Lout) yr[r] = acc[r][c] + bv;
     }
 }
 
 int n_groups(int cout) { return (cout + CO - 1) / CO; }
 
+template <int KT, bool DIL1>
+int launch_conv_t(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+    static PerDeviceSlot<bool> attr_once;
+    bool& attr_set = attr_once.get();
+    if (!attr_set) {
+        ES_CUDA(cudaFuncSetAttribute(hg_conv_kernel<KT, DIL1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+    }
+    hg_conv_kernel<KT, DIL1><<<grid, HG_THREADS, smem, s>>>(p);
+    ES_LAUNCH_OK();
+    return 0;
+}
+
 int launch_conv(const ConvParams& p, int B, cudaStream_t s) {
     const int n_cg = n_groups(p.Cout);
-    ES_CHECK(n_cg >= 1 && n_cg <= 32 && HG_THREADS % n_cg == 0, "output channels must split into 1..32 groups of 8 that divide 256");
+    ES_CHECK(n_cg >= 1 && n_cg <= 16 && (n_cg & (n_cg - 1)) == 0, "output channels must split into 1, 2, 4, 8 or 16 groups of 8");
     ES_CHECK(p.Cin % CI_CHUNK == 0, "input channels must be a multiple of 8");
     ES_CHECK(p.K >= 1 && p.K <= HG_MAX_K && (p.K & 1), "odd kernel size up to 15");
     const int TX = HG_THREADS / n_cg, TL = TX * PT;
     const int in_ld = (TL + (p.K - 1) * p.dil + 3) & ~3;
     const size_t smem = ((size_t)CI_CHUNK * in_ld + (size_t)CI_CHUNK * p.K * n_cg * CO) * sizeof(float);
     ES_CHECK(smem <= 160 * 1024, "tile does not fit shared memory");
-    static PerDeviceSlot<bool> attr_once;
-    bool& attr_set = attr_once.get();
-    if (!attr_set) {
-        ES_CUDA(cudaFuncSetAttribute(hg_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_set = true;
-    }
     dim3 grid((unsigned)((p.Lout + TL - 1) / TL), (unsigned)B);
-    hg_conv_kernel<<<grid, HG_THREADS, smem, s>>>(p);
-    ES_LAUNCH_OK();
-    return 0;
+    const bool d1 = p.dil == 1;
+    switch (p.K) {
+        case 3: return d1 ? launch_conv_t<3, true>(p, grid, smem, s) : launch_conv_t<3, false>(p, grid, smem, s);
+        case 7: return d1 ? launch_conv_t<7, true>(p, grid, smem, s) : launch_conv_t<7, false>(p, grid, smem, s);
+        case 11: return d1 ? launch_conv_t<11, true>(p, grid, smem, s) : launch_conv_t<11, false>(p, grid, smem, s);
+        default: return launch_conv_t<0, false>(p, grid, smem, s);
+    }
 }
 
 int launch_upsample(const ConvParams& p, int B, cudaStream_t s) {
     const int n_cg = n_groups(p.Cout);
-    ES_CHECK(n_cg >= 1 && n_cg <= 32 && HG_THREADS % n_cg == 0, "output channels must split into 1..32 groups of 8 that divide 256");
+    ES_CHECK(n_cg >= 1 && n_cg <= 16 && (n_cg & (n_cg - 1)) == 0, "output channels must split into 1, 2, 4, 8 or 16 groups of 8");
     ES_CHECK(p.Cin % CI_CHUNK == 0, "input channels must be a multiple of 8");
     ES_CHECK(p.K >= 1 && p.K <= HG_MAX_K && p.stride >= 1, "transposed kernel size up to 16");
-    const int TX = HG_THREADS / n_cg;
-    const int in_ld = (TX / p.stride + (p.K + p.stride - 1) / p.stride + 2 + 3) & ~3;
+    ES_CHECK(p.stride <= UP_MAX && p.pad >= 0 && p.pad < p.K, "upsampling rate up to 8");
+    const int TX = HG_THREADS / n_cg, TP = TX * p.stride;
+    const int in_ld = (TX + (p.stride - 1 + p.pad) / p.stride + (p.K - 1 - p.pad + p.stride - 1) / p.stride + 3) & ~3;
     const size_t smem = ((size_t)CI_CHUNK * in_ld + (size_t)CI_CHUNK * p.K * n_cg * CO) * sizeof(float);
     ES_CHECK(smem <= 160 * 1024, "tile does not fit shared memory");
     static PerDeviceSlot<bool> attr_once;
@@ -232,7 +312,7 @@ int launch_upsample(const ConvParams& p, int B, cudaStream_t s) {
         ES_CUDA(cudaFuncSetAttribute(hg_upsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_set = true;
     }
-    dim3 grid((unsigned)((p.Lout + TX - 1) / TX), (unsigned)B);
+    dim3 grid((unsigned)((p.Lout + TP - 1) / TP), (unsigned)B);
     hg_upsample_kernel<<<grid, HG_THREADS, smem, s>>>(p);
     ES_LAUNCH_OK();
     return 0;
@@ -254,7 +334,7 @@ int es_hifigan_create(const es_hifigan_config_t* cfg, const es_hifigan_weights_t
     ES_CHECK(cfg && w && out, "null argument");
     ES_CHECK(cfg->n_mel >= 8 && cfg->n_mel % 8 == 0, "n_mel must be a multiple of 8");
     ES_CHECK(cfg->n_up >= 1 && cfg->n_up <= ES_HG_MAX_UPS && cfg->n_res >= 1 && cfg->n_res <= ES_HG_MAX_RES, "bad stage counts");
-    ES_CHECK(cfg->initial_channel % (8 << cfg->n_up) == 0 && cfg->initial_channel <= 256, "initial channel count must stay a multiple of 8 through every halving");
+    ES_CHECK(cfg->initial_channel % (8 << cfg->n_up) == 0 && cfg->initial_channel <= 128, "initial channel count must stay a multiple of 8 through every halving");
     int up = 1;
     for (int i = 0; i < cfg->n_up; ++i) {
         ES_CHECK(cfg->up_rate[i] >= 1 && cfg->up_kernel[i] >= cfg->up_rate[i] && cfg->up_kernel[i] <= 16 &&
