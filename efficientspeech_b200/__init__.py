@@ -14,6 +14,8 @@ from .modules import (AcousticDecoder, Encoder, FeatureUpsampler, Fuse, MelDecod
 from .collate import collate, collate_flat  # noqa: F401
 from . import hifigan  # noqa: F401  (drop-in for the reference's hifigan package)
 from . import training  # noqa: F401
+from . import text  # noqa: F401
+from .pipeline import synthesize  # noqa: F401
 
 __version__ = "0.2.0"
 

@@ -76,3 +76,39 @@ def test_checkpoint_through_get_hifigan_flow_and_transposed_mel():
     assert np.abs(before - want).max() <= TOL_WAV
     assert np.abs(after - want).max() <= TOL_WAV
     assert np.abs(after).max() < 1.0
+
+
+def test_text_to_waveform_pipeline_matches_the_chained_oracles():
+    """es.synthesize: text -> ids -> device collation -> Phoneme2Mel (free running) -> HiFi-GAN, against the numpy oracles
+    chained on the host (es_oracle.collate / phoneme2mel, hifigan_oracle.generator).  Rows come back in the caller's order."""
+    import tempfile
+    from efficientspeech_b200 import text as T
+    from efficientspeech_b200.config import VARIANTS
+    from efficientspeech_b200.params import init_state_dict
+    from oracle import es_oracle
+    mg = _mg()
+    cfg = VARIANTS["tiny"]
+    sd = dict(init_state_dict(cfg, seed=2))
+    sd["encoder.duration_decoder.linear.bias"] = np.full_like(sd["encoder.duration_decoder.linear.bias"], 3.0)
+    model = es.build_model("tiny")
+    es.load_numpy_state(model, sd)
+    model = model.to(DEV).eval()
+    hsd = mg.hifigan_seeded_state(mg.HIFIGAN_V2, 21)
+    G = plain_generator(mg.HIFIGAN_V2, hsd)
+    lex_txt = "hello HH AH0 L OW1\\nworld W ER1 L D\\nthe DH AH0\\nquick K W IH1 K\\nbrown B R AW1 N\\nfox F AA1 K S\\n"
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        f.write(lex_txt)
+    lex = T.read_lexicon(f.name)
+    pc = {"preprocessing": {"text": {"language": "en", "text_cleaners": ["english_cleaners"]}}}
+    texts = ["hello world", "the quick, brown fox - hello world!", "fox"]
+    out = es.synthesize(texts, lex, None, model, G, pc, DEV)
+    # host-side chain
+    items = [{"phoneme": T.text2phoneme(lex, None, t, pc)} for t in texts]
+    ob = es_oracle.collate(items)
+    o = es_oracle.phoneme2mel({"phoneme": ob["phoneme"], "phoneme_mask": ob["phoneme_mask"]}, sd, train=False)
+    wav = ho.generator(np.ascontiguousarray(o["mel"].transpose(0, 2, 1)), hsd, mg.HIFIGAN_V2)[:, 0]
+    inv = np.argsort(ob["perm"])
+    assert np.array_equal(out["mel_len"].cpu().numpy(), o["mel_len"][inv])
+    assert np.array_equal(out["wav_len"].cpu().numpy(), o["mel_len"][inv] * 256)
+    assert np.abs(out["mel"].cpu().numpy() - o["mel"][inv]).max() <= 1e-3
+    assert np.abs(out["wav"].cpu().numpy() - wav[inv]).max() <= 5e-4
