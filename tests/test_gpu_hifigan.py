@@ -95,7 +95,7 @@ def test_text_to_waveform_pipeline_matches_the_chained_oracles():
     model = model.to(DEV).eval()
     hsd = mg.hifigan_seeded_state(mg.HIFIGAN_V2, 21)
     G = plain_generator(mg.HIFIGAN_V2, hsd)
-    lex_txt = "hello HH AH0 L OW1\\nworld W ER1 L D\\nthe DH AH0\\nquick K W IH1 K\\nbrown B R AW1 N\\nfox F AA1 K S\\n"
+    lex_txt = "hello HH AH0 L OW1\nworld W ER1 L D\nthe DH AH0\nquick K W IH1 K\nbrown B R AW1 N\nfox F AA1 K S\n"
     with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
         f.write(lex_txt)
     lex = T.read_lexicon(f.name)
