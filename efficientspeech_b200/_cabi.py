@@ -8,7 +8,7 @@ from typing import Optional
 
 from . import build as _build
 
-ES_ABI_VERSION = 11
+ES_ABI_VERSION = 12
 ES_GATHER_MATERIALIZE, ES_GATHER_FUSED = 1, 2
 ES_MAX_ENC_BLOCKS = 2
 ES_MAX_DEC_LAYERS = 24
@@ -78,7 +78,7 @@ class es_hifigan_weights_t(C.Structure):
 
 
 # name -> (restype, argtypes); exactly the functions include/es_b200.h declares
-_i, _sz, _vp = C.c_int, C.c_size_t, C.c_void_p
+_i, _sz, _vp, _ll = C.c_int, C.c_size_t, C.c_void_p, C.c_longlong
 PROTOTYPES = {
     "es_abi_version": (_i, []),
     "es_last_error": (C.c_char_p, []),
@@ -111,6 +111,29 @@ PROTOTYPES = {
     "es_loss_workspace_bytes": (_sz, []),
     "es_loss": (_i, [_vp, _i, _i, _i, _i] + [_vp] * 15 + [_vp, _sz]),
     "es_adamw_step": (_i, [_vp, _sz, _vp, _vp, _vp, _vp] + [C.c_float] * 7),
+    "es_t_gemm": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _ll, _i, _vp, _i, _ll, _i, _vp, _i, _ll, _vp, _i, _i]),
+    "es_t_im2col": (_i, [_vp, _vp, _vp] + [_i] * 7),
+    "es_t_col2im": (_i, [_vp, _vp, _vp] + [_i] * 8),
+    "es_t_dwconv_fwd": (_i, [_vp] * 5 + [_i] * 4),
+    "es_t_dwconv_bwd_workspace_floats": (_sz, [_i] * 4),
+    "es_t_dwconv_bwd": (_i, [_vp] * 7 + [_i] * 4 + [_vp, _sz]),
+    "es_t_layernorm_fwd": (_i, [_vp] * 7 + [_ll, _i]),
+    "es_t_layernorm_bwd_workspace_floats": (_sz, [_ll, _i]),
+    "es_t_layernorm_bwd": (_i, [_vp] * 8 + [_ll, _i, _vp, _sz]),
+    "es_t_colsum_workspace_floats": (_sz, [_ll, _i]),
+    "es_t_colsum": (_i, [_vp] * 4 + [_ll, _i, _i, _vp, _sz]),
+    "es_t_act_fwd": (_i, [_vp, _vp, _vp, _ll, _i]),
+    "es_t_act_bwd": (_i, [_vp, _vp, _vp, _vp, _ll, _i]),
+    "es_t_softmax_fwd": (_i, [_vp, _vp, _vp, _ll, _i, C.c_float]),
+    "es_t_softmax_bwd": (_i, [_vp, _vp, _vp, _vp, _ll, _i, C.c_float]),
+    "es_t_gather_rows": (_i, [_vp] * 4 + [_ll, _i]),
+    "es_t_scatter_add_rows": (_i, [_vp] * 4 + [_ll, _i, _i]),
+    "es_t_expand_rows": (_i, [_vp] * 4 + [_i] * 4),
+    "es_t_reduce_rows": (_i, [_vp] * 4 + [_i] * 4),
+    "es_t_bucketize": (_i, [_vp, _vp, _vp, _i, _vp, _ll]),
+    "es_t_axpby": (_i, [_vp] * 4 + [_ll, C.c_float, C.c_float]),
+    "es_t_mask_rows": (_i, [_vp] * 4 + [_ll, _i]),
+    "es_t_copy2d": (_i, [_vp, _vp, _i, _vp, _i, _ll, _i, _i]),
     "es_selftest_umma_gemm": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
 }
 

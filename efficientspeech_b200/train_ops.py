@@ -1,0 +1,497 @@
+"""Differentiable operators of the training step: ``torch.autograd.Function`` wrappers
+around the C-ABI primitives of ``csrc/es_train_ops.cu`` (include/es_b200.h: es_t_*).
+
+torch is the tape and the allocator here, nothing more: every forward and every adjoint below is one or a few launches
+of this repository's kernels, never a torch operator.  Two exceptions are worth naming because they are arithmetic:
+where a tensor fans out (the residual branches) the autograd engine adds the two incoming gradients itself, and
+``AccumulateGrad`` adds each parameter gradient into ``.grad``; both are elementwise adds of torch's.  Reshapes and
+views (``reshape``, ``squeeze``) move no data.
+
+Layout: activations are contiguous fp32 ``[B, T, C]`` (the reference permutes to ``[B, C, T]`` around every Conv1d,
+layers/networks.py:62-66; here time-major rows feed the GEMMs directly).  Parameters keep torch's layout, so a reference
+state dict loads unchanged and gradients come back in the layout ``torch.optim`` expects.
+
+There is no CPU path: every operator raises on a non-CUDA tensor.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+from torch.autograd import Function
+
+from . import _cabi
+
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3
+
+__all__ = ["linear", "conv1d", "conv_transpose1d", "dwconv1d", "layernorm", "act", "embedding", "expand_rows",
+           "mask_rows", "add", "concat_channels", "attention_core", "bucketize", "ACT_RELU", "ACT_GELU", "ACT_TANH"]
+
+
+# ------------------------------------------------------------------------------------------------ raw launches
+def _need_cuda(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("efficientspeech_b200.train_ops: tensors must be on a CUDA device (no CPU fallback)")
+
+
+def _f(t: torch.Tensor) -> torch.Tensor:
+    _need_cuda(t)
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"efficientspeech_b200.train_ops: fp32 tensors only (got {t.dtype})")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _launch(name: str, ref: torch.Tensor, *args) -> None:
+    dev = ref.device
+    with torch.cuda.device(dev):
+        _cabi.check(getattr(_cabi.load(), name)(torch.cuda.current_stream(dev).cuda_stream, *args))
+
+
+def _p(t: Optional[torch.Tensor], offset: int = 0):
+    return None if t is None else t.data_ptr() + 4 * offset
+
+
+def _gemm(A, B, C, M, N, K, lda, ldb, ldc, ta=False, tb=False, batch=1, sa=0, sb=0, sc=0, bias=None, acc=False, k_chunk=0,
+          a_off=0, b_off=0, c_off=0) -> None:
+    _launch("es_t_gemm", C, batch, M, N, K, _p(A, a_off), lda, sa, int(ta), _p(B, b_off), ldb, sb, int(tb), _p(C, c_off), ldc, sc,
+            _p(bias), int(acc), k_chunk)
+
+
+def _scratch(n_floats: int, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty(max(1, n_floats), dtype=torch.float32, device=like.device)
+
+
+def _colsum(A, Bm, out, rows, C, acc=False) -> None:
+    ws = _scratch(_cabi.load().es_t_colsum_workspace_floats(rows, C), out)
+    _launch("es_t_colsum", out, _p(A), _p(Bm), _p(out), rows, C, int(acc), _p(ws), ws.numel())
+
+
+def _atb(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a^T b for a [rows, M], b [rows, N] with rows >> M, N (a weight gradient): split-K partials, summed in order."""
+    rows, M = a.shape
+    N = b.shape[1]
+    chunk = max(256, -(-rows // 64))
+    splits = -(-rows // chunk)
+    if splits == 1:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+        _gemm(a, b, out, M, N, rows, M, N, N, ta=True)
+        return out
+    part = torch.empty(splits, M * N, dtype=torch.float32, device=a.device)
+    _gemm(a, b, part, M, N, rows, M, N, N, ta=True, batch=splits, sc=M * N, k_chunk=chunk)
+    out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    _colsum(part, None, out, splits, M * N)
+    return out
+
+
+def _rowsum(dy2: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(dy2.shape[1], dtype=torch.float32, device=dy2.device)
+    _colsum(dy2, None, out, dy2.shape[0], dy2.shape[1])
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ operators
+class _Linear(Function):
+    @staticmethod
+    def forward(ctx, x, W, b):
+        x2 = _f(x).reshape(-1, x.shape[-1])
+        W = _f(W)
+        rows, K = x2.shape
+        N = W.shape[0]
+        y = torch.empty(rows, N, dtype=torch.float32, device=x.device)
+        _gemm(x2, W, y, rows, N, K, K, K, N, tb=True, bias=None if b is None else _f(b))
+        ctx.save_for_backward(x2, W)
+        ctx.has_bias = b is not None
+        ctx.in_shape = x.shape
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W = ctx.saved_tensors
+        rows, K = x2.shape
+        N = W.shape[0]
+        dy2 = _f(dy).reshape(rows, N)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(rows, K, dtype=torch.float32, device=dy.device)
+            _gemm(dy2, W, dx, rows, K, N, N, K, K)
+            dx = dx.view(ctx.in_shape)
+        if ctx.needs_input_grad[1]:
+            dW = _atb(dy2, x2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _rowsum(dy2)
+        return dx, dW, db
+
+
+def linear(x, W, b=None):
+    """nn.Linear / a 1x1 Conv1d with its weight viewed [out, in]."""
+    return _Linear.apply(x, W, b)
+
+
+class _Conv1d(Function):
+    @staticmethod
+    def forward(ctx, x, W, b, stride, padding):
+        x = _f(x)
+        W = _f(W)
+        B, n, Cin = x.shape
+        Cout, _, k = W.shape
+        n_out = (n + 2 * padding - k) // stride + 1
+        cols = torch.empty(B * n_out, Cin * k, dtype=torch.float32, device=x.device)
+        _launch("es_t_im2col", x, _p(x), _p(cols), B, n, n_out, Cin, k, stride, padding)
+        y = torch.empty(B, n_out, Cout, dtype=torch.float32, device=x.device)
+        _gemm(cols, W, y, B * n_out, Cout, Cin * k, Cin * k, Cin * k, Cout, tb=True, bias=None if b is None else _f(b))
+        ctx.save_for_backward(cols, W)
+        ctx.geom = (B, n, n_out, Cin, Cout, k, stride, padding)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        cols, W = ctx.saved_tensors
+        B, n, n_out, Cin, Cout, k, stride, padding = ctx.geom
+        dy2 = _f(dy).reshape(B * n_out, Cout)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dcols = torch.empty_like(cols)
+            _gemm(dy2, W, dcols, B * n_out, Cin * k, Cout, Cout, Cin * k, Cin * k)
+            dx = torch.empty(B, n, Cin, dtype=torch.float32, device=dy.device)
+            _launch("es_t_col2im", dx, _p(dcols), _p(dx), B, n, n_out, Cin, k, stride, padding, 0)
+        if ctx.needs_input_grad[1]:
+            dW = _atb(dy2, cols).view(Cout, Cin, k)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _rowsum(dy2)
+        return dx, dW, db, None, None
+
+
+def conv1d(x, W, b=None, stride=1, padding=0):
+    """Dense nn.Conv1d over time on [B, n, Cin] (W [Cout, Cin, k]) as im2col + GEMM."""
+    return _Conv1d.apply(x, W, b, int(stride), int(padding))
+
+
+class _ConvTranspose1d(Function):
+    @staticmethod
+    def forward(ctx, x, W, b, stride, n_out):
+        x = _f(x)
+        W = _f(W)
+        B, n_s, Cin = x.shape
+        _, Cout, k = W.shape
+        cols = torch.empty(B * n_s, Cout * k, dtype=torch.float32, device=x.device)
+        _gemm(x, W, cols, B * n_s, Cout * k, Cin, Cin, Cout * k, Cout * k)
+        y = torch.empty(B, n_out, Cout, dtype=torch.float32, device=x.device)
+        _launch("es_t_col2im", y, _p(cols), _p(y), B, n_out, n_s, Cout, k, stride, 0, 0)
+        if b is not None:                                 # row stride 0 broadcasts the bias over every output position
+            _launch("es_t_copy2d", y, _p(_f(b)), 0, _p(y), Cout, B * n_out, Cout, 1)
+        ctx.save_for_backward(x, W)
+        ctx.geom = (B, n_s, n_out, Cin, Cout, k, stride)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        B, n_s, n_out, Cin, Cout, k, stride = ctx.geom
+        dy = _f(dy)
+        dcols = torch.empty(B * n_s, Cout * k, dtype=torch.float32, device=dy.device)
+        _launch("es_t_im2col", dy, _p(dy), _p(dcols), B, n_out, n_s, Cout, k, stride, 0)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B, n_s, Cin, dtype=torch.float32, device=dy.device)
+            _gemm(dcols, W, dx, B * n_s, Cin, Cout * k, Cout * k, Cout * k, Cin, tb=True)
+        if ctx.needs_input_grad[1]:
+            dW = _atb(x.reshape(B * n_s, Cin), dcols).view(Cin, Cout, k)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _rowsum(dy.reshape(B * n_out, Cout))
+        return dx, dW, db, None, None
+
+
+def conv_transpose1d(x, W, b, stride, n_out):
+    """nn.ConvTranspose1d (padding 0) on [B, n, Cin], W [Cin, Cout, k], output cut (or zero/bias-extended) to n_out
+    positions as Fuse.forward does (layers/networks.py:205-208)."""
+    return _ConvTranspose1d.apply(x, W, b, int(stride), int(n_out))
+
+
+class _DWConv1d(Function):
+    @staticmethod
+    def forward(ctx, x, W, b):
+        x = _f(x)
+        W = _f(W)
+        B, T, C = x.shape
+        k = W.shape[-1]
+        y = torch.empty_like(x)
+        _launch("es_t_dwconv_fwd", x, _p(x), _p(W), _p(_f(b)), _p(y), B, T, C, k)
+        ctx.save_for_backward(x, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        B, T, C = x.shape
+        k = W.shape[-1]
+        dy = _f(dy)
+        dx = torch.empty_like(x)
+        dW = torch.empty_like(W)
+        db = torch.empty(C, dtype=torch.float32, device=x.device)
+        ws = _scratch(_cabi.load().es_t_dwconv_bwd_workspace_floats(B, T, C, k), x)
+        _launch("es_t_dwconv_bwd", x, _p(dy), _p(x), _p(W), _p(dx), _p(dW), _p(db), B, T, C, k, _p(ws), ws.numel())
+        return dx, dW, db
+
+
+def dwconv1d(x, W, b):
+    """nn.Conv1d(C, C, k, groups=C, padding=k//2) on [B, T, C] (W [C, 1, k])."""
+    return _DWConv1d.apply(x, W, b)
+
+
+class _LayerNorm(Function):
+    @staticmethod
+    def forward(ctx, x, g, b):
+        x = _f(x)
+        C = x.shape[-1]
+        rows = x.numel() // C
+        y = torch.empty_like(x)
+        xhat = torch.empty_like(x)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        g = _f(g)
+        _launch("es_t_layernorm_fwd", x, _p(x), _p(g), _p(_f(b)), _p(y), _p(xhat), _p(rstd), rows, C)
+        ctx.save_for_backward(xhat, rstd, g)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xhat, rstd, g = ctx.saved_tensors
+        C = xhat.shape[-1]
+        rows = rstd.numel()
+        dy = _f(dy)
+        dx = torch.empty_like(xhat)
+        dg = torch.empty(C, dtype=torch.float32, device=dy.device)
+        db = torch.empty(C, dtype=torch.float32, device=dy.device)
+        ws = _scratch(_cabi.load().es_t_layernorm_bwd_workspace_floats(rows, C), dy)
+        _launch("es_t_layernorm_bwd", dy, _p(dy), _p(xhat), _p(rstd), _p(g), _p(dx), _p(dg), _p(db), rows, C, _p(ws), ws.numel())
+        return dx, dg, db
+
+
+def layernorm(x, g, b):
+    """nn.LayerNorm over the last dimension (eps 1e-5)."""
+    return _LayerNorm.apply(x, g, b)
+
+
+class _Act(Function):
+    @staticmethod
+    def forward(ctx, x, kind):
+        x = _f(x)
+        y = torch.empty_like(x)
+        _launch("es_t_act_fwd", x, _p(x), _p(y), x.numel(), kind)
+        ctx.save_for_backward(x if kind == ACT_GELU else y)
+        ctx.kind = kind
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (saved,) = ctx.saved_tensors
+        dy = _f(dy)
+        dx = torch.empty_like(saved)
+        _launch("es_t_act_bwd", dy, _p(dy), _p(saved), _p(dx), saved.numel(), ctx.kind)
+        return dx, None
+
+
+def act(x, kind):
+    """ReLU / GELU (exact erf, nn.GELU default) / tanh."""
+    return _Act.apply(x, int(kind))
+
+
+class _Embedding(Function):
+    @staticmethod
+    def forward(ctx, idx, table, padding_idx):
+        table = _f(table)
+        _need_cuda(idx)
+        idx = idx.to(torch.int32).contiguous()
+        rows = idx.numel()
+        C = table.shape[1]
+        out = torch.empty(*idx.shape, C, dtype=torch.float32, device=table.device)
+        _launch("es_t_gather_rows", table, _p(table), idx.data_ptr(), _p(out), rows, C)
+        ctx.save_for_backward(idx)
+        ctx.tshape = tuple(table.shape)
+        ctx.padding_idx = padding_idx
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        dout = _f(dout)
+        dt = torch.zeros(ctx.tshape, dtype=torch.float32, device=dout.device)
+        _launch("es_t_scatter_add_rows", dout, _p(dout), idx.data_ptr(), _p(dt), idx.numel(), ctx.tshape[1], ctx.padding_idx)
+        return None, dt, None
+
+
+def embedding(idx, table, padding_idx=-1):
+    """nn.Embedding lookup; the row ``padding_idx`` receives no gradient (layers/networks.py:35)."""
+    return _Embedding.apply(idx, table, int(padding_idx))
+
+
+class _ExpandRows(Function):
+    @staticmethod
+    def forward(ctx, x, cum, T):
+        x = _f(x)
+        B, N, C = x.shape
+        out = torch.empty(B, T, C, dtype=torch.float32, device=x.device)
+        _launch("es_t_expand_rows", x, _p(x), cum.data_ptr(), _p(out), B, N, T, C)
+        ctx.save_for_backward(cum)
+        ctx.geom = (B, N, T, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (cum,) = ctx.saved_tensors
+        B, N, T, C = ctx.geom
+        dout = _f(dout)
+        dx = torch.empty(B, N, C, dtype=torch.float32, device=dout.device)
+        _launch("es_t_reduce_rows", dout, _p(dout), cum.data_ptr(), _p(dx), B, N, T, C)
+        return dx, None, None
+
+
+def expand_rows(x, cum, T):
+    """The length regulator (FeatureUpsampler, layers/networks.py:228-258): phoneme n of utterance b is repeated over
+    frames [cum[b,n-1], cum[b,n]); frames past the last are zero.  ``cum``: int32 inclusive cumulative durations."""
+    if cum.dtype != torch.int32 or not cum.is_contiguous():
+        raise RuntimeError("expand_rows: cum must be contiguous int32")
+    return _ExpandRows.apply(x, cum, int(T))
+
+
+class _MaskRows(Function):
+    @staticmethod
+    def forward(ctx, x, mask):
+        x = _f(x)
+        C = x.shape[-1]
+        y = torch.empty_like(x)
+        _launch("es_t_mask_rows", x, _p(x), mask.data_ptr(), _p(y), x.numel() // C, C)
+        ctx.save_for_backward(mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        dy = _f(dy)
+        C = dy.shape[-1]
+        dx = torch.empty_like(dy)
+        _launch("es_t_mask_rows", dy, _p(dy), mask.data_ptr(), _p(dx), dy.numel() // C, C)
+        return dx, None
+
+
+def mask_rows(x, mask):
+    """x.masked_fill(mask[..., None], 0) for a boolean row mask."""
+    if mask.dtype == torch.bool:
+        mask = mask.contiguous().view(torch.uint8)
+    if mask.numel() != x.numel() // x.shape[-1]:
+        raise RuntimeError("mask_rows: one mask entry per row expected")
+    return _MaskRows.apply(x, mask)
+
+
+class _Add(Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = _f(x), _f(y)
+        out = torch.empty_like(x)
+        _launch("es_t_axpby", x, _p(x), _p(y), _p(out), x.numel(), 1.0, 1.0)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        return d, d
+
+
+def add(x, y):
+    if x.shape != y.shape:
+        raise RuntimeError("add: shapes differ")
+    return _Add.apply(x, y)
+
+
+class _Concat(Function):
+    @staticmethod
+    def forward(ctx, *xs):
+        xs = [_f(x) for x in xs]
+        widths = [x.shape[-1] for x in xs]
+        rows = xs[0].numel() // widths[0]
+        total = sum(widths)
+        out = torch.empty(*xs[0].shape[:-1], total, dtype=torch.float32, device=xs[0].device)
+        off = 0
+        for x, w in zip(xs, widths):
+            _launch("es_t_copy2d", x, _p(x), w, _p(out, off), total, rows, w, 0)
+            off += w
+        ctx.widths = widths
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        d = _f(d)
+        total = d.shape[-1]
+        rows = d.numel() // total
+        outs, off = [], 0
+        for w in ctx.widths:
+            g = torch.empty(*d.shape[:-1], w, dtype=torch.float32, device=d.device)
+            _launch("es_t_copy2d", d, _p(d, off), total, _p(g), w, rows, w, 0)
+            outs.append(g)
+            off += w
+        return tuple(outs)
+
+
+def concat_channels(xs: Sequence[torch.Tensor]):
+    """torch.cat(xs, dim=-1)."""
+    return _Concat.apply(*xs)
+
+
+class _AttentionCore(Function):
+    @staticmethod
+    def forward(ctx, qkv, H, C, scale):
+        qkv = _f(qkv)
+        B, N, _ = qkv.shape
+        ld = 3 * H * C
+        attn = torch.empty(B, H, N, N, dtype=torch.float32, device=qkv.device)
+        out = torch.empty(B, N, H * C, dtype=torch.float32, device=qkv.device)
+        for h in range(H):
+            # S[b,h] = q k^T (scale folded into the softmax)
+            _gemm(qkv, qkv, attn, N, N, C, ld, ld, N, tb=True, batch=B, sa=N * ld, sb=N * ld, sc=H * N * N,
+                  a_off=h * C, b_off=(H + h) * C, c_off=h * N * N)
+        _launch("es_t_softmax_fwd", attn, _p(attn), _p(attn), B * H * N, N, scale)
+        for h in range(H):
+            _gemm(attn, qkv, out, N, C, N, N, ld, H * C, batch=B, sa=H * N * N, sb=N * ld, sc=N * H * C,
+                  a_off=h * N * N, b_off=(2 * H + h) * C, c_off=h * C)
+        ctx.save_for_backward(qkv, attn)
+        ctx.geom = (B, N, H, C, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, attn = ctx.saved_tensors
+        B, N, H, C, scale = ctx.geom
+        ld = 3 * H * C
+        dout = _f(dout)
+        dqkv = torch.empty_like(qkv)
+        dattn = torch.empty_like(attn)
+        for h in range(H):
+            # dP = dO v^T ; dv = P^T dO
+            _gemm(dout, qkv, dattn, N, N, C, H * C, ld, N, tb=True, batch=B, sa=N * H * C, sb=N * ld, sc=H * N * N,
+                  a_off=h * C, b_off=(2 * H + h) * C, c_off=h * N * N)
+            _gemm(attn, dout, dqkv, N, C, N, N, H * C, ld, ta=True, batch=B, sa=H * N * N, sb=N * H * C, sc=N * ld,
+                  a_off=h * N * N, b_off=h * C, c_off=(2 * H + h) * C)
+        _launch("es_t_softmax_bwd", dattn, _p(dattn), _p(attn), _p(dattn), B * H * N, N, scale)
+        for h in range(H):
+            # dq = dS k ; dk = dS^T q
+            _gemm(dattn, qkv, dqkv, N, C, N, N, ld, ld, batch=B, sa=H * N * N, sb=N * ld, sc=N * ld,
+                  a_off=h * N * N, b_off=(H + h) * C, c_off=h * C)
+            _gemm(dattn, qkv, dqkv, N, C, N, N, ld, ld, ta=True, batch=B, sa=H * N * N, sb=N * ld, sc=N * ld,
+                  a_off=h * N * N, b_off=h * C, c_off=(H + h) * C)
+        return dqkv, None, None, None
+
+
+def attention_core(qkv, num_heads, dim, scale):
+    """softmax(scale q k^T) v for qkv [B, N, 3*H*dim] laid out as the reference's reshape(B, N, 3, H, C)
+    (layers/blocks.py:44-63; the padding mask is NOT applied to the scores there, and is not here); returns
+    [B, N, H*dim] with the heads side by side."""
+    return _AttentionCore.apply(qkv, int(num_heads), int(dim), float(scale))
+
+
+def bucketize(v: torch.Tensor, bins: torch.Tensor) -> torch.Tensor:
+    """torch.bucketize(v, bins) -> int32 (not differentiable)."""
+    v = _f(v.detach())
+    bins = _f(bins.detach())
+    out = torch.empty(v.shape, dtype=torch.int32, device=v.device)
+    _launch("es_t_bucketize", v, _p(v), _p(bins), bins.numel(), out.data_ptr(), v.numel())
+    return out

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ES_ABI_VERSION 11
+#define ES_ABI_VERSION 12
 #define ES_MAX_ENC_BLOCKS 2
 #define ES_MAX_DEC_LAYERS 24
 #define ES_MAX_DEC_BLOCKS 8
@@ -364,6 +364,53 @@ int    es_loss(void* stream, int B, int N, int T, int n_mel, const float* mel_pr
  * torch computes on the host in double: step_size = lr / (1 - beta1^t), bias_correction2_sqrt = sqrt(1 - beta2^t). */
 int    es_adamw_step(void* stream, size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float lr,
                      float beta1, float beta2, float eps, float weight_decay, float step_size, float bias_correction2_sqrt);
+
+/* ---- differentiable primitives of the training step (csrc/es_train_ops.cu) --------------
+ * Row-major fp32 activations [rows][C] ("B T C"), torch-layout parameters.  Together they stand in for what
+ * lightning's training_step runs through torch autograd on layers/networks.py (model.py:97-113): every call is one
+ * operator or its adjoint; efficientspeech_b200/train_ops.py composes them.  act kinds: 0 none, 1 ReLU, 2 GELU (erf), 3 tanh. */
+/* C[b] (+)= op(A[b]) op(B[b]) (+ bias[n]);  op(A) is M x K, op(B) is K x N; trans_x: the stored matrix is the transpose.
+ * k_chunk > 0: split-K -- slice b of `batch` takes k in [b k_chunk, (b+1) k_chunk) of ONE product and writes its partial
+ * to C + b stride_c (weight gradients contract over every frame of the batch; es_t_colsum adds the partials in order). */
+int es_t_gemm(void* stream, int batch, int M, int N, int K, const float* A, int lda, long long stride_a, int trans_a,
+              const float* B, int ldb, long long stride_b, int trans_b, float* C, int ldc, long long stride_c,
+              const float* bias, int accumulate, int k_chunk);
+/* cols[b, t, c*k + tau] = X[b, t*s + tau - p, c] (zero outside; a row is ordered like torch's flattened Conv1d weight),
+ * and its adjoint (also ConvTranspose1d's forward scatter). */
+int es_t_im2col(void* stream, const float* X, float* cols, int B, int n_in, int n_out, int C, int k, int s, int p);
+int es_t_col2im(void* stream, const float* cols, float* X, int B, int n_in, int n_out, int C, int k, int s, int p, int accumulate);
+/* depthwise Conv1d over time, "same" padding k/2 (layers/networks.py:281); w [C][k] */
+int es_t_dwconv_fwd(void* stream, const float* X, const float* w, const float* bias, float* Y, int B, int T, int C, int k);
+/* the weight / bias gradients reduce over every frame: row slices into `ws`, added in a fixed order (deterministic) */
+size_t es_t_dwconv_bwd_workspace_floats(int B, int T, int C, int k);
+int es_t_dwconv_bwd(void* stream, const float* dY, const float* X, const float* w, float* dX, float* dw, float* db, int B, int T, int C, int k,
+                    float* ws, size_t ws_floats);
+int es_t_layernorm_fwd(void* stream, const float* X, const float* g, const float* b, float* Y, float* xhat, float* rstd, long long rows, int C);
+/* one pass: dX and, per block, partial sums of dg / db in `ws`, then added in a fixed order.  C <= 256. */
+size_t es_t_layernorm_bwd_workspace_floats(long long rows, int C);
+int es_t_layernorm_bwd(void* stream, const float* dY, const float* xhat, const float* rstd, const float* g, float* dX, float* dg, float* db,
+                       long long rows, int C, float* ws, size_t ws_floats);
+/* out[c] (+)= sum_r A[r,c] (* B[r,c] when B is given); long reductions go through row slices in `ws` (may be null when
+ * es_t_colsum_workspace_floats returns 0) */
+size_t es_t_colsum_workspace_floats(long long rows, int C);
+int es_t_colsum(void* stream, const float* A, const float* B, float* out, long long rows, int C, int accumulate, float* ws, size_t ws_floats);
+int es_t_act_fwd(void* stream, const float* X, float* Y, long long n, int kind);
+/* saved: the OUTPUT for ReLU / tanh, the INPUT for GELU */
+int es_t_act_bwd(void* stream, const float* dY, const float* saved, float* dX, long long n, int kind);
+int es_t_softmax_fwd(void* stream, const float* X, float* Y, long long rows, int n, float scale);
+int es_t_softmax_bwd(void* stream, const float* dY, const float* Y, float* dX, long long rows, int n, float scale);
+/* out[r] = table[idx[r]] (idx < 0: zeros); d_table[idx[r]] += d_out[r] except rows idx == skip_index (padding_idx) */
+int es_t_gather_rows(void* stream, const float* table, const int32_t* idx, float* out, long long rows, int C);
+int es_t_scatter_add_rows(void* stream, const float* d_out, const int32_t* idx, float* d_table, long long rows, int C, int skip_index);
+/* length regulator (layers/blocks.py LengthRegulator): cum = inclusive cumulative durations [B,N]; frames past the sum
+ * are zero.  reduce_rows is its adjoint, a fixed-order segmented sum. */
+int es_t_expand_rows(void* stream, const float* in, const int32_t* cum, float* out, int B, int N, int T, int C);
+int es_t_reduce_rows(void* stream, const float* d_out, const int32_t* cum, float* d_in, int B, int N, int T, int C);
+/* torch.bucketize(v, bins): first i with bins[i] >= v (layers/networks.py:128-141 on the TARGET pitch / energy) */
+int es_t_bucketize(void* stream, const float* v, const float* bins, int n_bins, int32_t* out, long long n);
+int es_t_axpby(void* stream, const float* X, const float* Y, float* out, long long n, float a, float b);
+int es_t_mask_rows(void* stream, const float* X, const uint8_t* mask, float* Y, long long rows, int C);
+int es_t_copy2d(void* stream, const float* src, int lds, float* dst, int ldd, long long rows, int cols, int accumulate);
 
 #ifdef __cplusplus
 }

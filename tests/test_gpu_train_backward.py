@@ -1,0 +1,268 @@
+"""The training path on the GPU: every differentiable primitive (csrc/es_train_ops.cu through train_ops.py) against the
+torch operator it stands in for (forward values and all gradients, torch run on the CPU), then the whole network --
+``training.forward_train`` + ``training.loss`` + backward -- against the REFERENCE's own modules and loss under torch
+autograd on the CPU (oracle/_ref staged sources), parameter by parameter, and ``TrainStep`` against the reference +
+torch.optim.AdamW over several optimisation steps.
+
+Tolerances: fp32 on both sides, different summation orders.  Primitive outputs / gradients 2e-5 of the tensor's max;
+whole-network parameter gradients 2e-4 of each tensor's max (sums over up to ~1e5 frames).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import efficientspeech_b200 as es
+from efficientspeech_b200 import train_ops as ops
+from efficientspeech_b200 import training
+from efficientspeech_b200.config import VARIANTS
+from efficientspeech_b200.params import init_state_dict
+from efficientspeech_b200.synthetic import make_batch
+from oracle import ref_shim
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from test_training_cpu import HAVE_REF, reference_loss_fn  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_OP = 2e-5
+TOL_GRAD = 2e-4
+
+
+def close(got, want, tol, what=""):
+    got = got.detach().cpu().double().numpy()
+    want = want.detach().cpu().double().numpy()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    scale = max(1e-6, float(np.abs(want).max()))
+    err = float(np.abs(got - want).max())
+    assert err <= tol * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+def check_op(ours, theirs, inputs, tol=TOL_OP):
+    """inputs: list of CPU tensors (float ones get gradients).  Compares outputs and all input gradients."""
+    cpu = [t.clone().requires_grad_(t.is_floating_point()) for t in inputs]
+    gpu = [t.clone().to(DEV).requires_grad_(t.is_floating_point()) for t in inputs]
+    want = theirs(*cpu)
+    got = ours(*gpu)
+    close(got, want, tol, "forward")
+    g = torch.randn(want.shape, generator=torch.Generator().manual_seed(7))
+    want.backward(g)
+    got.backward(g.to(DEV))
+    for i, (a, b) in enumerate(zip(gpu, cpu)):
+        if b.requires_grad:
+            close(a.grad, b.grad, tol, f"grad of input {i}")
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+# ------------------------------------------------------------------------------------------------ primitives
+@pytest.mark.parametrize("rows,K,N,bias", [((3, 7), 5, 4, True), ((2, 130), 128, 96, True), ((40000,), 128, 128, False),
+                                           ((5, 33), 64, 1, True)])
+def test_linear(rows, K, N, bias):
+    ins = [rnd(*rows, K, seed=1), rnd(N, K, seed=2, scale=0.2)] + ([rnd(N, seed=3)] if bias else [])
+    check_op(lambda x, W, b=None: ops.linear(x, W, b), lambda x, W, b=None: F.linear(x, W, b), ins)
+
+
+@pytest.mark.parametrize("B,n,Cin,Cout,k,s,bias", [(2, 11, 8, 6, 3, 1, True), (3, 128, 128, 128, 3, 1, False),
+                                                   (3, 128, 32, 32, 3, 2, False), (2, 13, 16, 16, 3, 2, False),
+                                                   (2, 37, 32, 32, 5, 1, True), (2, 9, 24, 24, 1, 2, False)])
+def test_conv1d(B, n, Cin, Cout, k, s, bias):
+    ins = [rnd(B, n, Cin, seed=1), rnd(Cout, Cin, k, seed=2, scale=0.2)] + ([rnd(Cout, seed=3)] if bias else [])
+    check_op(lambda x, W, b=None: ops.conv1d(x, W, b, s, k // 2),
+             lambda x, W, b=None: F.conv1d(x.transpose(1, 2), W, b, stride=s, padding=k // 2).transpose(1, 2), ins)
+
+
+@pytest.mark.parametrize("B,n_s,C,k,s,n_out", [(2, 6, 8, 3, 2, 11), (3, 64, 32, 3, 2, 128), (2, 65, 64, 3, 2, 129),
+                                               (2, 32, 32, 3, 4, 125), (2, 16, 64, 5, 2, 32)])
+def test_conv_transpose1d(B, n_s, C, k, s, n_out):
+    ins = [rnd(B, n_s, C, seed=1), rnd(C, C, k, seed=2, scale=0.2), rnd(C, seed=3)]
+    check_op(lambda x, W, b: ops.conv_transpose1d(x, W, b, s, n_out),
+             lambda x, W, b: F.conv_transpose1d(x.transpose(1, 2), W, b, stride=s)[:, :, :n_out].transpose(1, 2), ins)
+
+
+@pytest.mark.parametrize("B,T,C,k", [(2, 9, 8, 5), (3, 301, 128, 5), (2, 50, 256, 3), (1, 3, 128, 5)])
+def test_dwconv1d(B, T, C, k):
+    ins = [rnd(B, T, C, seed=1), rnd(C, 1, k, seed=2), rnd(C, seed=3)]
+    check_op(ops.dwconv1d, lambda x, W, b: F.conv1d(x.transpose(1, 2), W, b, padding=k // 2, groups=C).transpose(1, 2), ins)
+
+
+@pytest.mark.parametrize("shape", [(3, 7, 32), (2, 300, 128), (2, 40, 256), (5, 64)])
+def test_layernorm(shape):
+    C = shape[-1]
+    ins = [rnd(*shape, seed=1) * 2 + 0.5, rnd(C, seed=2) + 1, rnd(C, seed=3)]
+    check_op(ops.layernorm, lambda x, g, b: F.layer_norm(x, (C,), g, b), ins)
+
+
+@pytest.mark.parametrize("kind,fn", [(ops.ACT_RELU, F.relu), (ops.ACT_GELU, F.gelu), (ops.ACT_TANH, torch.tanh)])
+def test_activations(kind, fn):
+    check_op(lambda x: ops.act(x, kind), fn, [rnd(3, 77, 32, seed=1) * 2])
+
+
+@pytest.mark.parametrize("B,N,H,C", [(2, 11, 1, 32), (3, 128, 1, 32), (2, 64, 1, 64), (2, 17, 2, 64), (2, 9, 4, 128)])
+def test_attention_core(B, N, H, C):
+    scale = float((C // H) ** -0.5)
+
+    def theirs(qkv):                                            # layers/blocks.py:44-63
+        q, k, v = qkv.reshape(B, N, 3, H, C).permute(2, 0, 3, 1, 4).unbind(0)
+        attn = ((q @ k.transpose(-2, -1)) * scale).softmax(dim=-1)
+        return (attn @ v).transpose(1, 2).reshape(B, N, -1)
+
+    check_op(lambda qkv: ops.attention_core(qkv, H, C, scale), theirs, [rnd(B, N, 3 * H * C, seed=1)])
+
+
+def test_embedding_with_padding_row():
+    idx = torch.randint(0, 20, (4, 33), generator=torch.Generator().manual_seed(1))
+    idx[:, -5:] = 0
+    table = rnd(20, 16, seed=2)
+    check_op(lambda i, t: ops.embedding(i, t, 0), lambda i, t: F.embedding(i, t, padding_idx=0), [idx, table])
+    check_op(lambda i, t: ops.embedding(i, t), lambda i, t: F.embedding(i, t), [idx, table])
+
+
+def test_expand_rows_is_repeat_interleave():
+    B, N, C, T = 3, 9, 8, 40
+    g = torch.Generator().manual_seed(3)
+    dur = torch.randint(0, 6, (B, N), generator=g)
+    dur[1, 4:] = 0
+    cum = torch.cumsum(dur, 1).to(torch.int32)
+
+    def theirs(x):                                              # layers/networks.py:233-243
+        rows = []
+        for b in range(B):
+            f = x[b].repeat_interleave(dur[b], dim=0)[:T]
+            rows.append(F.pad(f, (0, 0, 0, T - f.shape[0])))
+        return torch.stack(rows)
+
+    check_op(lambda x: ops.expand_rows(x, cum.to(DEV), T), theirs, [rnd(B, N, C, seed=1)])
+
+
+def test_mask_add_concat_bucketize():
+    mask = torch.rand(3, 17, generator=torch.Generator().manual_seed(1)) > 0.6
+    check_op(lambda x: ops.mask_rows(x, mask.to(DEV)), lambda x: x.masked_fill(mask[..., None], 0), [rnd(3, 17, 8, seed=2)])
+    check_op(ops.add, torch.add, [rnd(3, 17, 8, seed=2), rnd(3, 17, 8, seed=3)])
+    check_op(lambda a, b, c: ops.concat_channels([a, b, c]), lambda a, b, c: torch.cat([a, b, c], -1),
+             [rnd(3, 17, 8, seed=2), rnd(3, 17, 5, seed=3), rnd(3, 17, 32, seed=4)])
+    v = rnd(4, 50, seed=5) * 2
+    bins = torch.linspace(-2.9, 4.1, 31)
+    v[0, :31] = bins                                            # exact edges: right=False semantics
+    assert torch.equal(ops.bucketize(v.to(DEV), bins.to(DEV)).cpu().long(), torch.bucketize(v, bins))
+
+
+# ------------------------------------------------------------------------------------------------ whole network
+def mel_mask_of(batch, T):
+    return torch.from_numpy(np.arange(T)[None, :] >= batch["mel_len"][:, None])
+
+
+def reference_step(vname, sd, batch, mel_target):
+    """The reference's modules + its loss source under torch autograd on the CPU: (losses, total, grads by name, model)."""
+    cfg = VARIANTS[vname]
+    ref = ref_shim.build_reference_model(cfg, sd).train()
+    x = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in batch.items()}
+    T = int(batch["mel_len"].max())
+    x["mel_mask"] = mel_mask_of(batch, T)
+    pred = ref(x, train=True)
+    losses = reference_loss_fn()(None, pred, {"mel": mel_target}, x)
+    total = 10. * losses[0] + 2. * losses[1] + 2. * losses[2] + losses[3]                     # model.py:215
+    total.backward()
+    grads = {n: (None if p.grad is None else p.grad.clone()) for n, p in ref.named_parameters()}
+    return losses, total, grads, ref, pred
+
+
+def our_model(vname, sd):
+    m = es.build_model(vname)
+    es.load_numpy_state(m, sd)
+    return m.to(DEV)
+
+
+def dev_batch(batch):
+    x = {k: torch.from_numpy(np.ascontiguousarray(v)).to(DEV) for k, v in batch.items()}
+    x["max_mel_len"] = int(batch["mel_len"].max())
+    return x
+
+
+def spread_state(vname, seed):
+    sd = dict(init_state_dict(VARIANTS[vname], seed=seed))
+    # default init gives a duration head that sits at ~0 behind its ReLU (dead gradient): lift it
+    sd["encoder.duration_decoder.linear.bias"] = np.full_like(sd["encoder.duration_decoder.linear.bias"], 3.0)
+    return sd
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not staged (oracle/build_ref.py)")
+@pytest.mark.parametrize("vname,B,N,seed", [("tiny", 3, 11, 0), ("tiny", 4, 128, 1), ("tiny", 3, 37, 2), ("small", 3, 40, 3),
+                                            ("base", 3, 24, 4), ("tiny", 1, 19, 5)])
+def test_network_gradients_match_reference_autograd(vname, B, N, seed):
+    cfg = VARIANTS[vname]
+    sd = spread_state(vname, seed)
+    batch = make_batch(cfg, B, N, seed=seed, ragged=B > 1, fixed_duration=None)
+    T = int(batch["mel_len"].max())
+    mel_t = rnd(B, T, cfg.n_mel, seed=seed + 100)
+    ref_losses, ref_total, ref_grads, _, ref_pred = reference_step(vname, sd, batch, mel_t)
+
+    m = our_model(vname, sd)
+    x = dev_batch(batch)
+    pred = training.forward_train(m, x)
+    for k in ("mel", "pitch", "energy", "duration", "features"):
+        close(pred[k], ref_pred[k], 1e-4, f"forward {k}")
+    assert torch.equal(pred["mel_len"].cpu(), ref_pred["mel_len"].cpu().to(torch.int32))
+    losses, g = training.loss(pred, {"mel": mel_t.to(DEV)}, x, with_grads=True)
+    for a, b in zip(losses, ref_losses):
+        assert abs(float(a) - float(b)) <= 1e-4 * max(1.0, abs(float(b)))
+    torch.autograd.backward([pred["mel"], pred["pitch"], pred["energy"], pred["duration"]],
+                            [g["mel"], g["pitch"].view(B, N, 1), g["energy"].view(B, N, 1), g["duration"].view(B, N, 1)])
+    ours = dict(m.named_parameters())
+    checked = 0
+    for name, want in ref_grads.items():
+        p = ours[name]
+        if want is None:                                         # bins, and norm2 of the pitch / energy predictors
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        assert p.grad is not None, name
+        close(p.grad, want, TOL_GRAD, name)
+        checked += 1
+    assert checked >= 60
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not staged (oracle/build_ref.py)")
+def test_train_step_tracks_reference_adamw():
+    vname, B, N, steps = "tiny", 4, 48, 6
+    cfg = VARIANTS[vname]
+    sd = spread_state(vname, 11)
+    ref = ref_shim.build_reference_model(cfg, sd).train()
+    ref_opt = torch.optim.AdamW(ref.parameters(), lr=1e-3, weight_decay=1e-6)                 # model.py:280
+    sched = torch.optim.lr_scheduler.LambdaLR(ref_opt, lambda s: training.lr_lambda(s, 3, 50))
+    loss_fn = reference_loss_fn()
+    m = our_model(vname, sd)
+    step = training.TrainStep(m, lr=1e-3, weight_decay=1e-6, warmup_steps=3, total_steps=50)
+    for i in range(steps):
+        batch = make_batch(cfg, B, N, seed=20 + i, ragged=True, fixed_duration=None)
+        T = int(batch["mel_len"].max())
+        mel_t = rnd(B, T, cfg.n_mel, seed=300 + i)
+        x = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in batch.items()}
+        x["mel_mask"] = mel_mask_of(batch, T)
+        ref_opt.zero_grad()
+        ls = loss_fn(None, ref(x, train=True), {"mel": mel_t}, x)
+        total = 10. * ls[0] + 2. * ls[1] + 2. * ls[2] + ls[3]
+        total.backward()
+        ref_opt.step()
+        sched.step()
+        got = step(dev_batch(batch), {"mel": mel_t.to(DEV)})
+        assert abs(float(got[0]) - float(total)) <= 2e-3 * abs(float(total)), (i, float(got[0]), float(total))
+    ours = dict(m.named_parameters())
+    for name, p in ref.named_parameters():
+        if not p.requires_grad:
+            continue
+        a, b = ours[name].detach().cpu().numpy(), p.detach().numpy()
+        # Adam's first steps move every weight by ~lr regardless of the gradient's size, so a gradient that differs in
+        # the last bits can move a weight by a visible fraction of lr: bound by a few lr, not by fp32 epsilon
+        assert np.abs(a - b).max() <= 2e-3, name
+    # the step also has to leave the inference path usable: the fused kernels re-pack the updated weights
+    m.eval()
+    batch = make_batch(cfg, B, N, seed=99, ragged=True, fixed_duration=None)
+    with torch.no_grad():
+        mel = m(dev_batch(batch), train=True)["mel"]
+        want = ref.eval()({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in batch.items()}, train=True)["mel"]
+    assert float((mel.cpu() - want).abs().max()) <= 5e-3

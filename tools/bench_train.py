@@ -1,0 +1,49 @@
+"""Time the training step (forward_train + loss + backward + AdamW) on synthetic LJSpeech-shaped batches and list the
+kernels by time share.  python tools/bench_train.py [B] [N] [steps]"""
+import sys
+import time
+
+import numpy as np
+import torch
+
+import efficientspeech_b200 as es
+from efficientspeech_b200 import training
+from efficientspeech_b200.config import VARIANTS
+from efficientspeech_b200.synthetic import make_batch
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+dev = "cuda:0"
+cfg = VARIANTS["tiny"]
+m = es.build_model("tiny").to(dev)
+step = training.TrainStep(m)
+batches = []
+for i in range(4):
+    b = make_batch(cfg, B, N, seed=i, ragged=True, fixed_duration=None, max_dur=12)
+    T = int(b["mel_len"].max())
+    x = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in b.items()}
+    x["max_mel_len"] = T
+    y = {"mel": torch.randn(B, T, cfg.n_mel, device=dev)}
+    batches.append((x, y, int(b["mel_len"].sum())))
+for i in range(3):
+    out = step(*batches[i % 4][:2])
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0 = time.perf_counter()
+e0.record()
+frames = 0
+for i in range(steps):
+    out = step(*batches[i % 4][:2])
+    frames += batches[i % 4][2]
+e1.record()
+torch.cuda.synchronize()
+wall = time.perf_counter() - t0
+ms = e0.elapsed_time(e1) / steps
+print(f"B={B} N={N} T~{batches[0][0]['max_mel_len']}: {ms:.2f} ms/step (device), {wall / steps * 1e3:.2f} ms wall, "
+      f"{frames / (ms * steps) * 1e3 / 1e6:.2f} M frames/s, loss {float(out[0]):.4f}, peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB")
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    step(*batches[0][:2])
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
