@@ -151,6 +151,56 @@ def time_reference_b1(variant, N, duration, warm=10, timed=100, threads=None):
             "kind": "reference", "protocol": f"{warm} warm-up + {timed} timed single utterances (demo.py:149-167), free-running"}
 
 
+def train_batches(cfg, B, N, count, seed0, max_dur=12):
+    """LJSpeech-shaped synthetic training batches (BASELINE configs[4]): ragged phoneme lengths in [N/2, N], durations
+    U{0..max_dur} (so ~6 frames per phoneme, T ~ 800 at N = 128), pitch / energy targets, a random mel target."""
+    from efficientspeech_b200.synthetic import make_batch
+    out = []
+    for i in range(count):
+        b = make_batch(cfg, B, N, seed=seed0 + i, ragged=True, fixed_duration=None, max_dur=max_dur)
+        T = int(b["mel_len"].max())
+        rng = np.random.default_rng(1000 + seed0 + i)
+        b["mel"] = rng.standard_normal((B, T, cfg.n_mel)).astype(np.float32)
+        out.append(b)
+    return out
+
+
+def time_reference_train(B, N, steps, warmup=1, threads=None):
+    """The reference's training step on the host cores: its modules (train=True), its loss source (model.py:167-209),
+    torch autograd and torch.optim.AdamW (model.py:280).  Lightning only drives this loop upstream."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available() or not os.path.isfile(os.path.join(ref_shim.REF_DIR, "model.py")):
+        return None
+    import torch
+    from efficientspeech_b200.config import VARIANTS
+    from efficientspeech_b200.params import init_state_dict
+    threads = threads or cpu_threads()
+    torch.set_num_threads(threads)
+    cfg = VARIANTS["tiny"]
+    model = ref_shim.build_reference_model(cfg, init_state_dict(cfg, seed=0)).train()
+    fns, ns = ref_shim.reference_functions("model.py", ["loss"])
+    ns["nn"] = torch.nn
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-6)
+    batches = train_batches(cfg, B, N, 2, 0)
+    frames, dt = 0, 0.0
+    for i in range(warmup + steps):
+        b = batches[i % 2]
+        x = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in b.items() if k != "mel"}
+        T = int(b["mel_len"].max())
+        x["mel_mask"] = torch.from_numpy(np.arange(T)[None, :] >= b["mel_len"][:, None])
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        ls = fns["loss"](None, model(x, train=True), {"mel": torch.from_numpy(b["mel"])}, x)
+        (10. * ls[0] + 2. * ls[1] + 2. * ls[2] + ls[3]).backward()
+        opt.step()
+        if i >= warmup:
+            dt += time.perf_counter() - t0
+            frames += int(b["mel_len"].sum())
+    return {"value": frames / dt, "unit": "mel frames trained/s", "ms_per_step": dt / steps * 1e3, "cores": threads, "kind": "reference",
+            "sample": f"{steps} optimisation steps (+{warmup} warm-up) of {B} utterances x <= {N} phonemes (T ~ {T}) through the "
+                      f"unmodified reference modules + loss + torch autograd + torch.optim.AdamW (torch {torch.__version__} CPU, {threads} threads)"}
+
+
 def oracle_pass_parallel(batch, sd, workers):
     """One numpy-oracle forward over `batch`, utterances split across a thread pool."""
     from concurrent.futures import ThreadPoolExecutor
@@ -221,6 +271,7 @@ def run_reference_arm(a):
             r = time_reference_torch("base", 64, a.phonemes, a.duration, 3, 1)
             sub["base_b64_per_gpu"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ms_per_pass")}
         sub["tiny_b1_latency"] = time_reference_b1("tiny", a.phonemes, a.duration)
+        sub["tiny_train_b128_per_gpu"] = time_reference_train(32, a.phonemes, 2)
         line["configs"] = sub
         port = time_port(a.variant, a.phonemes, a.duration)
         line["cpu_port"] = port
@@ -726,6 +777,49 @@ def measure_hifigan(ctx, B, T, steps):
             "workload": f"HiFi-GAN V2 generator (hifigan/models.py:84-127), B={B} utterances of {T} mel frames, fp32, seeded weights"}
 
 
+def measure_train(ctx, B, N, steps, warmup=3):
+    """BASELINE configs[4]: the tiny training step (forward with a tape, the four losses, backward, gradient all-reduce
+    across ranks, AdamW), B utterances per GPU, data-parallel.  value = mel frames trained per second over all ranks."""
+    torch = ctx.torch
+    from efficientspeech_b200 import training
+    cfg, model = build_model_on(ctx, "tiny")
+    model.train()
+    step = training.TrainStep(model, lr=1e-3, weight_decay=1e-6, warmup_steps=50, total_steps=5000)
+    dev = ctx.dev
+    data = []
+    for b in train_batches(cfg, B, N, 4, 100 * ctx.rank):
+        x = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in b.items() if k != "mel"}
+        x["max_mel_len"] = int(b["mel_len"].max())
+        data.append((x, {"mel": torch.from_numpy(b["mel"]).to(dev)}, int(b["mel_len"].sum())))
+    it = [0]
+
+    def one():
+        x, y, _ = data[it[0] % len(data)]
+        it[0] += 1
+        return step(x, y)
+
+    first = one()
+    for _ in range(max(warmup, 2 * len(data)) - 1):     # every batch shape twice: the caching allocator must have seen them all
+        one()
+    it[0] = 0
+    ms = ctx.timed(one, steps)
+    last = one()
+    frames = sum(data[i % len(data)][2] for i in range(steps))
+    tot = torch.tensor([float(frames)], device=dev)
+    if ctx.world > 1:
+        ctx.dist.all_reduce(tot)
+    n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    rec = {"value": float(tot.item()) / (ms * 1e-3), "unit": "mel frames trained/s", "ms_per_step": ms / steps, "batch_per_gpu": B,
+           "global_batch": B * ctx.world, "frames_per_step_per_gpu": frames / steps, "params": n_params,
+           "loss_first_warmup_step": float(first[0]), "loss_after": float(last[0]),
+           "grad_allreduce": "one flat NCCL all-reduce of %d fp32 per step" % n_params if ctx.world > 1 else "none (1 GPU)",
+           "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+           "workload": f"tiny ES training step, {B} utterances per GPU x <= {N} phonemes (ragged), T ~ {data[0][0]['max_mel_len']} frames, "
+                       "fp32, synthetic LJSpeech-shaped batches; generic fp32 kernels + autograd tape (not the fused inference kernels)"}
+    del step, model
+    return rec
+
+
 def run_b200_arm(a):
     ctx = Ctx(a)
     torch, world, rank = ctx.torch, ctx.world, ctx.rank
@@ -765,6 +859,8 @@ def run_b200_arm(a):
         sub["tiny_free_running_ragged"] = measure_free_running(ctx, a, "tiny", 256, a.phonemes, a.duration, max(5, a.steps // 2))
         torch.cuda.empty_cache()
         sub["hifigan_v2_b16"] = measure_hifigan(ctx, 16, a.phonemes * a.duration, 3)
+        torch.cuda.empty_cache()
+        sub["tiny_train_b128_per_gpu"] = measure_train(ctx, 128, a.phonemes, 10)
 
     if rank != 0:
         if world > 1:

@@ -111,7 +111,8 @@ PROTOTYPES = {
     "es_loss_workspace_bytes": (_sz, []),
     "es_loss": (_i, [_vp, _i, _i, _i, _i] + [_vp] * 15 + [_vp, _sz]),
     "es_adamw_step": (_i, [_vp, _sz, _vp, _vp, _vp, _vp] + [C.c_float] * 7),
-    "es_t_gemm": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _ll, _i, _vp, _i, _ll, _i, _vp, _i, _ll, _vp, _i, _i]),
+    "es_t_gemm": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _ll, _i, _vp, _i, _ll, _i, _vp, _i, _ll, _vp, _i, _i, _i]),
+    "es_t_set_tensor_core": (None, [_i]),
     "es_t_im2col": (_i, [_vp, _vp, _vp] + [_i] * 7),
     "es_t_col2im": (_i, [_vp, _vp, _vp] + [_i] * 8),
     "es_t_dwconv_fwd": (_i, [_vp] * 5 + [_i] * 4),

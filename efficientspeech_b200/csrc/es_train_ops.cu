@@ -17,6 +17,7 @@
 //                              its adjoint (a segmented sum over each phoneme's frames: deterministic, no atomics)
 //   es_t_colsum      bias / LayerNorm-affine gradients; es_t_axpby, es_t_mask_rows, es_t_copy2d: glue
 #include "es_common.cuh"
+#include "es_kernels.cuh"
 
 namespace es {
 namespace {
@@ -460,13 +461,21 @@ inline int ln_bwd_blocks(long long rows) {
 using namespace es;
 #define ST static_cast<cudaStream_t>(stream)
 
+namespace { std::atomic<int> g_train_tc{1}; }
+
 extern "C" {
+
+void es_t_set_tensor_core(int enable) { g_train_tc.store(enable ? 1 : 0, std::memory_order_relaxed); }
 
 int es_t_gemm(void* stream, int batch, int M, int N, int K, const float* A, int lda, long long stride_a, int trans_a,
               const float* B, int ldb, long long stride_b, int trans_b, float* C, int ldc, long long stride_c,
-              const float* bias, int accumulate, int k_chunk) {
+              const float* bias, int accumulate, int k_chunk, int grad_mask) {
     ES_CHECK(A && B && C && batch >= 1 && M >= 1 && N >= 1 && K >= 1 && batch <= 65535 && k_chunk >= 0, "bad arguments");
     ES_CHECK(k_chunk == 0 || (long long)(batch - 1) * k_chunk < K, "split-K: empty slice");
+    if (g_train_tc.load(std::memory_order_relaxed) && !accumulate && (batch == 1 || k_chunk > 0)) {
+        const int rc = launch_train_gemm_tc(ST, batch, M, N, K, A, lda, trans_a, B, ldb, trans_b, C, ldc, stride_c, bias, k_chunk, grad_mask);
+        if (rc >= 0) return rc;
+    }
     dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT, batch);
     ES_CHECK(grid.y <= 65535, "M too large for one launch");
     t_gemm_kernel<<<grid, 256, 0, ST>>>(M, N, K, A, lda, stride_a, trans_a, B, ldb, stride_b, trans_b, C, ldc, stride_c, bias, accumulate,

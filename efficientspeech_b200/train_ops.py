@@ -25,7 +25,7 @@ from . import _cabi
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3
 
 __all__ = ["linear", "conv1d", "conv_transpose1d", "dwconv1d", "layernorm", "act", "embedding", "expand_rows",
-           "mask_rows", "add", "concat_channels", "attention_core", "bucketize", "ACT_RELU", "ACT_GELU", "ACT_TANH"]
+           "mask_rows", "add", "concat_channels", "attention_core", "bucketize", "set_tensor_core", "ACT_RELU", "ACT_GELU", "ACT_TANH"]
 
 
 # ------------------------------------------------------------------------------------------------ raw launches
@@ -51,10 +51,18 @@ def _p(t: Optional[torch.Tensor], offset: int = 0):
     return None if t is None else t.data_ptr() + 4 * offset
 
 
+GRAD_A, GRAD_B = 1, 2      # es_t_gemm grad_mask: the operand holds gradients (bf16 split on the tensor cores)
+
+
 def _gemm(A, B, C, M, N, K, lda, ldb, ldc, ta=False, tb=False, batch=1, sa=0, sb=0, sc=0, bias=None, acc=False, k_chunk=0,
-          a_off=0, b_off=0, c_off=0) -> None:
+          a_off=0, b_off=0, c_off=0, grad=0) -> None:
     _launch("es_t_gemm", C, batch, M, N, K, _p(A, a_off), lda, sa, int(ta), _p(B, b_off), ldb, sb, int(tb), _p(C, c_off), ldc, sc,
-            _p(bias), int(acc), k_chunk)
+            _p(bias), int(acc), k_chunk, grad)
+
+
+def set_tensor_core(enable: bool) -> None:
+    """True (default): the large GEMMs of the training step run on tcgen05 with split 16-bit operands; False: fp32 SIMT."""
+    _cabi.load().es_t_set_tensor_core(int(bool(enable)))
 
 
 def _scratch(n_floats: int, like: torch.Tensor) -> torch.Tensor:
@@ -66,18 +74,19 @@ def _colsum(A, Bm, out, rows, C, acc=False) -> None:
     _launch("es_t_colsum", out, _p(A), _p(Bm), _p(out), rows, C, int(acc), _p(ws), ws.numel())
 
 
-def _atb(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+def _atb(a: torch.Tensor, b: torch.Tensor, grad: int = 0) -> torch.Tensor:
     """a^T b for a [rows, M], b [rows, N] with rows >> M, N (a weight gradient): split-K partials, summed in order."""
     rows, M = a.shape
     N = b.shape[1]
-    chunk = max(256, -(-rows // 64))
+    chunk = max(256, -(-rows // 296))
+    chunk = -(-chunk // 32) * 32                      # the tensor-core kernel streams K in chunks of 32
     splits = -(-rows // chunk)
     if splits == 1:
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
-        _gemm(a, b, out, M, N, rows, M, N, N, ta=True)
+        _gemm(a, b, out, M, N, rows, M, N, N, ta=True, grad=grad)
         return out
     part = torch.empty(splits, M * N, dtype=torch.float32, device=a.device)
-    _gemm(a, b, part, M, N, rows, M, N, N, ta=True, batch=splits, sc=M * N, k_chunk=chunk)
+    _gemm(a, b, part, M, N, rows, M, N, N, ta=True, batch=splits, sc=M * N, k_chunk=chunk, grad=grad)
     out = torch.empty(M, N, dtype=torch.float32, device=a.device)
     _colsum(part, None, out, splits, M * N)
     return out
@@ -113,10 +122,10 @@ class _Linear(Function):
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(rows, K, dtype=torch.float32, device=dy.device)
-            _gemm(dy2, W, dx, rows, K, N, N, K, K)
+            _gemm(dy2, W, dx, rows, K, N, N, K, K, grad=GRAD_A)
             dx = dx.view(ctx.in_shape)
         if ctx.needs_input_grad[1]:
-            dW = _atb(dy2, x2)
+            dW = _atb(dy2, x2, GRAD_A)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _rowsum(dy2)
         return dx, dW, db
@@ -152,11 +161,11 @@ class _Conv1d(Function):
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dcols = torch.empty_like(cols)
-            _gemm(dy2, W, dcols, B * n_out, Cin * k, Cout, Cout, Cin * k, Cin * k)
+            _gemm(dy2, W, dcols, B * n_out, Cin * k, Cout, Cout, Cin * k, Cin * k, grad=GRAD_A)
             dx = torch.empty(B, n, Cin, dtype=torch.float32, device=dy.device)
             _launch("es_t_col2im", dx, _p(dcols), _p(dx), B, n, n_out, Cin, k, stride, padding, 0)
         if ctx.needs_input_grad[1]:
-            dW = _atb(dy2, cols).view(Cout, Cin, k)
+            dW = _atb(dy2, cols, GRAD_A).view(Cout, Cin, k)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _rowsum(dy2)
         return dx, dW, db, None, None
@@ -195,9 +204,9 @@ class _ConvTranspose1d(Function):
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, n_s, Cin, dtype=torch.float32, device=dy.device)
-            _gemm(dcols, W, dx, B * n_s, Cin, Cout * k, Cout * k, Cout * k, Cin, tb=True)
+            _gemm(dcols, W, dx, B * n_s, Cin, Cout * k, Cout * k, Cout * k, Cin, tb=True, grad=GRAD_A)
         if ctx.needs_input_grad[1]:
-            dW = _atb(x.reshape(B * n_s, Cin), dcols).view(Cin, Cout, k)
+            dW = _atb(x.reshape(B * n_s, Cin), dcols, GRAD_B).view(Cin, Cout, k)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _rowsum(dy.reshape(B * n_out, Cout))
         return dx, dW, db, None, None

@@ -374,7 +374,12 @@ int    es_adamw_step(void* stream, size_t n, float* param, const float* grad, fl
  * to C + b stride_c (weight gradients contract over every frame of the batch; es_t_colsum adds the partials in order). */
 int es_t_gemm(void* stream, int batch, int M, int N, int K, const float* A, int lda, long long stride_a, int trans_a,
               const float* B, int ldb, long long stride_b, int trans_b, float* C, int ldc, long long stride_c,
-              const float* bias, int accumulate, int k_chunk);
+              const float* bias, int accumulate, int k_chunk, int grad_mask);
+/* Products with N >= 16, K >= 16, M >= 32 (one matrix, or split-K) run on the tensor cores: each fp32 operand as two
+ * 16-bit halves, three tcgen05 MMAs per product, fp32 accumulation (csrc/es_train_gemm.cu).  grad_mask bit 0 / 1: A / B
+ * holds GRADIENTS; such a product splits both operands as bf16 pairs (fp32's exponent range) instead of fp16 pairs.  Everything else, and
+ * everything when switched off here, runs the fp32 SIMT kernel. */
+void es_t_set_tensor_core(int enable);
 /* cols[b, t, c*k + tau] = X[b, t*s + tau - p, c] (zero outside; a row is ordered like torch's flattened Conv1d weight),
  * and its adjoint (also ConvTranspose1d's forward scatter). */
 int es_t_im2col(void* stream, const float* X, float* cols, int B, int n_in, int n_out, int C, int k, int s, int p);

@@ -152,6 +152,31 @@ def test_mask_add_concat_bucketize():
     assert torch.equal(ops.bucketize(v.to(DEV), bins.to(DEV)).cpu().long(), torch.bucketize(v, bins))
 
 
+@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("M,N,K,ta,tb", [(300, 128, 128, 0, 1), (1000, 80, 128, 0, 1), (260, 384, 128, 0, 0), (128, 128, 5000, 1, 0),
+                                         (128, 96, 777, 1, 0), (500, 32, 48, 0, 1), (129, 272, 100, 1, 1)])
+def test_gemm_orientations_tensor_core_and_simt(M, N, K, ta, tb, tc):
+    """Every storage orientation of both operands, ragged M / N / K, activations (fp16 split) and gradient-sized values
+    (bf16 split: 1e-7 is below fp16's normal range), against float64."""
+    ops.set_tensor_core(tc)
+    try:
+        for grad, scale in ((0, 1.0), (ops.GRAD_A, 1e-7), (ops.GRAD_B, 1e-7)):
+            a = rnd(*((K, M) if ta else (M, K)), seed=1) * (scale if grad == ops.GRAD_A else 1.0)
+            b = rnd(*((N, K) if tb else (K, N)), seed=2) * (scale if grad == ops.GRAD_B else 1.0)
+            bias = rnd(N, seed=3) * scale
+            want = (a.double().T if ta else a.double()) @ (b.double().T if tb else b.double()) + bias.double()
+            A, Bm, out = a.to(DEV), b.to(DEV), torch.empty(M, N, device=DEV)
+            ops._gemm(A, Bm, out, M, N, K, a.shape[1], b.shape[1], N, ta=bool(ta), tb=bool(tb), bias=bias.to(DEV), grad=grad)
+            close(out, want, 5e-5, f"grad={grad}")
+        # split-K partials (the weight-gradient path)
+        if ta and not tb:
+            got = ops._atb(a.to(DEV), b.to(DEV), ops.GRAD_B)
+            close(got, a.double().T @ b.double(), 5e-5, "split-K")
+    finally:
+        ops.set_tensor_core(True)
+    es.Phoneme2Mel.check_async_errors(DEV)
+
+
 # ------------------------------------------------------------------------------------------------ whole network
 def mel_mask_of(batch, T):
     return torch.from_numpy(np.arange(T)[None, :] >= batch["mel_len"][:, None])
@@ -192,9 +217,19 @@ def spread_state(vname, seed):
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference sources not staged (oracle/build_ref.py)")
-@pytest.mark.parametrize("vname,B,N,seed", [("tiny", 3, 11, 0), ("tiny", 4, 128, 1), ("tiny", 3, 37, 2), ("small", 3, 40, 3),
-                                            ("base", 3, 24, 4), ("tiny", 1, 19, 5)])
-def test_network_gradients_match_reference_autograd(vname, B, N, seed):
+@pytest.mark.parametrize("vname,B,N,seed,tc", [("tiny", 3, 11, 0, True), ("tiny", 4, 128, 1, True), ("tiny", 3, 37, 2, True),
+                                               ("small", 3, 40, 3, True), ("base", 3, 24, 4, True), ("tiny", 1, 19, 5, True),
+                                               ("tiny", 4, 128, 1, False), ("base", 3, 24, 4, False)])
+def test_network_gradients_match_reference_autograd(vname, B, N, seed, tc):
+    ops.set_tensor_core(tc)
+    try:
+        _network_gradients(vname, B, N, seed)
+    finally:
+        ops.set_tensor_core(True)
+    es.Phoneme2Mel.check_async_errors(DEV)
+
+
+def _network_gradients(vname, B, N, seed):
     cfg = VARIANTS[vname]
     sd = spread_state(vname, seed)
     batch = make_batch(cfg, B, N, seed=seed, ragged=B > 1, fixed_duration=None)
