@@ -125,37 +125,57 @@ t_col2im_kernel(const float* __restrict__ cols, float* __restrict__ X, int B, in
 }
 
 // ----------------------------------------------------------------------------------------------------- depthwise conv
+// 4 consecutive floats; `aligned` (uniform per launch) selects the 16-byte access.  Parameters live at arbitrary element
+// offsets of the optimiser's flat buffer, and activations may be views, so alignment is a run-time property.
+__device__ __forceinline__ float4 ld4(const float* p, bool aligned) {
+    if (aligned) return __ldg(reinterpret_cast<const float4*>(p));
+    return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
+__device__ __forceinline__ void st4(float* p, float4 v, bool aligned) {
+    if (aligned) { *reinterpret_cast<float4*>(p) = v; return; }
+    p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+}
+__device__ __forceinline__ bool aligned16(const void* a, const void* b) {
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+// one thread = 4 channels of one frame (C % 4 == 0), 32-bit index arithmetic
 __global__ void __launch_bounds__(TB)
 t_dwconv_fwd_kernel(const float* __restrict__ X, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ Y,
                     int B, int T, int C, int k) {      // w [C][k] (torch [C,1,k])
-    const long long total = (long long)B * T * C;
-    const int p = k / 2;
-    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < total; i += (long long)gridDim.x * TB) {
-        const int c = (int)(i % C);
-        const long long row = i / C;
-        const int t = (int)(row % T);
-        float v = __ldg(bias + c);
+    const int C4 = C >> 2, total = B * T * C4, p = k / 2;
+    const bool al = aligned16(X, Y);
+    for (int i = blockIdx.x * TB + threadIdx.x; i < total; i += gridDim.x * TB) {
+        const int c = (i % C4) * 4, row = i / C4, t = row % T;
+        float4 v = ld4(bias + c, false);
         for (int tau = 0; tau < k; ++tau) {
             const int ti = t + tau - p;
-            if (ti >= 0 && ti < T) v = fmaf(__ldg(w + c * k + tau), __ldg(X + i + (long long)(tau - p) * C), v);
+            if (ti < 0 || ti >= T) continue;
+            const float4 x = ld4(X + (size_t)(row + tau - p) * C + c, al);
+            v.x = fmaf(__ldg(w + c * k + tau), x.x, v.x);
+            v.y = fmaf(__ldg(w + (c + 1) * k + tau), x.y, v.y);
+            v.z = fmaf(__ldg(w + (c + 2) * k + tau), x.z, v.z);
+            v.w = fmaf(__ldg(w + (c + 3) * k + tau), x.w, v.w);
         }
-        Y[i] = v;
+        st4(Y + (size_t)row * C + c, v, al);
     }
 }
 __global__ void __launch_bounds__(TB)
 t_dwconv_bwd_x_kernel(const float* __restrict__ dY, const float* __restrict__ w, float* __restrict__ dX, int B, int T, int C, int k) {
-    const long long total = (long long)B * T * C;
-    const int p = k / 2;
-    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < total; i += (long long)gridDim.x * TB) {
-        const int c = (int)(i % C);
-        const long long row = i / C;
-        const int ti = (int)(row % T);
-        float v = 0.f;
+    const int C4 = C >> 2, total = B * T * C4, p = k / 2;
+    const bool al = aligned16(dY, dX);
+    for (int i = blockIdx.x * TB + threadIdx.x; i < total; i += gridDim.x * TB) {
+        const int c = (i % C4) * 4, row = i / C4, ti = row % T;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int tau = 0; tau < k; ++tau) {
             const int t = ti - tau + p;                 // y[t] used x[t + tau - p]
-            if (t >= 0 && t < T) v = fmaf(__ldg(w + c * k + tau), __ldg(dY + i + (long long)(p - tau) * C), v);
+            if (t < 0 || t >= T) continue;
+            const float4 g = ld4(dY + (size_t)(row + p - tau) * C + c, al);
+            v.x = fmaf(__ldg(w + c * k + tau), g.x, v.x);
+            v.y = fmaf(__ldg(w + (c + 1) * k + tau), g.y, v.y);
+            v.z = fmaf(__ldg(w + (c + 2) * k + tau), g.z, v.z);
+            v.w = fmaf(__ldg(w + (c + 3) * k + tau), g.w, v.w);
         }
-        dX[i] = v;
+        st4(dX + (size_t)row * C + c, v, al);
     }
 }
 // dw[c][tau] = sum_{b,t} dY[b,t,c] X[b,t+tau-p,c]; db[c] = sum dY.  grid (ceil(C/32), S row slices); block = 32 channels x 8
@@ -302,20 +322,31 @@ __device__ __forceinline__ float act_f(float x, int kind) {
 }
 __global__ void __launch_bounds__(TB)
 t_act_fwd_kernel(const float* __restrict__ X, float* __restrict__ Y, long long n, int kind) {
-    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < n; i += (long long)gridDim.x * TB) Y[i] = act_f(X[i], kind);
+    const long long n4 = ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) ? 0 : n >> 2;
+    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < n4; i += (long long)gridDim.x * TB) {
+        float4 v = reinterpret_cast<const float4*>(X)[i];
+        v.x = act_f(v.x, kind); v.y = act_f(v.y, kind); v.z = act_f(v.z, kind); v.w = act_f(v.w, kind);
+        reinterpret_cast<float4*>(Y)[i] = v;
+    }
+    for (long long i = n4 * 4 + (long long)blockIdx.x * TB + threadIdx.x; i < n; i += (long long)gridDim.x * TB) Y[i] = act_f(X[i], kind);
+}
+__device__ __forceinline__ float act_df(float v, int kind) {
+    if (kind == ACT_RELU) return v > 0.f ? 1.f : 0.f;
+    if (kind == ACT_TANH) return 1.f - v * v;
+    if (kind == ACT_GELU) return 0.5f * (1.f + erff(v * 0.70710678118654752440f)) + v * 0.3989422804014327f * expf(-0.5f * v * v);
+    return 1.f;
 }
 // ReLU / tanh use the saved OUTPUT y, GELU the saved INPUT x
 __global__ void __launch_bounds__(TB)
 t_act_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ saved, float* __restrict__ dX, long long n, int kind) {
-    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < n; i += (long long)gridDim.x * TB) {
-        const float v = saved[i];
-        float d;
-        if (kind == ACT_RELU) d = v > 0.f ? 1.f : 0.f;
-        else if (kind == ACT_TANH) d = 1.f - v * v;
-        else if (kind == ACT_GELU) d = 0.5f * (1.f + erff(v * 0.70710678118654752440f)) + v * 0.3989422804014327f * expf(-0.5f * v * v);
-        else d = 1.f;
-        dX[i] = dY[i] * d;
+    const long long n4 = ((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(saved) | reinterpret_cast<uintptr_t>(dX)) & 15) ? 0 : n >> 2;
+    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < n4; i += (long long)gridDim.x * TB) {
+        const float4 g = reinterpret_cast<const float4*>(dY)[i], v = reinterpret_cast<const float4*>(saved)[i];
+        reinterpret_cast<float4*>(dX)[i] = make_float4(g.x * act_df(v.x, kind), g.y * act_df(v.y, kind), g.z * act_df(v.z, kind),
+                                                       g.w * act_df(v.w, kind));
     }
+    for (long long i = n4 * 4 + (long long)blockIdx.x * TB + threadIdx.x; i < n; i += (long long)gridDim.x * TB)
+        dX[i] = dY[i] * act_df(saved[i], kind);
 }
 
 // ------------------------------------------------------------------------------------------------------------ softmax
@@ -396,7 +427,12 @@ t_reduce_rows_kernel(const float* __restrict__ dOut, const int32_t* __restrict__
 // --------------------------------------------------------------------------------------------------------------- glue
 __global__ void __launch_bounds__(TB)
 t_axpby_kernel(const float* __restrict__ X, const float* __restrict__ Yin, float* __restrict__ out, long long n, float a, float b) {
-    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < n; i += (long long)gridDim.x * TB)
+    const long long n4 = (!Yin || ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Yin) | reinterpret_cast<uintptr_t>(out)) & 15)) ? 0 : n >> 2;
+    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < n4; i += (long long)gridDim.x * TB) {
+        const float4 x = reinterpret_cast<const float4*>(X)[i], y = reinterpret_cast<const float4*>(Yin)[i];
+        reinterpret_cast<float4*>(out)[i] = make_float4(a * x.x + b * y.x, a * x.y + b * y.y, a * x.z + b * y.z, a * x.w + b * y.w);
+    }
+    for (long long i = n4 * 4 + (long long)blockIdx.x * TB + threadIdx.x; i < n; i += (long long)gridDim.x * TB)
         out[i] = a * X[i] + (Yin ? b * Yin[i] : 0.f);
 }
 __global__ void __launch_bounds__(TB)
@@ -497,7 +533,8 @@ int es_t_col2im(void* stream, const float* cols, float* X, int B, int n_in, int 
 }
 int es_t_dwconv_fwd(void* stream, const float* X, const float* w, const float* bias, float* Y, int B, int T, int C, int k) {
     ES_CHECK(X && w && bias && Y, "null tensor");
-    t_dwconv_fwd_kernel<<<blocks_for((long long)B * T * C), TB, 0, ST>>>(X, w, bias, Y, B, T, C, k);
+    ES_CHECK(C % 4 == 0 && (long long)B * T * C < (1ll << 31), "depthwise conv: C must be a multiple of 4, B T C below 2^31");
+    t_dwconv_fwd_kernel<<<blocks_for((long long)B * T * C / 4), TB, 0, ST>>>(X, w, bias, Y, B, T, C, k);
     ES_LAUNCH_OK();
     return 0;
 }
@@ -509,7 +546,8 @@ int es_t_dwconv_bwd(void* stream, const float* dY, const float* X, const float* 
     ES_CHECK(dY && X && w && dX && dw && db && ws, "null tensor");
     ES_CHECK(k >= 1 && k <= DW_KMAX, "depthwise kernel size above 7");
     ES_CHECK(ws_floats >= es_t_dwconv_bwd_workspace_floats(B, T, C, k), "workspace too small");
-    t_dwconv_bwd_x_kernel<<<blocks_for((long long)B * T * C), TB, 0, ST>>>(dY, w, dX, B, T, C, k);
+    ES_CHECK(C % 4 == 0 && (long long)B * T * C < (1ll << 31), "depthwise conv: C must be a multiple of 4, B T C below 2^31");
+    t_dwconv_bwd_x_kernel<<<blocks_for((long long)B * T * C / 4), TB, 0, ST>>>(dY, w, dX, B, T, C, k);
     ES_LAUNCH_OK();
     const long long rows = (long long)B * T;
     const int S = slices_for(rows), W = C * (k + 1);

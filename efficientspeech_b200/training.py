@@ -103,8 +103,10 @@ class FusedAdamW:
             raise RuntimeError("FusedAdamW needs CUDA parameters (no CPU fallback)")
         dev = self.params[0].device
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        # every parameter starts on a 16-byte boundary of the flat buffer (kernels read weights with 128-bit loads when
+        # they can); the padding elements are zero and stay zero (zero gradient, zero moments)
+        n = sum(-(-p.numel() // 4) * 4 for p in self.params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
@@ -115,7 +117,7 @@ class FusedAdamW:
                 self.flat[off:off + k].copy_(p.detach().reshape(-1))
                 p.data = self.flat[off:off + k].view_as(p)
                 p.grad = self.flat_grad[off:off + k].view_as(p)
-                off += k
+                off += -(-k // 4) * 4
         self.t = 0
 
     def zero_grad(self):
@@ -267,8 +269,11 @@ class TrainStep:
     all-reduce -> ONE AdamW kernel.  Returns the five device scalars (total, mel, pitch, energy, duration); nothing
     synchronises the host."""
 
-    def __init__(self, model, lr: float = 1e-3, weight_decay: float = 1e-6, warmup_steps: int = 50, total_steps: int = 5000):
+    def __init__(self, model, lr: float = 1e-3, weight_decay: float = 1e-6, warmup_steps: int = 50, total_steps: int = 5000,
+                 use_graphs: bool = False):
         self.model = model
+        self.use_graphs = bool(use_graphs)
+        self._graphs, self._pool = {}, None
         # norm2 of the pitch / energy predictors never reaches an output (layers/networks.py:160-161: the head reads the
         # tensor BEFORE norm2, only the duration predictor's features use it): torch leaves their .grad None and AdamW
         # skips them, weight decay included -- so they stay out of the flat buffer here
@@ -278,8 +283,9 @@ class TrainStep:
         self.warmup_steps, self.total_steps = int(warmup_steps), int(total_steps)
         self.n = 0
 
-    def __call__(self, x: Dict[str, torch.Tensor], y: Dict[str, torch.Tensor]):
-        import torch.distributed as dist
+    def forward_backward(self, x: Dict[str, torch.Tensor], y: Dict[str, torch.Tensor]):
+        """Zero the flat gradient, run forward, loss and backward; returns (total, mel, pitch, energy, duration) device
+        scalars.  No host synchronisation when ``x["max_mel_len"]`` is given, so the whole call can be graph-captured."""
         self.opt.zero_grad()
         pred = forward_train(self.model, x)
         losses, g = loss(pred, y, x, with_grads=True)
@@ -287,8 +293,58 @@ class TrainStep:
         torch.autograd.backward(
             [pred["mel"], pred["pitch"], pred["energy"], pred["duration"]],
             [g["mel"], g["pitch"].view(B, N, 1), g["energy"].view(B, N, 1), g["duration"].view(B, N, 1)])
+        return (g["total"],) + tuple(losses)
+
+    def optimizer_step(self):
+        import torch.distributed as dist
         ddp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         # LambdaLR evaluates lr_lambda(0) at construction, so optimiser step k (0-based) runs at lr_lambda(k)
         self.opt.step(lr_scale=lr_lambda(self.n, self.warmup_steps, self.total_steps), allreduce=ddp)
         self.n += 1
-        return (g["total"],) + tuple(losses)
+
+    def __call__(self, x: Dict[str, torch.Tensor], y: Dict[str, torch.Tensor]):
+        if self.use_graphs:
+            return self._graphed(x, y)
+        out = self.forward_backward(x, y)
+        self.optimizer_step()
+        return out
+
+    # ---- CUDA-graph replay: a step is ~450 launches of 2-40 us kernels, and enqueueing them from Python takes longer
+    # than running them.  forward + loss + backward are captured once per batch geometry (B, N, T) and replayed; the
+    # all-reduce and the AdamW kernel stay outside the graph (the learning rate changes every step and NCCL keeps its own
+    # stream semantics).  Callers bucket T (pad the mel target, pass the bucket as x["max_mel_len"]) to bound the number
+    # of graphs; all graphs share one memory pool.
+    def _graphed(self, x, y):
+        if "max_mel_len" not in x:
+            raise RuntimeError("TrainStep(use_graphs=True) needs x['max_mel_len'] (python int): a captured step cannot "
+                               "read it back from the device")
+        key = (tuple(x["phoneme"].shape), int(x["max_mel_len"]), int(x.get("global_batch_size", x["phoneme"].shape[0])))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture(x, y)
+            self._graphs[key] = g
+        sx, sy, graph, out = g
+        for k, v in x.items():
+            if torch.is_tensor(v):
+                sx[k].copy_(v, non_blocking=True)
+        sy["mel"].copy_(y["mel"], non_blocking=True)
+        graph.replay()
+        self.optimizer_step()
+        return out
+
+    def _capture(self, x, y):
+        dev = x["phoneme"].device
+        sx = {k: (v.detach().to(dev).clone() if torch.is_tensor(v) else v) for k, v in x.items()}
+        sy = {"mel": y["mel"].detach().to(dev).clone()}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                     # warm-up off the capture: lazy allocations, function attributes
+            for _ in range(2):
+                self.forward_backward(sx, sy)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, pool=self._pool):
+            out = self.forward_backward(sx, sy)
+        return sx, sy, graph, out

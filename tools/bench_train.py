@@ -1,7 +1,10 @@
 """Time the training step (forward_train + loss + backward + AdamW) on synthetic LJSpeech-shaped batches and list the
 kernels by time share.  python tools/bench_train.py [B] [N] [steps]"""
+import os
 import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 import torch
@@ -65,6 +68,17 @@ if os.environ.get("ES_TRAIN_TC") == "0":
     e1.record()
     torch.cuda.synchronize()
     print(f"tensor-core GEMMs again: {e0.elapsed_time(e1) / steps:.2f} ms/step")
+gstep = training.TrainStep(m, use_graphs=True)
+gstep.opt = step.opt            # same flat buffers
+for i in range(8):
+    out = gstep(*batches[i % 4][:2])
+torch.cuda.synchronize()
+e0.record()
+for i in range(steps):
+    out = gstep(*batches[i % 4][:2])
+e1.record()
+torch.cuda.synchronize()
+print(f"graph replay (forward+loss+backward), eager AdamW: {e0.elapsed_time(e1) / steps:.2f} ms/step, loss {float(out[0]):.4f}")
 # host-only cost of a step: enqueue without waiting (the queue is deep enough for one step)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
