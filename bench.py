@@ -814,11 +814,18 @@ def measure_train(ctx, B, N, steps, warmup=3):
     if ctx.world > 1:
         ctx.dist.all_reduce(tot)
     n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    # data-parallel sanity: after the same averaged gradients every rank must hold bit-identical weights
+    chk = step.opt.flat.double().sum().reshape(1)
+    lo, hi = chk.clone(), chk.clone()
+    if ctx.world > 1:
+        ctx.dist.all_reduce(lo, op=ctx.dist.ReduceOp.MIN)
+        ctx.dist.all_reduce(hi, op=ctx.dist.ReduceOp.MAX)
     rec = {"value": float(tot.item()) / (ms * 1e-3), "unit": "mel frames trained/s", "ms_per_step": ms / steps, "ms_per_step_eager": ms_eager / steps,
            "launch_mode": "CUDA-graph replay of forward + loss + backward (one graph per batch geometry); all-reduce and AdamW eager",
            "batch_per_gpu": B, "global_batch": B * ctx.world, "frames_per_step_per_gpu": frames / steps, "params": n_params,
            "loss_first_warmup_step": float(first[0]), "loss_after": float(last[0]),
            "grad_allreduce": "one flat NCCL all-reduce of %d fp32 per step" % n_params if ctx.world > 1 else "none (1 GPU)",
+           "replicas_in_sync": bool(float(lo.item()) == float(hi.item())),
            "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
            "workload": f"tiny ES training step, {B} utterances per GPU x <= {N} phonemes (ragged), T ~ {data[0][0]['max_mel_len']} frames, "
                        "fp32, synthetic LJSpeech-shaped batches; generic fp32 kernels + autograd tape (not the fused inference kernels)"}
