@@ -8,7 +8,7 @@ from typing import Optional
 
 from . import build as _build
 
-ES_ABI_VERSION = 12
+ES_ABI_VERSION = 13
 ES_GATHER_MATERIALIZE, ES_GATHER_FUSED = 1, 2
 ES_MAX_ENC_BLOCKS = 2
 ES_MAX_DEC_LAYERS = 24
@@ -136,6 +136,7 @@ PROTOTYPES = {
     "es_t_mask_rows": (_i, [_vp] * 4 + [_ll, _i]),
     "es_t_copy2d": (_i, [_vp, _vp, _i, _vp, _i, _ll, _i, _i]),
     "es_selftest_umma_gemm": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "es_selftest_attention": (_i, [_vp, _i, _i, _i, _i, C.c_float, _vp, _vp, _i]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -272,6 +272,15 @@ bool decoder_all_umma128(const es_model* m);
 extern "C" {
 
 int es_abi_version(void) { return ES_ABI_VERSION; }
+
+int es_selftest_attention(void* stream, int B, int n, int C, int H, float scale, const float* qkv, float* out, int tensor_core) {
+    ES_CHECK(qkv && out && B >= 1 && n >= 1 && C >= 1 && H >= 1, "bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!tensor_core) return es::launch_attention(qkv, out, B, n, C, H, scale, s);
+    const int rc = es::launch_umma_attention(qkv, out, B, n, C, H, scale, s);
+    if (rc < 0) { es::set_error("es_selftest_attention: shape outside the tcgen05 attention envelope"); return 2; }
+    return rc;
+}
 const char* es_last_error(void) { return es::g_error.c_str(); }
 uint64_t es_launch_count(void) { return es::g_launches.load(); }
 int es_debug_set_trace(void* dev_buf_i64) { es::umma_dec_set_trace(static_cast<long long*>(dev_buf_i64)); return 0; }

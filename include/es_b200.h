@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ES_ABI_VERSION 12
+#define ES_ABI_VERSION 13
 #define ES_MAX_ENC_BLOCKS 2
 #define ES_MAX_DEC_LAYERS 24
 #define ES_MAX_DEC_BLOCKS 8
@@ -304,6 +304,11 @@ int es_profile_collect(int32_t* kinds_host, float* ms_host, int capacity, int* n
 /* Self-test of the tcgen05/TMA building block: C[M,N] = A[M,K] B[N,K]^T with split-fp16
  * operands (3 MMAs), M multiple of 128, N in {128,256}, K multiple of 64.  fp32 in/out. */
 int es_selftest_umma_gemm(void* stream, int M, int N, int K, const float* A, const float* Bm, float* C);
+/* The attention core of one encoder block in isolation (layers/blocks.py:44-63: softmax(scale q k^T) v over ALL n keys,
+ * every head full width C): qkv [B,n,3*H*C] -> out [B,n,H*C].  tensor_core != 0: the tcgen05 kernels (C in {32, 64} with
+ * n <= 128; C = 128 with n <= 128; C = 256 with n <= 64) -- returns 2 when the shape is outside their envelope;
+ * tensor_core == 0: the fp32 SIMT kernel. */
+int es_selftest_attention(void* stream, int B, int n, int C, int H, float scale, const float* qkv, float* out, int tensor_core);
 
 /* =====================================================================================================================
  * HiFi-GAN generator -- the step AFTER the acoustic path.
