@@ -8,7 +8,7 @@ from typing import Optional
 
 from . import build as _build
 
-ES_ABI_VERSION = 13
+ES_ABI_VERSION = 14
 ES_GATHER_MATERIALIZE, ES_GATHER_FUSED = 1, 2
 ES_MAX_ENC_BLOCKS = 2
 ES_MAX_DEC_LAYERS = 24
@@ -28,7 +28,8 @@ class es_config_t(C.Structure):
 class es_enc_block_w_t(C.Structure):
     _fields_ = [(n, _fp) for n in (
         "merge_w", "qkv_w", "proj_w", "proj_b", "ln1_g", "ln1_b", "ffn1_w", "ffn1_tapb", "ffn1_b",
-        "ffn2_w", "ffn2_b", "ln2_g", "ln2_b", "merge_w_h16", "qkv_w_h16", "proj_w_h16", "ffn1_w_h16", "ffn2_w_h16")]
+        "ffn2_w", "ffn2_b", "ln2_g", "ln2_b", "merge_w_h16", "qkv_w_h16", "proj_w_h16", "ffn1_w_h16", "ffn2_w_h16",
+        "merge2_w", "merge2_w_h16")]
 
 
 class es_predictor_w_t(C.Structure):

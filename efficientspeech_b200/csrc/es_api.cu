@@ -424,8 +424,15 @@ int es_encoder_forward(es_model_t* m, void* stream, int B, int N,
     {
         RowGemmParams p = base_params(B, N, n1, m->C[0], m->C[1], e.feat0, m->C[0], m->w.enc[1].merge_w, e.xm1, m->C[1]);
         p.taps = m->k[1]; p.stride = 2; p.pad = m->k[1] / 2;
+        const void* img = m->w.enc[1].merge_w_h16;
+        if (m->use_tensor_core && m->w.enc[1].merge2_w_h16 && m->k[1] == 3 && N % 2 == 0 && n1 == N / 2) {
+            // paired rows: [N][C] read as [N/2][2C], stride-1 conv with K = 2C (es_b200.h: merge2_w)
+            p = base_params(B, N / 2, n1, 2 * m->C[0], m->C[1], e.feat0, 2 * m->C[0], m->w.enc[1].merge2_w, e.xm1, m->C[1]);
+            p.taps = 3; p.stride = 1; p.pad = 1;
+            img = m->w.enc[1].merge2_w_h16;
+        }
         ProfRange r(ES_K_ENC_GEMM, s);
-        if (gemm(m, p, m->w.enc[1].merge_w_h16, s)) return 1;
+        if (gemm(m, p, img, s)) return 1;
     }
     const uint8_t* mask1 = nullptr;
     if (phoneme_mask) {

@@ -193,6 +193,12 @@ class _Backend:
                 ci, hi, hci = c.enc_dims[i], c.enc_heads[i], c.enc_dims[i] * c.expansion
                 if i == 1:
                     folded["enc1.merge_w_h16"] = image("enc1.merge_w", ci, stride=2)
+                    wm = folded["enc1.merge_w"]                     # [k'][Cin][C_padded]
+                    if wm.shape[0] == 3 and lib.es_dense_layout(int(wm.shape[1]), int(ci), 3, 2) == 0 \
+                            and lib.es_dense_layout(2 * int(wm.shape[1]), int(ci), 3, 1) >= 2:
+                        # no strided tensor-core form for 3 taps (base): the same conv over paired rows (es_b200.h)
+                        folded["enc1.merge2_w"] = packing.pair_stride2_taps(wm)
+                        folded["enc1.merge2_w_h16"] = image("enc1.merge2_w", ci)
                 folded[f"enc{i}.qkv_w_h16"] = image(f"enc{i}.qkv_w", 3 * hi * ci)
                 folded[f"enc{i}.proj_w_h16"] = image(f"enc{i}.proj_w", ci)
                 folded[f"enc{i}.ffn1_w_h16"] = image(f"enc{i}.ffn1_w", hci)

@@ -188,6 +188,18 @@ def canon_split_units(w_tkn: np.ndarray, n: int, nt: int, kc: int = 32) -> np.nd
     return np.concatenate(out)
 
 
+def pair_stride2_taps(w_tkn: np.ndarray) -> np.ndarray:
+    """A 3-tap stride-2 conv [3][K][N] as a 3-tap stride-1 "same" conv over paired rows X2[t] = [x[2t] | x[2t+1]]:
+    y[t] = W0 x[2t-1] + W1 x[2t] + W2 x[2t+1] = [0 | W0] X2[t-1] + [W1 | W2] X2[t]  ->  [3][2K][N], third tap zero."""
+    assert w_tkn.shape[0] == 3
+    _, k, n = w_tkn.shape
+    out = np.zeros((3, 2 * k, n), dtype=w_tkn.dtype)
+    out[0, k:] = w_tkn[0]
+    out[1, :k] = w_tkn[1]
+    out[1, k:] = w_tkn[2]
+    return out
+
+
 def pack(folded: Dict[str, np.ndarray]) -> Tuple[np.ndarray, Dict[str, int]]:
     """Concatenate the folded arrays (fp32, 256-byte aligned) -> (flat buffer, element offsets)."""
     offsets: Dict[str, int] = {}

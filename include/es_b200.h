@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ES_ABI_VERSION 13
+#define ES_ABI_VERSION 14
 #define ES_MAX_ENC_BLOCKS 2
 #define ES_MAX_DEC_LAYERS 24
 #define ES_MAX_DEC_BLOCKS 8
@@ -77,6 +77,13 @@ typedef struct es_enc_block_w {
     const void*  proj_w_h16;
     const void*  ffn1_w_h16;
     const void*  ffn2_w_h16;
+    /* block 1, merge conv with 3 taps and stride 2 (base: kernel_size 5 -> k' = 3): the same conv over PAIRED rows.
+     * With X2[t] = [x[2t] | x[2t+1]] (a free view of [n][C] as [n/2][2C], n even),
+     *   y[t] = W0 x[2t-1] + W1 x[2t] + W2 x[2t+1] = [0 | W0] X2[t-1] + [W1 | W2] X2[t]
+     * is a stride-1 "same" conv with K = 2C, which the streamed-weight tcgen05 kernel runs (es_umma_wide.cu has no
+     * strided form).  [3][2 Cin][C] (third tap zero) and its split-fp16 units; NULL -> strided fp32 SIMT kernel. */
+    const float* merge2_w;
+    const void*  merge2_w_h16;
 } es_enc_block_w_t;
 
 typedef struct es_predictor_w {     /* AcousticDecoder, networks.py:98-122,151-165 */

@@ -82,3 +82,21 @@ def test_streamed_units_image_order():
             for t in range(taps):
                 ref = packing.canon_split_fp16(np.ascontiguousarray(w[t, c * 32:(c + 1) * 32, y * nt:(y + 1) * nt].T))
                 assert np.array_equal(img[y, c, t], ref.view(np.float16))
+
+
+def test_pair_stride2_taps_is_the_same_convolution():
+    """The paired-row form of a 3-tap stride-2 conv (base, encoder block 1 merge): a stride-1 'same' conv over
+    X2[t] = [x[2t] | x[2t+1]] with K doubled must give the strided conv's output."""
+    import numpy as np
+    from efficientspeech_b200 import packing
+    rng = np.random.default_rng(5)
+    n, K, N = 12, 6, 4
+    x = rng.standard_normal((n, K))
+    w = rng.standard_normal((3, K, N))
+    xp = np.concatenate([np.zeros((1, K)), x, np.zeros((1, K))])
+    want = np.stack([sum(xp[2 * t + tau] @ w[tau] for tau in range(3)) for t in range(n // 2)])      # pad 1, stride 2
+    w2 = packing.pair_stride2_taps(w)
+    x2 = x.reshape(n // 2, 2 * K)
+    x2p = np.concatenate([np.zeros((1, 2 * K)), x2, np.zeros((1, 2 * K))])
+    got = np.stack([sum(x2p[t + tau] @ w2[tau] for tau in range(3)) for t in range(n // 2)])           # pad 1, stride 1
+    assert np.abs(got - want).max() < 1e-12
