@@ -61,32 +61,46 @@ __device__ __forceinline__ void split8_wide(const float (&v)[8], uint4& hi, uint
 
 // Stage `rows_pad` rows x KC of one operand.  Element (r, k) of the operand is src[r * ld + k] (rowmajor) or
 // src[k * ld + r] (transposed storage); r in [r0, r0 + rows_pad) valid below r_end, k in [k0, k0 + KC) valid below k_end.
+// The loads of UNROLL items (2 x 16 bytes or 8 x 4 bytes each) are all issued before the first conversion: with 12
+// resident warps per SM the kernel lives on memory-level parallelism per thread, not on occupancy (the first version
+// converted item by item and sat at 11 % of DRAM bandwidth, stalled on long_scoreboard; profiles/r02_ncu_train_gemm.txt).
 template <bool WIDE>
 __device__ __forceinline__ void stage_operand(const float* __restrict__ src, int ld, bool transposed, int r0, int r_end, int k0, int k_end,
                                               int rows_pad, uint8_t* hi_base, uint8_t* lo_base, int tid, bool vec_ok) {
+    constexpr int UNROLL = 4;
     const int items = rows_pad * (KC / 8);
-    for (int idx = tid; idx < items; idx += 128) {
-        int r, kc;
-        if (transposed) { r = idx % rows_pad; kc = idx / rows_pad; }      // lanes along r: coalesced for [k][r] storage
-        else            { kc = idx & 3; r = idx >> 2; }                   // 4 lanes cover 128 contiguous bytes of a row
-        const int gr = r0 + r, gk = k0 + kc * 8;
-        float v[8];
-        if (gr < r_end && !transposed && vec_ok && gk + 8 <= k_end) {
-            const float4* p = reinterpret_cast<const float4*>(src + (size_t)gr * ld + gk);
-            const float4 a = __ldg(p), b = __ldg(p + 1);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
+    for (int base = 0; base < items; base += UNROLL * 128) {
+        float v[UNROLL][8];
+        uint32_t off[UNROLL];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int k = gk + i;
-                v[i] = (gr < r_end && k < k_end) ? __ldg(transposed ? src + (size_t)k * ld + gr : src + (size_t)gr * ld + k) : 0.f;
+        for (int u = 0; u < UNROLL; ++u) {
+            const int idx = base + u * 128 + tid;
+            int r, kc;
+            if (transposed) { r = idx % rows_pad; kc = idx / rows_pad; }      // lanes along r: coalesced for [k][r] storage
+            else            { kc = idx & 3; r = idx >> 2; }                   // 4 lanes cover 128 contiguous bytes of a row
+            off[u] = idx < items ? canon_off(r, kc, rows_pad) : 0xffffffffu;
+            const int gr = r0 + r, gk = k0 + kc * 8;
+            if (idx < items && gr < r_end && !transposed && vec_ok && gk + 8 <= k_end) {
+                const float4* p = reinterpret_cast<const float4*>(src + (size_t)gr * ld + gk);
+                const float4 a = __ldg(p), b = __ldg(p + 1);
+                v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = gk + i;
+                    v[u][i] = (idx < items && gr < r_end && k < k_end)
+                                  ? __ldg(transposed ? src + (size_t)k * ld + gr : src + (size_t)gr * ld + k) : 0.f;
+                }
             }
         }
-        uint4 hi, lo;
-        if (WIDE) split8_wide(v, hi, lo); else split8(v, hi, lo);
-        const uint32_t off = canon_off(r, kc, rows_pad);
-        *reinterpret_cast<uint4*>(hi_base + off) = hi;
-        *reinterpret_cast<uint4*>(lo_base + off) = lo;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (off[u] == 0xffffffffu) continue;
+            uint4 hi, lo;
+            if (WIDE) split8_wide(v[u], hi, lo); else split8(v[u], hi, lo);
+            *reinterpret_cast<uint4*>(hi_base + off[u]) = hi;
+            *reinterpret_cast<uint4*>(lo_base + off[u]) = lo;
+        }
     }
 }
 

@@ -178,6 +178,105 @@ t_dwconv_bwd_x_kernel(const float* __restrict__ dY, const float* __restrict__ w,
         st4(dX + (size_t)row * C + c, v, al);
     }
 }
+// ---- sliding-window forms (k known at compile time): every input row is loaded ONCE ---------------------------------
+__device__ __forceinline__ float4 fma4(float4 w, float4 x, float4 a) {
+    return make_float4(fmaf(w.x, x.x, a.x), fmaf(w.y, x.y, a.y), fmaf(w.z, x.z, a.z), fmaf(w.w, x.w, a.w));
+}
+// Y[b,t,c] = bias[c] + sum_tau w[c][flip ? K-1-tau : tau] X[b,t+tau-p,c].  One thread = 4 channels x RB consecutive frames
+// of one utterance: RB + K - 1 row loads for RB outputs instead of RB K.  flip (with bias == nullptr) is the input
+// gradient: dX = conv(dY, reversed taps).
+template <int K, int RB>
+__global__ void __launch_bounds__(TB)
+t_dwconv_win_kernel(const float* __restrict__ X, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ Y,
+                    int B, int T, int C, int flip) {
+    constexpr int P = K / 2;
+    const int C4 = C >> 2, tiles = (T + RB - 1) / RB, total = B * tiles * C4;
+    const bool al = aligned16(X, Y);
+    for (int i = blockIdx.x * TB + threadIdx.x; i < total; i += gridDim.x * TB) {
+        const int c = (i % C4) * 4, bt = i / C4, b = bt / tiles, t0 = (bt - b * tiles) * RB;
+        float4 wt[K];
+#pragma unroll
+        for (int tau = 0; tau < K; ++tau) {
+            const int s = flip ? K - 1 - tau : tau;
+            wt[tau] = make_float4(__ldg(w + c * K + s), __ldg(w + (c + 1) * K + s), __ldg(w + (c + 2) * K + s), __ldg(w + (c + 3) * K + s));
+        }
+        float4 acc[RB];
+        const float4 b4 = bias ? ld4(bias + c, false) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int o = 0; o < RB; ++o) acc[o] = b4;
+        const float* xb = X + (size_t)b * T * C + c;
+#pragma unroll
+        for (int j = 0; j < RB + K - 1; ++j) {
+            const int t = t0 + j - P;
+            if (t < 0 || t >= T) continue;
+            const float4 x = ld4(xb + (size_t)t * C, al);
+#pragma unroll
+            for (int o = 0; o < RB; ++o) {
+                const int tau = j - o;                  // output t0 + o reads row t0 + o + tau - P
+                if (tau >= 0 && tau < K) acc[o] = fma4(wt[tau], x, acc[o]);
+            }
+        }
+        float* yb = Y + (size_t)b * T * C + c;
+#pragma unroll
+        for (int o = 0; o < RB; ++o)
+            if (t0 + o < T) st4(yb + (size_t)(t0 + o) * C, acc[o], al);
+    }
+}
+// Weight / bias gradient partials.  grid (ceil(C/128), slices); block = 32 lanes x 4 channels, 8 row lanes; a row lane
+// walks its contiguous share of the slice frame by frame with the K input rows of the current frame in registers.
+template <int K>
+__global__ void __launch_bounds__(256)
+t_dwconv_bwd_w_win_kernel(const float* __restrict__ dY, const float* __restrict__ X, float* __restrict__ part, int B, int T, int C,
+                          int rows_per_slice) {
+    constexpr int P = K / 2;
+    __shared__ float4 red[8][32];
+    const int cl = threadIdx.x & 31, c = (blockIdx.x * 32 + cl) * 4, lane_r = threadIdx.x >> 5;
+    const int rows = B * T;
+    const int s0 = blockIdx.y * rows_per_slice, s1 = min(rows, s0 + rows_per_slice);
+    const int per = (s1 - s0 + 7) / 8;
+    const int r0 = s0 + lane_r * per, r1 = min(s1, r0 + per);
+    const bool al = aligned16(dY, X);
+    float4 acc[K + 1], win[K];
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i <= K; ++i) acc[i] = z;
+    if (c < C && r0 < r1) {
+        int t = r0 % T;
+        // win[tau] = X[row + tau - P] (zero outside the utterance); filled at the start and whenever an utterance begins
+        bool refill = true;
+        for (int row = r0; row < r1; ++row) {
+            if (refill) {
+#pragma unroll
+                for (int tau = 0; tau < K - 1; ++tau) {
+                    const int ti = t + tau - P;
+                    win[tau + 1] = (ti >= 0 && ti < T) ? ld4(X + (size_t)(row + tau - P) * C + c, al) : z;
+                }
+                refill = false;
+            }
+#pragma unroll
+            for (int tau = 0; tau < K - 1; ++tau) win[tau] = win[tau + 1];
+            win[K - 1] = (t + P < T) ? ld4(X + (size_t)(row + P) * C + c, al) : z;
+            const float4 g = ld4(dY + (size_t)row * C + c, al);
+            acc[K].x += g.x; acc[K].y += g.y; acc[K].z += g.z; acc[K].w += g.w;
+#pragma unroll
+            for (int tau = 0; tau < K; ++tau) acc[tau] = fma4(g, win[tau], acc[tau]);
+            if (++t == T) { t = 0; refill = true; }
+        }
+    }
+    // block reduction over the 8 row lanes, one tap at a time, in a fixed order
+    for (int i = 0; i <= K; ++i) {
+        red[lane_r][cl] = acc[i];
+        __syncthreads();
+        if (lane_r == 0 && c < C) {
+            float4 tsum = z;
+            for (int r = 0; r < 8; ++r) { const float4 v = red[r][cl]; tsum.x += v.x; tsum.y += v.y; tsum.z += v.z; tsum.w += v.w; }
+            float* out = part + ((size_t)blockIdx.y * C + c) * (K + 1) + i;
+            out[0] = tsum.x; out[K + 1] = tsum.y; out[2 * (K + 1)] = tsum.z; out[3 * (K + 1)] = tsum.w;
+        }
+        __syncthreads();
+    }
+}
+
 // dw[c][tau] = sum_{b,t} dY[b,t,c] X[b,t+tau-p,c]; db[c] = sum dY.  grid (ceil(C/32), S row slices); block = 32 channels x 8
 // row lanes; every thread keeps the k taps + the bias sum in registers and the block writes ONE partial row
 // part[slice][c (k+1) + tau] -- the slices are added afterwards in a fixed order (t_colsum_kernel), so the result does not
@@ -534,12 +633,22 @@ int es_t_col2im(void* stream, const float* cols, float* X, int B, int n_in, int 
 int es_t_dwconv_fwd(void* stream, const float* X, const float* w, const float* bias, float* Y, int B, int T, int C, int k) {
     ES_CHECK(X && w && bias && Y, "null tensor");
     ES_CHECK(C % 4 == 0 && (long long)B * T * C < (1ll << 31), "depthwise conv: C must be a multiple of 4, B T C below 2^31");
-    t_dwconv_fwd_kernel<<<blocks_for((long long)B * T * C / 4), TB, 0, ST>>>(X, w, bias, Y, B, T, C, k);
+    constexpr int RB = 8;
+    const long long work = (long long)B * ((T + RB - 1) / RB) * (C / 4);
+    if (k == 3)      t_dwconv_win_kernel<3, RB><<<blocks_for(work), TB, 0, ST>>>(X, w, bias, Y, B, T, C, 0);
+    else if (k == 5) t_dwconv_win_kernel<5, RB><<<blocks_for(work), TB, 0, ST>>>(X, w, bias, Y, B, T, C, 0);
+    else if (k == 7) t_dwconv_win_kernel<7, RB><<<blocks_for(work), TB, 0, ST>>>(X, w, bias, Y, B, T, C, 0);
+    else             t_dwconv_fwd_kernel<<<blocks_for((long long)B * T * C / 4), TB, 0, ST>>>(X, w, bias, Y, B, T, C, k);
     ES_LAUNCH_OK();
     return 0;
 }
+// slices of the depthwise weight-gradient reduction: 256 frames each (8 row lanes x 32), at most 1024
+static int dw_slices(long long rows) {
+    long long sl = (rows + 255) / 256;
+    return (int)(sl < 1 ? 1 : (sl > 1024 ? 1024 : sl));
+}
 size_t es_t_dwconv_bwd_workspace_floats(int B, int T, int C, int k) {
-    return (size_t)(slices_for((long long)B * T) + 1) * C * (k + 1);
+    return (size_t)(dw_slices((long long)B * T) + 1) * C * (k + 1);
 }
 int es_t_dwconv_bwd(void* stream, const float* dY, const float* X, const float* w, float* dX, float* dw, float* db, int B, int T, int C, int k,
                     float* ws, size_t ws_floats) {
@@ -547,12 +656,22 @@ int es_t_dwconv_bwd(void* stream, const float* dY, const float* X, const float* 
     ES_CHECK(k >= 1 && k <= DW_KMAX, "depthwise kernel size above 7");
     ES_CHECK(ws_floats >= es_t_dwconv_bwd_workspace_floats(B, T, C, k), "workspace too small");
     ES_CHECK(C % 4 == 0 && (long long)B * T * C < (1ll << 31), "depthwise conv: C must be a multiple of 4, B T C below 2^31");
-    t_dwconv_bwd_x_kernel<<<blocks_for((long long)B * T * C / 4), TB, 0, ST>>>(dY, w, dX, B, T, C, k);
+    constexpr int RB = 8;
+    const long long work = (long long)B * ((T + RB - 1) / RB) * (C / 4);
+    if (k == 3)      t_dwconv_win_kernel<3, RB><<<blocks_for(work), TB, 0, ST>>>(dY, w, nullptr, dX, B, T, C, 1);
+    else if (k == 5) t_dwconv_win_kernel<5, RB><<<blocks_for(work), TB, 0, ST>>>(dY, w, nullptr, dX, B, T, C, 1);
+    else if (k == 7) t_dwconv_win_kernel<7, RB><<<blocks_for(work), TB, 0, ST>>>(dY, w, nullptr, dX, B, T, C, 1);
+    else             t_dwconv_bwd_x_kernel<<<blocks_for((long long)B * T * C / 4), TB, 0, ST>>>(dY, w, dX, B, T, C, k);
     ES_LAUNCH_OK();
     const long long rows = (long long)B * T;
-    const int S = slices_for(rows), W = C * (k + 1);
+    const int S = dw_slices(rows), W = C * (k + 1);
+    const int per_slice = (int)((rows + S - 1) / S);
     float* sum = ws + (size_t)S * W;
-    t_dwconv_bwd_w_kernel<<<dim3((C + 31) / 32, S), 256, 0, ST>>>(dY, X, ws, B, T, C, k, (rows + S - 1) / S);
+    const dim3 gw((C / 4 + 31) / 32, S);
+    if (k == 3)      t_dwconv_bwd_w_win_kernel<3><<<gw, 256, 0, ST>>>(dY, X, ws, B, T, C, per_slice);
+    else if (k == 5) t_dwconv_bwd_w_win_kernel<5><<<gw, 256, 0, ST>>>(dY, X, ws, B, T, C, per_slice);
+    else if (k == 7) t_dwconv_bwd_w_win_kernel<7><<<gw, 256, 0, ST>>>(dY, X, ws, B, T, C, per_slice);
+    else             t_dwconv_bwd_w_kernel<<<dim3((C + 31) / 32, S), 256, 0, ST>>>(dY, X, ws, B, T, C, k, per_slice);
     ES_LAUNCH_OK();
     t_colsum_kernel<<<dim3((W + 31) / 32, 1), 256, 0, ST>>>(ws, nullptr, sum, S, W, 0, S, W);
     ES_LAUNCH_OK();
