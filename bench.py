@@ -820,11 +820,19 @@ def measure_train(ctx, B, N, steps, warmup=3):
     if ctx.world > 1:
         ctx.dist.all_reduce(lo, op=ctx.dist.ReduceOp.MIN)
         ctx.dist.all_reduce(hi, op=ctx.dist.ReduceOp.MAX)
+    # multiply-accumulates of one forward: every weight matrix times the positions it is applied at (decoder: frames;
+    # phoneme side: phonemes, block 1 at half length); a training step is ~3 forwards' worth (forward, dX, dW)
+    dec_w = sum(p.numel() for n_, p in model.decoder.named_parameters() if p.dim() >= 2)
+    enc_w = sum(p.numel() for n_, p in model.encoder.named_parameters() if p.dim() >= 2 and "embed" not in n_)
+    phon = sum(float(d[0]["phoneme_len"].sum()) for d in data) / len(data)
+    gflop = 6.0 * (dec_w * frames / steps + enc_w * phon) / 1e9
     rec = {"value": float(tot.item()) / (ms * 1e-3), "unit": "mel frames trained/s", "ms_per_step": ms / steps, "ms_per_step_eager": ms_eager / steps,
            "launch_mode": "CUDA-graph replay of forward + loss + backward (one graph per batch geometry); all-reduce and AdamW eager",
            "batch_per_gpu": B, "global_batch": B * ctx.world, "frames_per_step_per_gpu": frames / steps, "params": n_params,
            "loss_first_warmup_step": float(first[0]), "loss_after": float(last[0]),
            "grad_allreduce": "one flat NCCL all-reduce of %d fp32 per step" % n_params if ctx.world > 1 else "none (1 GPU)",
+           "gflop_per_step_per_gpu": gflop, "achieved_tflops_per_gpu": gflop / (ms / steps),
+           "bound": "passes over the saved activations (unfused operators), not arithmetic: DESIGN.md section 13",
            "replicas_in_sync": bool(float(lo.item()) == float(hi.item())),
            "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
            "workload": f"tiny ES training step, {B} utterances per GPU x <= {N} phonemes (ragged), T ~ {data[0][0]['max_mel_len']} frames, "

@@ -58,8 +58,9 @@ int launch_umma_dec256(int mode, int B, int T, int K, int N, const float* X, con
 void umma_dec_set_trace(long long* buf);
 int* umma_err_flag();
 // es_train_gemm.cu: tcgen05 split-16-bit GEMM of the training step; -1 = outside its envelope
-int launch_train_gemm_tc(cudaStream_t s, int slices, int M, int N, int K, const float* A, int lda, int ta, const float* B, int ldb, int tb,
-                         float* C, int ldc, long long sc, const float* bias, int k_chunk, int wide_mask);
+int launch_train_gemm_tc(cudaStream_t s, int slices, int M, int N, int K, const float* A, int lda, long long sa, int ta,
+                         const float* B, int ldb, long long sb, int tb, float* C, int ldc, long long sc, const float* bias, int k_chunk,
+                         int wide_mask);
 
 // tcgen05 row GEMM for the phoneme-side layers (es_umma_enc.cu); -1: outside its envelope
 int launch_umma_rowgemm(const RowGemmParams& p, const void* w_h16, cudaStream_t s);

@@ -38,7 +38,7 @@ struct TcGemmParams {
     const float* A; const float* B; float* C; const float* bias;
     int M, N, K, lda, ldb, ldc, ta, tb;
     int k_chunk;             // > 0: blockIdx.z owns k in [z k_chunk, ...) and writes C + z * sc
-    long long sc;
+    long long sa, sb, sc;    // k_chunk == 0: blockIdx.z is a batch index, operands advance by these strides
     int wide;                // an operand holds gradients: both operands are split as bf16 pairs instead of fp16 pairs
     int ntp;                 // N tile padded to 16
     int* err;
@@ -113,11 +113,15 @@ t_gemm_tc_kernel(const TcGemmParams p) {
     const int m0 = blockIdx.x * GM, n0 = blockIdx.y * p.ntp;
     const int n_end = min(p.N, n0 + p.ntp);
     int k_lo = 0, k_hi = p.K;
-    float* C = p.C;
+    const float* Ap = p.A;
+    const float* Bp = p.B;
+    float* C = p.C + (long long)blockIdx.z * p.sc;
     if (p.k_chunk > 0) {
         k_lo = blockIdx.z * p.k_chunk;
         k_hi = min(p.K, k_lo + p.k_chunk);
-        C += (long long)blockIdx.z * p.sc;
+    } else {
+        Ap += (long long)blockIdx.z * p.sa;
+        Bp += (long long)blockIdx.z * p.sb;
     }
     const uint32_t a_bytes = GM * KC * 2, b_bytes = (uint32_t)p.ntp * KC * 2, stage_bytes = 2 * a_bytes + 2 * b_bytes;
     const uint32_t ncols = p.ntp <= 32 ? 32u : p.ntp <= 64 ? 64u : p.ntp <= 128 ? 128u : 256u;
@@ -132,8 +136,8 @@ t_gemm_tc_kernel(const TcGemmParams p) {
     tc_fence_after_sync();
     const uint32_t tmem = tmem_base_s;
 
-    const bool a_vec = !p.ta && (p.lda & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && (k_lo & 3) == 0;
-    const bool b_vec = p.tb && (p.ldb & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0) && (k_lo & 3) == 0;
+    const bool a_vec = !p.ta && (p.lda & 3) == 0 && ((reinterpret_cast<uintptr_t>(Ap) & 15) == 0) && (k_lo & 3) == 0;
+    const bool b_vec = p.tb && (p.ldb & 3) == 0 && ((reinterpret_cast<uintptr_t>(Bp) & 15) == 0) && (k_lo & 3) == 0;
     // a/b_format: 0 = F16, 1 = BF16 (bits [7,10) and [10,13) of the kind::f16 instruction descriptor)
     const uint32_t idesc = make_idesc_f16(GM, p.ntp) | (p.wide ? ((1u << 7) | (1u << 10)) : 0u);
     const int nkc = (k_hi - k_lo + KC - 1) / KC;
@@ -146,11 +150,11 @@ t_gemm_tc_kernel(const TcGemmParams p) {
         uint8_t* a_hi = st; uint8_t* a_lo = st + a_bytes; uint8_t* b_hi = st + 2 * a_bytes; uint8_t* b_lo = b_hi + b_bytes;
         const int k0 = k_lo + c * KC;
         // op(A)(m, k): stored [m][k] (ta = 0) or [k][m] (ta = 1)
-        if (p.wide) stage_operand<true>(p.A, p.lda, p.ta != 0, m0, p.M, k0, k_hi, GM, a_hi, a_lo, tid, a_vec);
-        else          stage_operand<false>(p.A, p.lda, p.ta != 0, m0, p.M, k0, k_hi, GM, a_hi, a_lo, tid, a_vec);
+        if (p.wide) stage_operand<true>(Ap, p.lda, p.ta != 0, m0, p.M, k0, k_hi, GM, a_hi, a_lo, tid, a_vec);
+        else          stage_operand<false>(Ap, p.lda, p.ta != 0, m0, p.M, k0, k_hi, GM, a_hi, a_lo, tid, a_vec);
         // op(B)(k, n): the canonical tile holds rows n, columns k; stored [n][k] (tb = 1) or [k][n] (tb = 0)
-        if (p.wide) stage_operand<true>(p.B, p.ldb, p.tb == 0, n0, n_end, k0, k_hi, p.ntp, b_hi, b_lo, tid, b_vec);
-        else          stage_operand<false>(p.B, p.ldb, p.tb == 0, n0, n_end, k0, k_hi, p.ntp, b_hi, b_lo, tid, b_vec);
+        if (p.wide) stage_operand<true>(Bp, p.ldb, p.tb == 0, n0, n_end, k0, k_hi, p.ntp, b_hi, b_lo, tid, b_vec);
+        else          stage_operand<false>(Bp, p.ldb, p.tb == 0, n0, n_end, k0, k_hi, p.ntp, b_hi, b_lo, tid, b_vec);
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
@@ -206,15 +210,16 @@ PerDeviceSlot<int> g_tc_enabled_init;      // 0: not read yet, 1: on, 2: off
 }  // namespace
 
 // Returns -1 when the product is outside the kernel's envelope (the caller then uses the SIMT kernel), 0 on launch.
-int launch_train_gemm_tc(cudaStream_t s, int slices, int M, int N, int K, const float* A, int lda, int ta, const float* B, int ldb, int tb,
-                         float* C, int ldc, long long sc, const float* bias, int k_chunk, int wide_mask) {
+int launch_train_gemm_tc(cudaStream_t s, int slices, int M, int N, int K, const float* A, int lda, long long sa, int ta,
+                         const float* B, int ldb, long long sb, int tb, float* C, int ldc, long long sc, const float* bias, int k_chunk,
+                         int wide_mask) {
     if (N < 16 || K < 16 || M < 32) return -1;
     if (k_chunk > 0 && (k_chunk % KC) != 0) return -1;
     int* err_flag = umma_err_flag();
     ES_CHECK(err_flag, "cannot allocate the device error flag");
     TcGemmParams p;
     p.A = A; p.B = B; p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ta = ta; p.tb = tb;
-    p.k_chunk = k_chunk; p.sc = sc; p.wide = wide_mask != 0; p.err = err_flag;
+    p.k_chunk = k_chunk; p.sa = sa; p.sb = sb; p.sc = sc; p.wide = wide_mask != 0; p.err = err_flag;
     const int n_tiles = (N + 255) / 256;
     const int per = (N + n_tiles - 1) / n_tiles;
     p.ntp = (per + 15) / 16 * 16;
@@ -224,7 +229,7 @@ int launch_train_gemm_tc(cudaStream_t s, int slices, int M, int N, int K, const 
         ES_CUDA(cudaFuncSetAttribute(t_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * (2 * GM * KC * 2 + 2 * 256 * KC * 2)));
         attr_set = true;
     }
-    dim3 grid((M + GM - 1) / GM, n_tiles, k_chunk > 0 ? slices : 1);
+    dim3 grid((M + GM - 1) / GM, n_tiles, slices);          // slices: split-K slices (k_chunk > 0) or batch entries
     t_gemm_tc_kernel<<<grid, 128, smem, s>>>(p);
     ES_LAUNCH_OK();
     return 0;

@@ -607,8 +607,9 @@ int es_t_gemm(void* stream, int batch, int M, int N, int K, const float* A, int 
               const float* bias, int accumulate, int k_chunk, int grad_mask) {
     ES_CHECK(A && B && C && batch >= 1 && M >= 1 && N >= 1 && K >= 1 && batch <= 65535 && k_chunk >= 0, "bad arguments");
     ES_CHECK(k_chunk == 0 || (long long)(batch - 1) * k_chunk < K, "split-K: empty slice");
-    if (g_train_tc.load(std::memory_order_relaxed) && !accumulate && (batch == 1 || k_chunk > 0)) {
-        const int rc = launch_train_gemm_tc(ST, batch, M, N, K, A, lda, trans_a, B, ldb, trans_b, C, ldc, stride_c, bias, k_chunk, grad_mask);
+    if (g_train_tc.load(std::memory_order_relaxed) && !accumulate) {
+        const int rc = launch_train_gemm_tc(ST, batch, M, N, K, A, lda, stride_a, trans_a, B, ldb, stride_b, trans_b, C, ldc, stride_c, bias,
+                                            k_chunk, grad_mask);
         if (rc >= 0) return rc;
     }
     dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT, batch);

@@ -477,16 +477,16 @@ class _AttentionCore(Function):
         for h in range(H):
             # dP = dO v^T ; dv = P^T dO
             _gemm(dout, qkv, dattn, N, N, C, H * C, ld, N, tb=True, batch=B, sa=N * H * C, sb=N * ld, sc=H * N * N,
-                  a_off=h * C, b_off=(2 * H + h) * C, c_off=h * N * N)
+                  a_off=h * C, b_off=(2 * H + h) * C, c_off=h * N * N, grad=GRAD_A)
             _gemm(attn, dout, dqkv, N, C, N, N, H * C, ld, ta=True, batch=B, sa=H * N * N, sb=N * H * C, sc=N * ld,
-                  a_off=h * N * N, b_off=h * C, c_off=(2 * H + h) * C)
+                  a_off=h * N * N, b_off=h * C, c_off=(2 * H + h) * C, grad=GRAD_B)
         _launch("es_t_softmax_bwd", dattn, _p(dattn), _p(attn), _p(dattn), B * H * N, N, scale)
         for h in range(H):
             # dq = dS k ; dk = dS^T q
             _gemm(dattn, qkv, dqkv, N, C, N, N, ld, ld, batch=B, sa=H * N * N, sb=N * ld, sc=N * ld,
-                  a_off=h * N * N, b_off=(H + h) * C, c_off=h * C)
+                  a_off=h * N * N, b_off=(H + h) * C, c_off=h * C, grad=GRAD_A)
             _gemm(dattn, qkv, dqkv, N, C, N, N, ld, ld, ta=True, batch=B, sa=H * N * N, sb=N * ld, sc=N * ld,
-                  a_off=h * N * N, b_off=h * C, c_off=(H + h) * C)
+                  a_off=h * N * N, b_off=h * C, c_off=(H + h) * C, grad=GRAD_A)
         return dqkv, None, None, None
 
 
