@@ -814,6 +814,7 @@ def measure_train(ctx, B, N, steps, warmup=3):
     if ctx.world > 1:
         ctx.dist.all_reduce(tot)
     n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    model.check_async_errors(dev)                    # a tcgen05 GEMM that timed out on an mbarrier raises here
     # data-parallel sanity: after the same averaged gradients every rank must hold bit-identical weights
     chk = step.opt.flat.double().sum().reshape(1)
     lo, hi = chk.clone(), chk.clone()

@@ -267,7 +267,9 @@ class TrainStep:
 
     ``forward_train`` -> ``loss`` (which also produces the gradient seeds) -> backward through the tape -> ONE flat
     all-reduce -> ONE AdamW kernel.  Returns the five device scalars (total, mel, pitch, energy, duration); nothing
-    synchronises the host."""
+    synchronises the host.  The tensor-core GEMMs bound every mbarrier wait and raise a device flag instead of hanging;
+    ``Phoneme2Mel.check_async_errors()`` (one stream sync) reads it -- call it wherever the loop synchronises anyway
+    (logging a loss value, an epoch end)."""
 
     def __init__(self, model, lr: float = 1e-3, weight_decay: float = 1e-6, warmup_steps: int = 50, total_steps: int = 5000,
                  use_graphs: bool = False):
