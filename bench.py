@@ -850,7 +850,7 @@ def measure_train(ctx, B, N, steps, warmup=3):
                    "note": "batch copied from pinned host memory inside the timed region, same stream (not overlapped)"},
            "launch_mode": "CUDA-graph replay of forward + loss + backward (one graph per batch geometry); all-reduce and AdamW eager",
            "batch_per_gpu": B, "global_batch": B * ctx.world, "frames_per_step_per_gpu": frames / steps, "params": n_params,
-           "loss_first_warmup_step": float(first[0]), "loss_after": float(last[0]),
+           "loss_first_step": float(first[0]), "loss_after_timed_steps": float(last[0]),
            "grad_allreduce": "one flat NCCL all-reduce of %d fp32 per step" % n_params if ctx.world > 1 else "none (1 GPU)",
            "gflop_per_step_per_gpu": gflop, "achieved_tflops_per_gpu": gflop / (ms / steps),
            "bound": "passes over the saved activations (unfused operators), not arithmetic: DESIGN.md section 13",

@@ -315,7 +315,7 @@ class TrainStep:
     # than running them.  forward + loss + backward are captured once per batch geometry (B, N, T) and replayed; the
     # all-reduce and the AdamW kernel stay outside the graph (the learning rate changes every step and NCCL keeps its own
     # stream semantics).  Callers bucket T (pad the mel target, pass the bucket as x["max_mel_len"]) to bound the number
-    # of graphs; all graphs share one memory pool.
+    # of graphs; all graphs share one memory pool (replays are sequential; outputs are copied out of the pool at once).
     def _graphed(self, x, y):
         if "max_mel_len" not in x:
             raise RuntimeError("TrainStep(use_graphs=True) needs x['max_mel_len'] (python int): a captured step cannot "
@@ -331,8 +331,11 @@ class TrainStep:
                 sx[k].copy_(v, non_blocking=True)
         sy["mel"].copy_(y["mel"], non_blocking=True)
         graph.replay()
+        # the graphs share one memory pool: a temporary of a graph captured EARLIER may live where this graph's output
+        # was allocated later, so the five scalars are copied out before any other graph replays
+        res = torch.stack(out)
         self.optimizer_step()
-        return out
+        return tuple(res.unbind(0))
 
     def _capture(self, x, y):
         dev = x["phoneme"].device

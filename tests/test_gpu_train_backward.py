@@ -320,6 +320,7 @@ def test_graphed_train_step_matches_eager():
     sd = spread_state(vname, 21)
     eager = training.TrainStep(our_model(vname, sd), warmup_steps=2, total_steps=40)
     graphed = training.TrainStep(our_model(vname, sd), warmup_steps=2, total_steps=40, use_graphs=True)
+    kept = []
     for i in range(6):
         batch = make_batch(cfg, B, N, seed=30 + i % 2, ragged=True, fixed_duration=None)
         T = -(-int(batch["mel_len"].max()) // 64) * 64            # bucketed length: padded target, mel_len unchanged
@@ -328,8 +329,13 @@ def test_graphed_train_step_matches_eager():
         y = {"mel": rnd(B, T, cfg.n_mel, seed=400 + i).to(DEV)}
         a = eager(x, y)
         b = graphed(x, y)
+        kept.append((a, b))
         for u, v in zip(a, b):
             assert abs(float(u) - float(v)) <= 1e-4 * max(1.0, abs(float(u))), i
+    # results handed out earlier must survive later replays of OTHER graphs (they share a memory pool)
+    for a, b in kept:
+        for u, v in zip(a, b):
+            assert abs(float(u) - float(v)) <= 1e-4 * max(1.0, abs(float(u)))
     assert len(graphed._graphs) <= 2
     pe, pg = dict(eager.model.named_parameters()), dict(graphed.model.named_parameters())
     for name in pe:
