@@ -371,56 +371,65 @@ variance_scan_kernel(const float* __restrict__ fused, const float* __restrict__ 
                      const float* __restrict__ ebins, const float* __restrict__ etab,
                      float* __restrict__ fused4, int32_t* __restrict__ dur_int, int32_t* __restrict__ dur_cum,
                      int32_t* __restrict__ mel_len, int N, int d) {
-    extern __shared__ int sidx[];                 // [2][N] bucket indices
+    extern __shared__ int sidx[];                 // [2][rows of this block] bucket indices
     __shared__ int warp_tot[8];
     __shared__ int carry_s;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t rb = (size_t)b * N;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    // ---- durations + scan, 256 phonemes per pass
-    for (int n0 = 0; n0 < N; n0 += 256) {
-        const int n = n0 + tid;
-        int dv = 0;
-        if (n < N) {
-            const bool pad = mask && mask[rb + n];
-            float df = dur_tgt ? (float)dur_tgt[rb + n] : rintf(dur_pred[rb + n]);   // torch.round = half-to-even
-            if (pad) df = 0.f;
-            df = fminf(fmaxf(df, 0.f), 65535.f);   // clamp(min=0); upper clamp only guards int overflow
-            dv = (int)df;                           // .int()
-            dur_int[rb + n] = dv;
-            const float pv = pitch_tgt ? pitch_tgt[rb + n] : pitch_pred[rb + n];
-            const float ev = energy_tgt ? energy_tgt[rb + n] : energy_pred[rb + n];
-            sidx[n] = bucketize_left(pbins, d - 1, pv);
-            sidx[N + n] = bucketize_left(ebins, d - 1, ev);
-        }
-        int incl = dv;                              // warp-shuffle inclusive scan
+    // grid.y splits the concat rows of one utterance (64 blocks of 256 threads left most of the GPU idle at B = 64);
+    // the duration scan needs the whole utterance and is done by the y == 0 block alone
+    const int rpc = (N + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * rpc, r1 = min(N, r0 + rpc);
+    if (blockIdx.y == 0) {
+        if (tid == 0) carry_s = 0;
+        __syncthreads();
+        // ---- durations + scan, 256 phonemes per pass
+        for (int n0 = 0; n0 < N; n0 += 256) {
+            const int n = n0 + tid;
+            int dv = 0;
+            if (n < N) {
+                const bool pad = mask && mask[rb + n];
+                float df = dur_tgt ? (float)dur_tgt[rb + n] : rintf(dur_pred[rb + n]);   // torch.round = half-to-even
+                if (pad) df = 0.f;
+                df = fminf(fmaxf(df, 0.f), 65535.f);   // clamp(min=0); upper clamp only guards int overflow
+                dv = (int)df;                           // .int()
+                dur_int[rb + n] = dv;
+            }
+            int incl = dv;                              // warp-shuffle inclusive scan
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (lane == 31) warp_tot[warp] = incl;
+            __syncthreads();
+            int prefix = carry_s;
+            for (int w = 0; w < warp; ++w) prefix += warp_tot[w];
+            if (n < N) dur_cum[rb + n] = prefix + incl;
+            __syncthreads();
+            if (tid == 255) carry_s = prefix + incl;
+            __syncthreads();
         }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        int prefix = carry_s;
-        for (int w = 0; w < warp; ++w) prefix += warp_tot[w];
-        if (n < N) dur_cum[rb + n] = prefix + incl;
-        __syncthreads();
-        if (tid == 255) carry_s = prefix + incl;
-        __syncthreads();
+        if (tid == 0) mel_len[b] = carry_s;
     }
-    if (tid == 0) mel_len[b] = carry_s;
+    // ---- bucket indices of this block's rows
+    for (int n = r0 + tid; n < r1; n += 256) {
+        const float pv = pitch_tgt ? pitch_tgt[rb + n] : pitch_pred[rb + n];
+        const float ev = energy_tgt ? energy_tgt[rb + n] : energy_pred[rb + n];
+        sidx[n - r0] = bucketize_left(pbins, d - 1, pv);
+        sidx[rpc + n - r0] = bucketize_left(ebins, d - 1, ev);
+    }
+    __syncthreads();
     // ---- concat rows: 4 channels (one float4) per thread step; group boundaries are multiples of d (>= 32)
     const int d4 = 4 * d, q4 = d4 >> 2;
-    for (int idx = tid; idx < N * q4; idx += 256) {
-        const int n = idx / q4, c = (idx - n * q4) * 4;
+    for (int idx = tid; idx < (r1 - r0) * q4; idx += 256) {
+        const int nl = idx / q4, n = r0 + nl, c = (idx - nl * q4) * 4;
         const bool pad = mask && mask[rb + n];
         const int grp = c / d, cc = c - grp * d;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (grp == 0) v = *reinterpret_cast<const float4*>(fused + (rb + n) * d + cc);        // already masked by the fuse stage
         else if (!pad) {
-            if (grp == 1) v = __ldg(reinterpret_cast<const float4*>(ptab + (size_t)sidx[n] * d + cc));
-            else if (grp == 2) v = __ldg(reinterpret_cast<const float4*>(etab + (size_t)sidx[N + n] * d + cc));
+            if (grp == 1) v = __ldg(reinterpret_cast<const float4*>(ptab + (size_t)sidx[nl] * d + cc));
+            else if (grp == 2) v = __ldg(reinterpret_cast<const float4*>(etab + (size_t)sidx[rpc + nl] * d + cc));
             else v = *reinterpret_cast<const float4*>(dur_feat + (rb + n) * d + cc);
         }
         *reinterpret_cast<float4*>(fused4 + (rb + n) * d4 + c) = v;
@@ -433,9 +442,13 @@ int launch_variance_scan(const float* fused, const float* dur_feat, const float*
                          const es_predictor_w_t& pw, const es_predictor_w_t& ew, float* fused4,
                          int32_t* dur_int, int32_t* dur_cum, int32_t* mel_len, int B, int N, int d,
                          cudaStream_t s) {
-    const size_t smem = (size_t)2 * N * sizeof(int);
+    // enough row chunks to put ~4 blocks on every SM at this batch size, at least 8 rows each
+    int chunks = (4 * 148 + B - 1) / B;
+    chunks = chunks < 1 ? 1 : (chunks > (N + 7) / 8 ? (N + 7) / 8 : chunks);
+    const int rpc = (N + chunks - 1) / chunks;
+    const size_t smem = (size_t)2 * rpc * sizeof(int);
     ES_CHECK(smem <= 40 * 1024, "phoneme sequence too long");
-    variance_scan_kernel<<<B, 256, smem, s>>>(fused, dur_feat, pitch_pred, energy_pred, dur_pred, pitch_tgt,
+    variance_scan_kernel<<<dim3(B, chunks), 256, smem, s>>>(fused, dur_feat, pitch_pred, energy_pred, dur_pred, pitch_tgt,
                                               energy_tgt, dur_tgt, mask, pw.bins, pw.table, ew.bins, ew.table,
                                               fused4, dur_int, dur_cum, mel_len, N, d);
     ES_LAUNCH_OK();
