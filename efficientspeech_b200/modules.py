@@ -505,6 +505,11 @@ class Phoneme2Mel(nn.Module):
         # train=True returns the reference's dict, which includes the expanded "features" /
         # "masks"; set False to skip materialising them (nothing on the mel path reads them).
         self.return_features = True
+        # model.py:156 calls phoneme2mel(x, train=True) from the Lightning training loop and differentiates the result.
+        # The fused inference kernels keep no tape, so in that situation -- module in train() mode, train=True, autograd
+        # enabled -- forward() goes through training.forward_train: the same parameters, the reference's dict, every
+        # operator and adjoint a kernel of this library.  eval() / torch.no_grad() callers keep the fused path.
+        self.autograd_when_training = True
 
     def set_tensor_core(self, enable: bool) -> None:
         """True (default): tcgen05 kernels wherever a layer is inside their envelope; False: fp32 SIMT only."""
@@ -532,6 +537,9 @@ class Phoneme2Mel(nn.Module):
     def forward(self, x, train=False):
         if isinstance(x, list):                                         # networks.py:418
             x = x[0]
+        if train and self.training and self.autograd_when_training and torch.is_grad_enabled():
+            from . import training
+            return training.forward_train(self, x)
         pred = self.encoder._core(x, train)
         T = pred["_T"]
         if T <= 0:

@@ -171,7 +171,7 @@ def _acoustic_decoder(dec, fused):
 
 def forward_train(model, x: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """``Phoneme2Mel.forward(x, train=True)`` with a tape: returns the reference's dict (``mel`` [B,T,80], ``pitch`` /
-    ``energy`` / ``duration`` [B,N,1], ``mel_len`` [B] int32, ``features`` [B,T,4d], ``masks`` [B,T] bool or None).
+    ``energy`` / ``duration`` [B,N,1], ``mel_len`` [B] int32, ``features`` [B,T,4d], ``masks`` [B,T,4d] bool or None).
     ``model`` is this package's ``Phoneme2Mel`` (its parameters are the leaves).  ``x["max_mel_len"]`` (python int)
     spares the one host sync of networks.py:344."""
     pe, md = model.encoder, model.decoder
@@ -257,8 +257,10 @@ def forward_train(model, x: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     mel = ops.linear(skip, md.mel_linear.weight, md.mel_linear.bias)
     if frame_mask is not None and gB > 1:
         mel = ops.mask_rows(mel, frame_mask)                                                   # networks.py:424-427
+    # the reference returns the [B,T,4d] bool tensor; the same values as a broadcast view (None for a single utterance)
+    masks = None if frame_mask is None else frame_mask.unsqueeze(-1).expand(B, T, fused4.shape[-1])
     return {"pitch": pitch_pred, "energy": energy_pred, "duration": dur_pred, "mel_len": mel_len_pred, "features": features,
-            "masks": frame_mask, "mel": mel}
+            "masks": masks, "mel": mel}
 
 
 class TrainStep:

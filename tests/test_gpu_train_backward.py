@@ -340,3 +340,42 @@ def test_graphed_train_step_matches_eager():
     pe, pg = dict(eager.model.named_parameters()), dict(graphed.model.named_parameters())
     for name in pe:
         assert float((pe[name] - pg[name]).abs().max()) <= 1e-4, name
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not staged (oracle/build_ref.py)")
+def test_module_forward_is_differentiable_in_train_mode():
+    """The Lightning loop as upstream writes it (model.py:155-156, 211-217, 279-283): phoneme2mel(x, train=True) on a module
+    in train() mode, the reference's OWN loss source applied to the result with torch ops, loss.backward(), a stock
+    torch.optim.AdamW over model.parameters().  Gradients must match the reference run end to end; in eval() / no_grad
+    the same call must take the fused inference path (no tape)."""
+    vname, B, N, seed = "tiny", 3, 29, 8
+    cfg = VARIANTS[vname]
+    sd = spread_state(vname, seed)
+    batch = make_batch(cfg, B, N, seed=seed, ragged=True, fixed_duration=None)
+    T = int(batch["mel_len"].max())
+    mel_t = rnd(B, T, cfg.n_mel, seed=77)
+    _, ref_total, ref_grads, _, ref_pred = reference_step(vname, sd, batch, mel_t)
+
+    m = our_model(vname, sd).train()
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-6)
+    x = dev_batch(batch)
+    x["mel_mask"] = mel_mask_of(batch, T).to(DEV)
+    y_hat = m(x, train=True)
+    assert y_hat["mel"].requires_grad and y_hat["duration"].requires_grad
+    assert torch.equal(y_hat["masks"].cpu(), ref_pred["masks"])
+    ls = reference_loss_fn()(None, y_hat, {"mel": mel_t.to(DEV)}, x)
+    total = 10. * ls[0] + 2. * ls[1] + 2. * ls[2] + ls[3]
+    assert abs(float(total.detach()) - float(ref_total.detach())) <= 1e-4 * abs(float(ref_total.detach()))
+    opt.zero_grad()
+    total.backward()
+    for name, p in m.named_parameters():
+        want = ref_grads[name]
+        if want is None:
+            assert p.grad is None, name
+        else:
+            close(p.grad, want, TOL_GRAD, name)
+    opt.step()                                        # torch's optimiser on our parameters: nothing special needed
+    m.eval()
+    with torch.no_grad():
+        out = m(x, train=True)
+    assert not out["mel"].requires_grad and "_fused4" in out           # the fused inference path
