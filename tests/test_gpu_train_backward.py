@@ -339,7 +339,7 @@ def test_graphed_train_step_matches_eager():
     assert len(graphed._graphs) <= 2
     pe, pg = dict(eager.model.named_parameters()), dict(graphed.model.named_parameters())
     for name in pe:
-        assert float((pe[name] - pg[name]).abs().max()) <= 1e-4, name
+        assert float((pe[name] - pg[name]).detach().abs().max()) <= 1e-4, name
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference sources not staged (oracle/build_ref.py)")
