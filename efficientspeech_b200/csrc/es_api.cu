@@ -571,7 +571,7 @@ int es_decoder_forward_gathered(es_model_t* m, void* stream, int B, int N, int T
                               m->dx2, db.P + (size_t)R * m->dx2, s, ragged ? db.tiles : nullptr, db.tile_count,
                               tile_frames, halo, mel, m->cfg.n_mel)) return 1; }
     int rc;
-    if (m->gather_mode == ES_GATHER_FUSED && decoder_all_umma128(m)) {
+    if (m->gather_mode == ES_GATHER_FUSED && (decoder_all_umma128(m) || decoder_all_umma256(m))) {
         // the first block reads its input and skip rows straight from the table: [B,T,dx2] is never materialised
         rc = decoder_layers(m, B, T, db, -1, zero_padded_frames ? mel_len : nullptr, mel, s, ragged);
     } else {
@@ -633,8 +633,10 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
             const bool last = (l == m->cfg.block_depth - 1);
             const bool gx = in_idx < 0, gs = last && s_idx < 0;
             if (gx || gs)
-                ES_CHECK(db.P && db.src && w.pw_w_h16 && umma_dec_supported(C, m->cfg.decoder_kernel_size, C),
-                         "virtual skip needs the 128-channel tcgen05 layer kernel");
+                ES_CHECK(db.P && db.src && w.pw_w_h16 && m->use_tensor_core &&
+                             (umma_dec_supported(C, m->cfg.decoder_kernel_size, C) ||
+                              (C == 256 && umma_dec256_supported(C, m->cfg.decoder_kernel_size, C, 0))),
+                         "virtual skip needs a tcgen05 layer kernel");
             if (m->use_tensor_core && w.pw_w_h16 && umma_dec_supported(C, m->cfg.decoder_kernel_size, C)) {
                 // 128-channel decoders: one fused tcgen05 kernel per layer; in the first block of the gathered entry the
                 // input and / or skip rows come from the projection table through the frame -> row map
@@ -656,10 +658,20 @@ int decoder_layers(const es_model* m, int B, int T, DecBufs& db, int s_idx, cons
             }
             if (m->use_tensor_core && w.pw_w_h16 && C == 256 && umma_dec256_supported(C, m->cfg.decoder_kernel_size, C, 0)) {
                 ProfRange r(ES_K_DEC_LAYER, s);
-                if (launch_umma_dec256(0, B, T, C, C, db.buf[in_idx], w.dw_w, w.dw_b, w.pw_w_h16,
-                                       w.pw_b, 1, w.ln_g, w.ln_b, last ? db.buf[s_idx] : nullptr,
-                                       last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
-                                       nullptr, db.buf[out_idx], s, tl, tc)) return 1;
+                int rc;
+                if (gx || gs) {
+                    const float* xin = gx ? db.P : db.buf[in_idx];
+                    const float* skip = last ? (s_idx < 0 ? db.P : db.buf[s_idx]) : nullptr;
+                    rc = launch_umma_dec256_gathered(B, T, xin, w.dw_w, w.dw_b, w.pw_w_h16, w.pw_b, w.ln_g, w.ln_b, skip,
+                                                     last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
+                                                     db.src, gx, gs, db.buf[out_idx], s, tl, tc);
+                } else {
+                    rc = launch_umma_dec256(0, B, T, C, C, db.buf[in_idx], w.dw_w, w.dw_b, w.pw_w_h16,
+                                            w.pw_b, 1, w.ln_g, w.ln_b, last ? db.buf[s_idx] : nullptr,
+                                            last ? m->w.blk_ln_g[blk] : nullptr, last ? m->w.blk_ln_b[blk] : nullptr,
+                                            nullptr, db.buf[out_idx], s, tl, tc);
+                }
+                if (rc) return 1;
                 in_idx = out_idx;
                 continue;
             }

@@ -55,6 +55,10 @@ int launch_umma_dec256(int mode, int B, int T, int K, int N, const float* X, con
                        const float* bias, int act_tanh, const float* ln_g, const float* ln_b,
                        const float* res2, const float* ln2_g, const float* ln2_b, const int* zero_from,
                        float* Y, cudaStream_t s, const int2* tile_list = nullptr, const int* tile_count = nullptr);
+int launch_umma_dec256_gathered(int B, int T, const float* X, const float* dw_w, const float* dw_b, const void* w_chunks,
+                                const float* bias, const float* ln_g, const float* ln_b,
+                                const float* res2, const float* ln2_g, const float* ln2_b, const int* src, bool gx, bool gs,
+                                float* Y, cudaStream_t s, const int2* tile_list = nullptr, const int* tile_count = nullptr);
 void umma_dec_set_trace(long long* buf);
 int* umma_err_flag();
 // es_train_gemm.cu: tcgen05 split-16-bit GEMM of the training step; -1 = outside its envelope

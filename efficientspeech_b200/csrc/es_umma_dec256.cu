@@ -84,6 +84,7 @@ struct Dec256Params {
     int* err;
     const int2* tile_list;       // ragged scheduling (es_gather.cu): (b, t0) of the tiles that can reach a valid frame, or null
     const int* tile_count;
+    const int* src;              // GX / GS kernels: frame -> table row map [B*T] (es_gather.cu); X / res2 is the projection table
 };
 
 constexpr float kTanhScale2 = 2.8853900817779268f;
@@ -126,7 +127,10 @@ __device__ __forceinline__ void norm_frag(uint32_t (&r)[32], const float* g, con
     }
 }
 
-template <int MODE, int N>
+// GX: the input rows, GS: the skip rows of a block-end layer are rows p.src[b*T + t] of a table instead of rows
+// b*T + t of a [B,T,256] tensor -- the length regulator fused into the first decoder block,
+// separate instantiations because the dense kernel sits at its register limit.
+template <int MODE, int N, bool GX = false, bool GS = false>
 __global__ void __launch_bounds__(NTHR, 1)
 umma_dec256_kernel(const Dec256Params p) {
     constexpr int HALO = (MODE == MODE_DWCONV) ? DWK / 2 : 0;
@@ -271,6 +275,7 @@ umma_dec256_kernel(const Dec256Params p) {
         const int q = ptid & 7, rg = ptid >> 3;              // conv: channel quad of the chunk, 8-row group
         const int xrow = ptid >> 3;                           // loads: rows xrow + 16*it, 16-byte piece q
         const uint32_t x_smem = smem_u32(smem + OFF_X);
+        int* rows_s = reinterpret_cast<int*>(smem + OFF_SRC);   // GX: table row of every tile row (XROWS <= 144 ints)
 
         // ---- load stream (runs three chunks ahead of the conv stream) ---------------------------
         int ld_i = 0, ld_c = 0, ld_s = 0;                     // tile, chunk, x stage of the next chunk to load
@@ -283,11 +288,18 @@ umma_dec256_kernel(const Dec256Params p) {
                 const int tf = t0 - HALO + xrow;
                 ld_base = p.X + ((long long)b * p.T + tf) * K + q * 4;
                 ld_mask = 0;
+                // GX: the table rows of this thread's tile rows go to shared memory (the 8 threads of a row group are
+                // neighbouring lanes and write the same values; the previous tile's loads have all been issued)
+                if (GX) __syncwarp();
 #pragma unroll
                 for (int it = 0; it < XITER; ++it) {
                     const int t = tf + 16 * it;
-                    if (t >= 0 && t < p.T && xrow + 16 * it < XROWS) ld_mask |= 1u << it;
+                    if (t >= 0 && t < p.T && xrow + 16 * it < XROWS) {
+                        ld_mask |= 1u << it;
+                        if (GX) rows_s[xrow + 16 * it] = __ldg(p.src + (size_t)b * p.T + t);
+                    }
                 }
+                if (GX) __syncwarp();
             }
         };
         auto load_next = [&]() {
@@ -298,7 +310,8 @@ umma_dec256_kernel(const Dec256Params p) {
                     const float* src;
                     bool ok;
                     ok = (ld_mask >> it) & 1u;
-                    src = ok ? ld_base + (size_t)(16 * it) * K + ld_c * KC : p.X;
+                    if (GX) src = ok ? p.X + (size_t)rows_s[xrow + 16 * it] * K + q * 4 + ld_c * KC : p.X;
+                    else    src = ok ? ld_base + (size_t)(16 * it) * K + ld_c * KC : p.X;
                     cp_async16(dst + (uint32_t)it * (16u * KC * 4u), src, ok ? 16u : 0u);
                 }
             }
@@ -390,7 +403,8 @@ umma_dec256_kernel(const Dec256Params p) {
             if (p.res2) {   // pull this warp's 16 skip rows (16 KB) towards L2 while the GEMM runs
                 const int pr = rbase + (lane >> 1);
                 if (pr < rows_valid) {
-                    const float* sp = p.res2 + ((size_t)b * p.T + t0 + pr) * N + (lane & 1) * 128;
+                    const size_t srow = GS ? (size_t)__ldg(p.src + (size_t)b * p.T + t0 + pr) : (size_t)b * p.T + t0 + pr;
+                    const float* sp = p.res2 + srow * N + (lane & 1) * 128;
                     prefetch_l2(sp); prefetch_l2(sp + 32); prefetch_l2(sp + 64); prefetch_l2(sp + 96);
                 }
             }
@@ -469,6 +483,10 @@ umma_dec256_kernel(const Dec256Params p) {
                     s0 = q0 = s1 = q1 = 0.f;
                     const float* sp0 = p.res2 + ((size_t)b * p.T + t0 + row0) * N + 2 * t4;
                     const float* sp1 = sp0 + 8 * N;
+                    if (GS) {
+                        sp0 = p.res2 + (size_t)(ok0 ? __ldg(p.src + (size_t)b * p.T + t0 + row0) : 0) * N + 2 * t4;
+                        sp1 = p.res2 + (size_t)(ok1 ? __ldg(p.src + (size_t)b * p.T + t0 + row1) : 0) * N + 2 * t4;
+                    }
 #pragma unroll
                     for (int h = 0; h < NH; ++h) {
                         uint32_t r[32];
@@ -523,14 +541,14 @@ umma_dec256_kernel(const Dec256Params p) {
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int MODE, int N>
+template <int MODE, int N, bool GX = false, bool GS = false>
 int launch_mode256(const Dec256Params& p, int grid, cudaStream_t s) {
     static PerDeviceSlot<bool> attr_once; bool& attr_set = attr_once.get();   // function attributes are per device
     if (!attr_set) {
-        ES_CUDA(cudaFuncSetAttribute(umma_dec256_kernel<MODE, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        ES_CUDA(cudaFuncSetAttribute(umma_dec256_kernel<MODE, N, GX, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    ES_CUDA(launch_pdl(umma_dec256_kernel<MODE, N>, grid, NTHR, SMEM_BYTES, s, p));
+    ES_CUDA(launch_pdl(umma_dec256_kernel<MODE, N, GX, GS>, grid, NTHR, SMEM_BYTES, s, p));
     ES_LAUNCH_OK();
     return 0;
 }
@@ -566,7 +584,7 @@ int launch_umma_dec256(int mode, int B, int T, int K, int N, const float* X, con
     p.B = B; p.T = T; p.K = K; p.X = X;
     p.dw_w = dw_w; p.dw_b = dw_b; p.w_chunks = w_chunks; p.bias = bias; p.act_tanh = act_tanh;
     p.ln_g = ln_g; p.ln_b = ln_b; p.res2 = res2; p.ln2_g = ln2_g; p.ln2_b = ln2_b;
-    p.zero_from = zero_from; p.Y = Y; p.err = err_flag; p.tile_list = tile_list; p.tile_count = tile_count;
+    p.zero_from = zero_from; p.Y = Y; p.err = err_flag; p.tile_list = tile_list; p.tile_count = tile_count; p.src = nullptr;
     const int n_tiles = B * ((T + TM2 - 1) / TM2);
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
     switch (mode) {
@@ -575,6 +593,35 @@ int launch_umma_dec256(int mode, int B, int T, int K, int N, const float* X, con
             if (N == 256) return launch_mode256<MODE_PLAIN, 256>(p, grid, s);
             return launch_mode256<MODE_PLAIN, 80>(p, grid, s);
     }
+}
+
+// Depthwise layer of the FIRST decoder block with the length regulator fused in: gx -- the input rows, gs -- the skip
+// rows (block-end layer) are rows src[b*T + t] of the projection table X / res2 (es_umma_dec.cu has the same pair).
+int launch_umma_dec256_gathered(int B, int T, const float* X, const float* dw_w, const float* dw_b, const void* w_chunks,
+                                const float* bias, const float* ln_g, const float* ln_b,
+                                const float* res2, const float* ln2_g, const float* ln2_b, const int* src, bool gx, bool gs,
+                                float* Y, cudaStream_t s, const int2* tile_list, const int* tile_count) {
+    ES_CHECK(w_chunks && X && Y && bias && ln_g && src, "null tensor");
+    ES_CHECK(gx || gs, "nothing to gather");
+    ES_CHECK(!gs || res2, "the gathered skip needs the table");
+    int* err_flag = umma_err_flag();
+    ES_CHECK(err_flag, "cannot allocate the device error flag");
+    static PerDeviceSlot<int> n_sm_once; int& n_sm = n_sm_once.get();
+    if (!n_sm) {
+        int dev = 0;
+        ES_CUDA(cudaGetDevice(&dev));
+        ES_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    Dec256Params p;
+    p.B = B; p.T = T; p.K = 256; p.X = X;
+    p.dw_w = dw_w; p.dw_b = dw_b; p.w_chunks = w_chunks; p.bias = bias; p.act_tanh = 1;
+    p.ln_g = ln_g; p.ln_b = ln_b; p.res2 = res2; p.ln2_g = ln2_g; p.ln2_b = ln2_b;
+    p.zero_from = nullptr; p.Y = Y; p.err = err_flag; p.tile_list = tile_list; p.tile_count = tile_count; p.src = src;
+    const int n_tiles = B * ((T + TM2 - 1) / TM2);
+    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    if (gx && gs) return launch_mode256<MODE_DWCONV, 256, true, true>(p, grid, s);
+    if (gx) return launch_mode256<MODE_DWCONV, 256, true, false>(p, grid, s);
+    return launch_mode256<MODE_DWCONV, 256, false, true>(p, grid, s);
 }
 
 }  // namespace es
