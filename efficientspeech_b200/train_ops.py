@@ -78,7 +78,9 @@ def _atb(a: torch.Tensor, b: torch.Tensor, grad: int = 0) -> torch.Tensor:
     """a^T b for a [rows, M], b [rows, N] with rows >> M, N (a weight gradient): split-K partials, summed in order."""
     rows, M = a.shape
     N = b.shape[1]
-    chunk = max(256, -(-rows // 296))
+    # ~2 slices per SM; short slices matter for the phoneme-side layers (16 k rows): with 256-row slices their 64 CTAs each
+    # walked 8 dependent K steps (55 us per product, ncu launch list), with 64-row slices 256 CTAs walk 2
+    chunk = max(64, -(-rows // 296))
     chunk = -(-chunk // 32) * 32                      # the tensor-core kernel streams K in chunks of 32
     splits = -(-rows // chunk)
     if splits == 1:
